@@ -1,0 +1,305 @@
+#!/usr/bin/env python3
+"""bench.py -- audio frames/s per train step (comp_4c), BASELINE.json's metric.
+
+  python bench.py --gpus N --steps K --warmup W           # this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N ...           # the reference's algorithm on the host CPU (oracle port)
+
+A "step" is one full iteration of the reference's loop body (train.py:112-151): forward, log-cosh/L1 loss,
+backward, L1 clip, Adam, on one batch of synthetic comp_4c windows.  1 audio frame = 1 input PCM sample consumed
+(B * chunk per step).  Workload at N=1: BASELINE.json configs[1] (chunk 8192, batch 200,
+fp32); at N>1 each rank gets its own batch of 200 windows (weak scaling) and gradients are allreduced over NCCL.
+
+Timing: W warm-up steps, then K steps bracketed by barrier + cuda synchronize, CUDA events on the launching
+stream, max over ranks.  Every step reads a different slice of a window pool larger than L2 (config.l2: "pool").
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHUNK_SCALE, SHRINK, KNOBS, SR = 1, 4, 4, 44100
+METRIC = "audio frames/sec per train step (comp_4c)"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=float(p["hbm_gbs"]), bf16=float(p["bf16_tflops"]), bf16_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def stage_work(d, B):
+    """Algorithmic FLOPs / bytes per launch of each stage, SURVEY.md section 8(d) (fp32 words)."""
+    BTF, BOF, W = B * d.T * d.F, B * d.OT * d.F, 2 * d.F * d.N
+    ae_mac = sum(o * i for o, i in zip([64, 32, 16, 16, 16, 16, 32, 64, d.OT], [d.T, 64, 32, 16, 16 + d.K, 16, 16, 32, 64]))
+    p_ae = 2 * (ae_mac + 64 + 32 + 16 * 4 + 32 + 64 + d.OT)
+    p_live = 2 * d.F * d.N + 2 * d.N * d.N + p_ae
+    return {
+        "gemm_analysis": dict(bound="tensor", flops=4 * d.T * d.F * d.N * B, bytes=4 * (B * d.C + W + 2 * BTF)),
+        "ae_forward": dict(bound="hbm", flops=4 * d.F * ae_mac * B, bytes=4 * (2 * BTF + BTF + 2 * BOF + 2 * BOF + B * d.K + p_ae)),
+        "gemm_synthesis": dict(bound="tensor", flops=4 * d.OT * d.F * d.N * B, bytes=4 * (2 * BOF + W + B * d.OT * d.N)),
+        "gemm_synthesis_dgrad": dict(bound="tensor", flops=4 * d.OT * d.F * d.N * B, bytes=4 * (B * d.L + 2 * BOF + W)),
+        "gemm_synthesis_wgrad": dict(bound="tensor", flops=4 * d.OT * d.F * d.N * B, bytes=4 * (B * d.L + 2 * BOF + W)),
+        "ae_backward": dict(bound="hbm", flops=12 * d.F * ae_mac * B, bytes=4 * (4 * BOF + 4 * BTF + 2 * p_ae)),
+        "gemm_analysis_wgrad": dict(bound="tensor", flops=4 * d.T * d.F * d.N * B, bytes=4 * (B * d.C + 2 * BTF + W)),
+        "adam": dict(bound="hbm", flops=12 * p_live, bytes=7 * 4 * p_live),
+        "pack_weights": dict(bound="hbm", flops=0, bytes=4 * (4 * d.N * d.N * 3 // 4 + 2 * W)),
+        "finalize_dft_grads": dict(bound="hbm", flops=0, bytes=4 * (2 * W + 4 * d.N * d.N)),
+        "l1_norm": dict(bound="hbm", flops=0, bytes=4 * 4 * d.N * d.N),
+        "overlap_add": dict(bound="hbm", flops=0, bytes=4 * (B * d.OT * d.N + 2 * B * d.L)),
+        "loss": dict(bound="hbm", flops=0, bytes=4 * (3 * B * d.L + 2 * BOF)),
+    }
+
+
+class ClockSampler:
+    """nvidia-smi sampled during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_step_rate(B, steps, warmup, threads):
+    """The reference's algorithm (oracle port, float32) on the host cores: frames/s and ms/step."""
+    from oracle import st_oracle as O
+    from signaltrain_b200 import data
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        threadpool_limits = None
+    d = O.model_dims(CHUNK_SCALE, SHRINK, KNOBS)
+    x, y, k = data.make_pool(B, d.C, d.L, data.Compressor_4c(), SR, seed=218)
+    lr_sched, _ = O.get_1cycle_schedule(1e-4, 200000, 1000, 200)
+    tr = O.Trainer(d, O.init_params(d, seed=218), lr_sched, dtype=np.float32)
+    ctx = threadpool_limits(limits=threads) if threadpool_limits else None
+    for _ in range(warmup):
+        tr.step(x, y, k)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(x, y, k)
+    dt = time.perf_counter() - t0
+    if ctx is not None:
+        ctx.unregister() if hasattr(ctx, "unregister") else None
+    return B * d.C * steps / dt, 1e3 * dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B = args.batch
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    fps, ms = cpu_reference_step_rate(B, steps, warm, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"comp_4c synthetic, chunk=8192, batch={B}, fp32 (BASELINE configs[1])", "where": "host CPU"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": f"{steps} full train steps of B={B} windows (oracle/st_oracle.py Trainer, float32, "
+                                       f"numpy/BLAS on {threads} threads)"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import signaltrain_b200 as st
+    from signaltrain_b200 import data
+    from signaltrain_b200.train import FusedTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the measured path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = args.batch, args.steps, max(3, args.warmup)
+
+    torch.manual_seed(218)
+    model = st.nn_proc.st_model(scale_factor=CHUNK_SCALE, shrink_factor=SHRINK, num_knobs=KNOBS, sr=SR).to(dev)
+    C, L = model.in_chunk_size, model.out_chunk_size
+    lr_sched, _ = st.learningrate.get_1cycle_schedule(lr_max=1e-4, n_data_points=200000, epochs=1000, batch_size=200)
+    trainer = FusedTrainer(model, lr_sched)
+
+    # window pool larger than L2 (126 MB): P windows * (C + L + K) * 4 B
+    nbatch = max(4, -(-int(168e6) // (B * (C + L + KNOBS) * 4)))
+    P = nbatch * B
+    xh, yh, kh = data.make_pool(P, C, L, data.Compressor_4c(), SR, seed=218 + rank)
+    xp, yp, kp = (torch.from_numpy(a).pin_memory() for a in (xh, yh, kh))
+    xd, yd, kd = xp.to(dev), yp.to(dev), kp.to(dev)
+
+    def batch_of(i, src):
+        s = (i % nbatch) * B
+        return src[0][s:s + B], src[1][s:s + B], src[2][s:s + B]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    it = 0
+    for _ in range(Wm):
+        trainer.step(*batch_of(it, (xd, yd, kd)))
+        it += 1
+    eng = trainer.eng
+    # ---- timed region: K steps, device-resident inputs ------------------------------------------------------
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = trainer.step(*batch_of(it, (xd, yd, kd)))
+        it += 1
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0 + (K if world > 1 else 0)
+    clk = clocks.stop() if rank == 0 else None
+    final_loss = float(loss.item())
+    # ---- end-to-end: host (pinned) inputs, H2D copies and a D2H loss read inside the timed region ------------
+    xs, ys, ks = (torch.empty((B,) + tuple(a.shape[1:]), device=dev) for a in (xp, yp, kp))
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    Ke = K
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        bx, by, bk = batch_of(it, (xp, yp, kp))
+        xs.copy_(bx, non_blocking=True)
+        ys.copy_(by, non_blocking=True)
+        ks.copy_(bk, non_blocking=True)
+        l = trainer.step(xs, ys, ks)
+        loss_host.copy_(l, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller reads the loss every step
+        it += 1
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = B * (C + L + KNOBS) * 4
+    # ---- per-stage device time (separate pass: the event pairs perturb the pipeline slightly) ---------------
+    stages = {}
+    if rank == 0:
+        eng.profile(True)
+        eng.profile_read()
+        for _ in range(max(3, min(K, 10))):
+            trainer.step(*batch_of(it, (xd, yd, kd)))
+            it += 1
+        stages = {k: (ms / max(c, 1), c) for k, (ms, c) in eng.profile_read().items() if c}
+        eng.profile(False)
+    # ---- max over ranks ---------------------------------------------------------------------------------------
+    t = torch.tensor([ms_total, e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    from oracle import st_oracle as O
+    d = O.model_dims(CHUNK_SCALE, SHRINK, KNOBS)
+    peaks = measured_peaks()
+    work = stage_work(d, B)
+    step_sum = sum(v[0] for v in stages.values())
+    top = max((k for k in stages if k in work), key=lambda k: stages[k][0])
+    w = work[top]
+    dur_s = stages[top][0] * 1e-3
+    if w["bound"] == "tensor":
+        achieved, peak, unit = w["flops"] / dur_s / 1e12, peaks["bf16_sustained"], "TFLOP/s"
+    else:
+        achieved, peak, unit = w["bytes"] / dur_s / 1e9, peaks["hbm"], "GB/s"
+    roofline = {"kernel": top, "bound": w["bound"], "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                "traffic": None, "peak_source": peaks["src"], "kernel_ms": stages[top][0],
+                "share_of_step": stages[top][0] / step_sum if step_sum else None,
+                "algorithmic_bytes": w["bytes"], "algorithmic_flops": w["flops"],
+                "stages_ms": {k: round(v[0], 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])}}
+    # CPU baseline: the oracle port on this box's host cores, bounded sample
+    cores = os.cpu_count() or 1
+    cpu_fps, cpu_ms = (None, None)
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_fps, cpu_ms = cpu_reference_step_rate(B, 3, 1, cores)
+    frames = world * B * C
+    line = {"metric": METRIC, "value": frames * K / (ms_total * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"comp_4c synthetic, chunk={C}, batch={B} per GPU, fp32, {world}xB200 (BASELINE configs[1])",
+                       "global_batch": world * B, "windows_per_s": world * B * K / (ms_total * 1e-3),
+                       "stft_frames_per_s": world * B * d.T * K / (ms_total * 1e-3),
+                       "l2": f"pool: each step reads a different batch of a {P}-window ({P * (C + L + KNOBS) * 4 / 1e6:.0f} MB) pool",
+                       "parallelism": f"dp{world}", "final_loss": final_loss},
+            "e2e": {"value": frames * Ke / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": 1e3 * e2e_s / Ke,
+                    "api": "signaltrain_b200.train.FusedTrainer.step (st_train_step) on pinned host batches, loss read back"},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
+    if cpu_fps is not None:
+        line["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port", "ms_per_step": cpu_ms,
+                                "sample": f"3 full train steps of B={B} windows by oracle/st_oracle.py (float32 numpy/BLAS, {cores} threads)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=200)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

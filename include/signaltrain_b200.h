@@ -1,0 +1,132 @@
+/*
+ * signaltrain_b200.h -- C ABI of the B200-native SignalTrain train-step library.
+ *
+ * The reference has no FFI for this path: its boundary is a Python class API.
+ * Each entry point below replaces the reference call named beside it; the Python mirror in
+ * signaltrain_b200/ binds them with ctypes (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; st_last_error() gives the message.
+ *     Nothing throws across the ABI.
+ *   - all pointers are DEVICE pointers to float32 unless the name ends in _host.  Buffers are
+ *     borrowed for the duration of the call (asynchronous on `stream`); no ownership moves.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - one handle per device; a handle is not thread-safe (the reference drives the device from a
+ *     single host thread, signaltrain/train.py:104-151).
+ *   - `params`, `grads`, `exp_avg`, `exp_avg_sq` are host arrays of ST_NUM_PARAMS device pointers in
+ *     the reference's state_dict order (st_param_name / st_param_numel describe each slot):
+ *       0..3   mpaec.dft_analysis.conv_analysis_{real,imag}.weight, mpaec.dft_synthesis.conv_synthesis_{real,imag}.weight  (N,1,N)
+ *       4..21  mpaec.aenc.{fnn_enc,fnn_enc2,fnn_enc3,fnn_enc4,fnn_addknobs,fnn_dec4,fnn_dec3,fnn_dec2,fnn_dec}.{weight,bias}
+ *       22..39 mpaec.phs_aenc.<same nine layers>.{weight,bias}
+ */
+#ifndef SIGNALTRAIN_B200_H
+#define SIGNALTRAIN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ST_NUM_PARAMS 40
+#define ST_NUM_ACTS 30
+#define ST_ABI_VERSION 1
+
+typedef struct st_handle st_handle;
+
+/* Geometry of one model instance.  Mirrors st_model.__init__ (signaltrain/nn_proc.py:348-385). */
+typedef struct st_config {
+    int chunk;       /* C : input samples per window            nn_proc.py:357 */
+    int ft;          /* N : DFT size / taps (1024)              nn_proc.py:370 */
+    int hop;         /* H : hop (384)                           nn_proc.py:371 */
+    int frames_in;   /* T : expected_time_frames                nn_proc.py:378 */
+    int frames_out;  /* OT: output_time_frames                  nn_proc.py:379 */
+    int knobs;       /* K : number of knobs                     nn_proc.py:363 */
+    int rank;        /* R : decomposition rank (64)             nn_proc.py:279 */
+} st_config;
+
+/* Adam hyper-parameters (torch.optim.Adam defaults used at signaltrain/train.py:228). */
+typedef struct st_adam {
+    float lr;          /* learning rate for THIS step (train.py:150 lag is the caller's business) */
+    float beta1, beta2, eps;
+    int step;          /* 1-based step count t, for the bias corrections */
+    float grad_scale;  /* multiply every gradient by this first (1/world_size after an allreduce-sum) */
+    float max_norm;    /* L1 clip threshold over the four DFT tensors (nn_proc.py:299-302); <=0 disables */
+} st_adam;
+
+int st_abi_version(void);
+
+/* st_model(...) constructor: nn_proc.py:348-385.  Allocates the device workspace lazily per batch. */
+int st_create(const st_config* cfg, int device, st_handle** out);
+void st_destroy(st_handle* h);
+const char* st_last_error(const st_handle* h);   /* h may be NULL: last error of a failed st_create */
+
+/* state_dict slot description. */
+const char* st_param_name(const st_handle* h, int idx);
+long st_param_numel(const st_handle* h, int idx);
+int st_out_samples(const st_handle* h);           /* L = (OT-1)*hop - ft   nn_proc.py:380 */
+int st_bins(const st_handle* h);                  /* F = ft/2+1            cls_fe_dft.py:24 */
+
+/* Analysis / Synthesis .initialize(): cls_fe_dft.py:36-48 and :87-100 (incl. GLA window :133-163).
+ * Writes the four (N,N) front-end matrices into params[0..3]. */
+int st_init_frontend(st_handle* h, float* const* params, void* stream);
+
+/* st_model.forward(x, knobs, return_acts): nn_proc.py:392 -> AsymMPAEC.forward :305-340.
+ *   x (B,C)  knobs (B,K)  ->  y_hat (B,L) [= 2*y_hat of :340]  mag (B,T,F)  mag_hat (B,OT,F)
+ *   acts: NULL, or ST_NUM_ACTS device pointers receiving the reference's layer_acts (:311-335), each
+ *   contiguous in the reference's logical shape. */
+int st_forward(st_handle* h, const float* x, const float* knobs, int batch,
+               const float* const* params, float* y_hat, float* mag, float* mag_hat,
+               float* const* acts, void* stream);
+
+/* loss_functions.calc_loss(y_hat, y, mag_hat, scale_by_freq=..., l1_lambda): loss_functions.py:26-43,
+ * branches :34 (scale_by_freq NULL: l1_coef*mean|mag_hat|) and :36 (l1_coef*mean|mag_hat*s|; the caller
+ * passes l1_coef = l1_lambda/10 as the reference does).  scale_by_freq is F floats (the reference
+ * expands exp(7f/F) over (B,OT,F), train.py:115-117).
+ * Writes the scalar loss to loss[0] and, if non-NULL, dLoss/dy_hat (B,L) and dLoss/dmag_hat (B,OT,F). */
+int st_loss(st_handle* h, const float* y_hat, const float* y, const float* mag_hat,
+            const float* scale_by_freq, float l1_coef, int batch,
+            float* loss, float* g_y_hat, float* g_mag_hat, void* stream);
+
+/* loss_functions.mae (loss_functions.py:22-23) -- validation metric, train.py:58. */
+int st_mae(st_handle* h, const float* a, const float* b, long n, float* out, void* stream);
+
+/* loss.backward() through st_model.forward (train.py:138).  Must follow the st_forward of the same
+ * batch on the same handle (activations live in the handle's workspace).  g_mag / g_mag_hat may be NULL.
+ * Writes (overwrites) all ST_NUM_PARAMS gradients. */
+int st_backward(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat,
+                int batch, const float* const* params, float* const* grads, void* stream);
+
+/* model.clip_grad_norm_() (nn_proc.py:299-302, torch clip_grad_norm_ max_norm=1 norm_type=1 over the
+ * four DFT tensors): scales grads[0..3] in place, writes the total L1 norm to total_norm[0] (device). */
+int st_clip_grad_norm(st_handle* h, float* const* grads, float max_norm, float* total_norm, void* stream);
+
+/* optimizer.step() of torch.optim.Adam (train.py:147), all tensors in one launch; optional fused
+ * gradient scaling + L1 clip (hp->max_norm > 0) so the unfused clip pass is not needed. */
+int st_adam_step(st_handle* h, float* const* params, const float* const* grads,
+                 float* const* exp_avg, float* const* exp_avg_sq, const st_adam* hp, void* stream);
+
+/* One whole iteration of the loop body train.py:112-147: forward, calc_loss, backward, clip, Adam.
+ * y is (B,L) float32.  loss[0] (device) receives the scalar loss.  If allreduce-before-update is
+ * needed (data parallel), call st_forward/st_loss/st_backward, reduce, then st_adam_step instead. */
+int st_train_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch,
+                  float* const* params, float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const float* scale_by_freq, float l1_coef,
+                  const st_adam* hp, float* loss, void* stream);
+
+/* Measurement support (bench.py): number of kernels / device copies this handle has launched, and per-stage
+ * device time bracketed with CUDA events on the launching stream.  st_profile_read synchronises the device,
+ * fills ms[i] / calls[i] for i < st_profile_stage_count() with the totals since the previous read, and resets. */
+long st_launch_count(const st_handle* h);
+int st_profile_stage_count(void);
+const char* st_profile_stage_name(int i);
+int st_profile(st_handle* h, int enable);
+int st_profile_read(st_handle* h, float* ms, long* calls);
+
+/* Test/diagnostic access to workspace buffers by name ("spec", "ri", "frames_out", "g_ri", "g_spec",
+ * "wcat", "sfold").  Copies up to n floats to a HOST buffer, synchronising the device. */
+int st_debug_read(st_handle* h, const char* name, float* dst_host, long n);
+long st_debug_numel(st_handle* h, const char* name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGNALTRAIN_B200_H */

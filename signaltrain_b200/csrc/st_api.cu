@@ -1,0 +1,602 @@
+// C ABI of signaltrain_b200 (include/signaltrain_b200.h): handle, workspace, and the kernel sequences of
+// forward / loss / backward / clip / Adam.  Host code only orchestrates; all arithmetic is in the kernels.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/signaltrain_b200.h"
+#include "st_common.cuh"
+
+struct st_handle {
+    StDims d;
+    AeGeom g;
+    int device = 0;
+    int sm_count = 148;
+    int maxB = 0;
+    int fwdB = 0;                 // batch of the last st_forward (st_backward must match)
+    int ae_grid = 0;
+    // workspace (device)
+    float *xpad = nullptr, *wcat = nullptr, *sfold = nullptr, *spec = nullptr, *ri = nullptr, *fo = nullptr;
+    float *mag_hat_ws = nullptr, *phs_hat_ws = nullptr, *gwave = nullptr, *g_ri = nullptr, *g_spec = nullptr;
+    float *part_a = nullptr, *part_s = nullptr, *ae_part = nullptr;
+    float *yhat_ws = nullptr, *gy_ws = nullptr, *gmh_ws = nullptr;   // fused train step only
+    float* knobs_ws = nullptr;    // copy of the forward's knobs (the backward recomputes the AE chain)
+    float* small = nullptr;       // reduction scratch + scalar outputs
+    unsigned* counters = nullptr;
+    double* win = nullptr;        // [hamming | GLA] in double, for st_init_frontend
+    int2 *map_live = nullptr, *map_full = nullptr;
+    int n_live = 0, n_full = 0;
+    long numel[ST_NUM_PARAMS];
+    std::string names[ST_NUM_PARAMS];
+    // per-stage profiling (st_profile / st_profile_read): CUDA events on the launching stream
+    bool prof_on = false;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
+    long launches = 0;            // kernels + device copies launched by this handle since creation
+    char err[1024];
+};
+
+enum Stage { SG_PAD_X, SG_PACK_W, SG_GEMM_ANALYSIS, SG_AE_FWD, SG_GEMM_SYNTH, SG_OLA, SG_LOSS, SG_PAD_G, SG_GEMM_SYNTH_DGRAD,
+             SG_GEMM_SYNTH_WGRAD, SG_AE_BWD, SG_AE_REDUCE, SG_GEMM_ANALYSIS_WGRAD, SG_FINALIZE, SG_L1NORM, SG_ADAM, SG_COUNT };
+static const char* kStageNames[SG_COUNT] = {"pad_x", "pack_weights", "gemm_analysis", "ae_forward", "gemm_synthesis",
+    "overlap_add", "loss", "pad_grad", "gemm_synthesis_dgrad", "gemm_synthesis_wgrad", "ae_backward", "ae_grad_reduce",
+    "gemm_analysis_wgrad", "finalize_dft_grads", "l1_norm", "adam"};
+
+// RAII scope around one stage: counts its launches and, when profiling is on, brackets it with events.
+struct StageScope {
+    st_handle* h; int stage; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr;
+    StageScope(st_handle* h_, int stage_, int nlaunch, cudaStream_t s_) : h(h_), stage(stage_), s(s_) {
+        h->launches += nlaunch;
+        if (h->prof_on) {
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            cudaEventRecord(a, s);
+        }
+    }
+    ~StageScope() {
+        if (a) {
+            cudaEventRecord(b, s);
+            h->prof_events.push_back({stage, {a, b}});
+        }
+    }
+};
+
+static thread_local char g_create_err[1024] = "";
+
+// offsets inside h->small (floats)
+enum { SM_LOSS = 0, SM_NORM = 2400, SM_MAE = 3008, SM_TOTAL_NORM = 4200, SM_COEF = 4201, SM_FLOATS = 4352 };
+enum { CT_LOSS = 0, CT_NORM = 1, CT_MAE = 2, CT_COUNT = 4 };
+static const int kMaxSplits = 8;
+
+int st_fail_msg(st_handle* h, const char* fmt, ...) {
+    char* dst = h ? h->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 1024, fmt, ap);
+    va_end(ap);
+    return 1;
+}
+int st_fail_cuda(st_handle* h, cudaError_t e, const char* what, const char* file, int line) {
+    return st_fail_msg(h, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+}
+
+#define ST_LAUNCH_OK(h)                                                                        \
+    do {                                                                                       \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess) return st_fail_cuda(h, e__, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+static int opw_for(int n) { return n <= 16 ? 1 : (n <= 32 ? 2 : 4); }
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static void build_geom(const StDims& d, AeGeom& g) {
+    const int in[ST_AE_LAYERS] = {d.T, 64, 32, 16, 16 + d.K, 16, 16, 32, 64};
+    const int out[ST_AE_LAYERS] = {64, 32, 16, 16, 16, 16, 32, 64, d.OT};
+    int owt = 0, ow = 0, flat = 0;
+    for (int l = 0; l < ST_AE_LAYERS; ++l) {
+        g.in[l] = in[l];
+        g.out[l] = out[l];
+        g.opw[l] = opw_for(out[l]);
+        g.outp[l] = 16 * g.opw[l];
+        const int back_out = (l == 4) ? 16 : in[l];       // data-gradient width (knobs carry none)
+        g.inp[l] = std::max(round_up(in[l], 4), 16 * opw_for(back_out));
+        g.off_wt[l] = owt;
+        owt += in[l] * g.outp[l];
+        g.off_w[l] = ow;
+        ow += out[l] * g.inp[l];
+        g.flat_off[l] = flat;
+        flat += out[l] * in[l] + out[l];
+    }
+    for (int l = 0; l < ST_AE_LAYERS; ++l) {
+        g.off_b[l] = owt;
+        owt += g.outp[l];
+    }
+    g.wt_floats = round_up(owt, 4);
+    g.w_floats = round_up(ow, 4);
+    g.flat_total = flat;
+    g.opw_T = opw_for(d.T);
+}
+
+static std::vector<double> hamming_sym(int n) {
+    std::vector<double> w(n);
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i < n; ++i) w[i] = 0.54 - 0.46 * std::cos(2.0 * pi * i / (n - 1));
+    return w;
+}
+
+extern "C" int st_abi_version(void) { return ST_ABI_VERSION; }
+
+extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
+    if (!cfg || !out) return st_fail_msg(nullptr, "st_create: null argument");
+    *out = nullptr;
+    const int C = cfg->chunk, N = cfg->ft, H = cfg->hop, T = cfg->frames_in, OT = cfg->frames_out, K = cfg->knobs;
+    if (cfg->rank != 64) return st_fail_msg(nullptr, "st_create: decomposition rank %d unsupported (reference hard-codes 64)", cfg->rank);
+    if (N < 64 || (N & 7) || (H & 3) || (C & 3) || H <= 0 || C <= 0)
+        return st_fail_msg(nullptr, "st_create: need ft %% 8 == 0, hop %% 4 == 0, chunk %% 4 == 0 (got ft=%d hop=%d chunk=%d)", N, H, C);
+    if (K < 0 || K > 16) return st_fail_msg(nullptr, "st_create: knobs=%d outside [0,16]", K);
+    if ((C + N) / H + 1 != T)
+        return st_fail_msg(nullptr, "st_create: conv output frames %d != expected_time_frames %d (the reference would fail at nn_proc.py:81)",
+                           (C + N) / H + 1, T);
+    if (OT > T || OT < 2 || T > ST_MAX_TFRAMES)
+        return st_fail_msg(nullptr, "st_create: need 2 <= frames_out <= frames_in <= %d (got %d, %d)", ST_MAX_TFRAMES, OT, T);
+    const int L = (OT - 1) * H - N;
+    if (L <= 0 || L > C || (L & 3)) return st_fail_msg(nullptr, "st_create: invalid output size L=%d", L);
+
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return st_fail_cuda(nullptr, e, "cudaSetDevice", __FILE__, __LINE__);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return st_fail_cuda(nullptr, e, "cudaGetDeviceProperties", __FILE__, __LINE__);
+    if (prop.major != 10)
+        return st_fail_msg(nullptr, "st_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+
+    st_handle* h = new st_handle();
+    h->err[0] = 0;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    StDims& d = h->d;
+    d.C = C; d.N = N; d.H = H; d.F = N / 2 + 1; d.Fp = round_up(d.F, 8); d.T = T; d.OT = OT; d.L = L; d.K = K; d.R = 64;
+    d.Cp = C + 2 * N; d.Lp = L + 2 * N;
+    build_geom(d, h->g);
+    if (st_ae_configure(h, d, h->g)) {
+        snprintf(g_create_err, sizeof(g_create_err), "%s", h->err);
+        delete h;
+        return 1;
+    }
+    // parameter table
+    const char* dft[4] = {"mpaec.dft_analysis.conv_analysis_real.weight", "mpaec.dft_analysis.conv_analysis_imag.weight",
+                          "mpaec.dft_synthesis.conv_synthesis_real.weight", "mpaec.dft_synthesis.conv_synthesis_imag.weight"};
+    const char* layers[ST_AE_LAYERS] = {"fnn_enc", "fnn_enc2", "fnn_enc3", "fnn_enc4", "fnn_addknobs",
+                                        "fnn_dec4", "fnn_dec3", "fnn_dec2", "fnn_dec"};
+    for (int i = 0; i < 4; ++i) { h->names[i] = dft[i]; h->numel[i] = (long)N * N; }
+    for (int a = 0; a < 2; ++a)
+        for (int l = 0; l < ST_AE_LAYERS; ++l) {
+            const int i = 4 + a * 18 + 2 * l;
+            h->names[i] = std::string("mpaec.") + (a ? "phs_aenc." : "aenc.") + layers[l] + ".weight";
+            h->names[i + 1] = std::string("mpaec.") + (a ? "phs_aenc." : "aenc.") + layers[l] + ".bias";
+            h->numel[i] = (long)h->g.out[l] * h->g.in[l];
+            h->numel[i + 1] = h->g.out[l];
+        }
+    // persistent small buffers
+    auto fail = [&](cudaError_t ce, const char* what) {
+        st_fail_cuda(nullptr, ce, what, __FILE__, __LINE__);
+        st_destroy(h);
+        return 1;
+    };
+    if ((e = cudaMalloc(&h->small, SM_FLOATS * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(small)");
+    if ((e = cudaMalloc(&h->counters, CT_COUNT * sizeof(unsigned))) != cudaSuccess) return fail(e, "cudaMalloc(counters)");
+    if ((e = cudaMemset(h->counters, 0, CT_COUNT * sizeof(unsigned))) != cudaSuccess) return fail(e, "cudaMemset(counters)");
+    if ((e = cudaMalloc(&h->wcat, 2L * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(wcat)");
+    if ((e = cudaMalloc(&h->sfold, 2L * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(sfold)");
+    if ((e = cudaMalloc(&h->part_a, (long)kMaxSplits * 2 * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(part_a)");
+    if ((e = cudaMalloc(&h->part_s, (long)kMaxSplits * 2 * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(part_s)");
+    // windows for st_init_frontend: hamming (cls_fe_dft.py:38) and the Griffin-Lim LSEE window (:133-163)
+    {
+        std::vector<double> w = hamming_sym(N), win(2 * N), env(N, 0.0);
+        const int red = N / H;
+        for (int k = -red; k <= red; ++k) {
+            const int lo = std::max(0, H * k), hi = std::min(N, N + H * k);
+            for (int j = lo; j < hi; ++j) env[j] += w[j - H * k] * w[j - H * k];
+        }
+        for (int i = 0; i < N; ++i) { win[i] = w[i]; win[N + i] = w[i] / env[i]; }
+        if ((e = cudaMalloc(&h->win, 2 * N * sizeof(double))) != cudaSuccess) return fail(e, "cudaMalloc(win)");
+        if ((e = cudaMemcpy(h->win, win.data(), 2 * N * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "cudaMemcpy(win)");
+    }
+    // Adam chunk maps: live-only (analysis rows >= F never receive gradient) and full
+    {
+        std::vector<int2> live, full;
+        for (int i = 0; i < ST_NUM_PARAMS; ++i) {
+            const long nf = h->numel[i], nl = (i < 2) ? (long)d.F * N : nf;
+            for (long c = 0; c * ST_ADAM_CHUNK < nf; ++c) full.push_back(make_int2(i, (int)c));
+            for (long c = 0; c * ST_ADAM_CHUNK < nl; ++c) live.push_back(make_int2(i, (int)c));
+        }
+        h->n_live = (int)live.size();
+        h->n_full = (int)full.size();
+        if ((e = cudaMalloc(&h->map_live, live.size() * sizeof(int2))) != cudaSuccess) return fail(e, "cudaMalloc(map_live)");
+        if ((e = cudaMalloc(&h->map_full, full.size() * sizeof(int2))) != cudaSuccess) return fail(e, "cudaMalloc(map_full)");
+        cudaMemcpy(h->map_live, live.data(), live.size() * sizeof(int2), cudaMemcpyHostToDevice);
+        cudaMemcpy(h->map_full, full.data(), full.size() * sizeof(int2), cudaMemcpyHostToDevice);
+    }
+    *out = h;
+    return 0;
+}
+
+static void free_batch_buffers(st_handle* h) {
+    float** bufs[] = {&h->xpad, &h->spec, &h->ri, &h->fo, &h->mag_hat_ws, &h->phs_hat_ws, &h->gwave, &h->g_ri,
+                      &h->g_spec, &h->ae_part, &h->yhat_ws, &h->gy_ws, &h->gmh_ws, &h->knobs_ws};
+    for (float** b : bufs) {
+        if (*b) cudaFree(*b);
+        *b = nullptr;
+    }
+    h->maxB = 0;
+}
+
+extern "C" void st_destroy(st_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    free_batch_buffers(h);
+    if (h->small) cudaFree(h->small);
+    if (h->counters) cudaFree(h->counters);
+    if (h->wcat) cudaFree(h->wcat);
+    if (h->sfold) cudaFree(h->sfold);
+    if (h->part_a) cudaFree(h->part_a);
+    if (h->part_s) cudaFree(h->part_s);
+    if (h->win) cudaFree(h->win);
+    if (h->map_live) cudaFree(h->map_live);
+    if (h->map_full) cudaFree(h->map_full);
+    delete h;
+}
+
+extern "C" const char* st_last_error(const st_handle* h) { return h ? h->err : g_create_err; }
+extern "C" const char* st_param_name(const st_handle* h, int idx) {
+    return (h && idx >= 0 && idx < ST_NUM_PARAMS) ? h->names[idx].c_str() : "";
+}
+extern "C" long st_param_numel(const st_handle* h, int idx) { return (h && idx >= 0 && idx < ST_NUM_PARAMS) ? h->numel[idx] : -1; }
+extern "C" int st_out_samples(const st_handle* h) { return h ? h->d.L : -1; }
+extern "C" int st_bins(const st_handle* h) { return h ? h->d.F : -1; }
+
+// (Re)allocate the batch-sized workspace.  Grows only; a steady-state training loop never allocates.
+static int ensure_workspace(st_handle* h, int B) {
+    if (B <= 0) return st_fail_msg(h, "batch must be positive (got %d)", B);
+    ST_CUDA_OK(cudaSetDevice(h->device));
+    if (B <= h->maxB) return 0;
+    ST_CUDA_OK(cudaDeviceSynchronize());
+    free_batch_buffers(h);
+    const StDims& d = h->d;
+    const long BT = (long)B * d.T, BO = (long)B * d.OT;
+    const long tiles = ((long)B * d.F + ST_AE_ROWS - 1) / ST_AE_ROWS;
+    h->ae_grid = (int)std::min<long>(tiles, h->sm_count);
+    struct { float** p; long n; bool zero; } req[] = {
+        {&h->xpad, (long)B * d.Cp, false},       {&h->spec, BT * 2 * d.Fp, true},   {&h->ri, BO * 2 * d.Fp, true},
+        {&h->fo, BO * d.N, false},               {&h->mag_hat_ws, BO * d.F, false}, {&h->phs_hat_ws, BO * d.F, false},
+        {&h->gwave, (long)B * d.Lp, false},      {&h->g_ri, BO * 2 * d.Fp, true},   {&h->g_spec, BT * 2 * d.Fp, true},
+        {&h->ae_part, (long)h->sm_count * 2 * h->g.flat_total, true},
+        {&h->yhat_ws, (long)B * d.L, false},     {&h->gy_ws, (long)B * d.L, false}, {&h->gmh_ws, BO * d.F, false},
+        {&h->knobs_ws, (long)B * std::max(d.K, 1), false},
+    };
+    for (auto& r : req) {
+        ST_CUDA_OK(cudaMalloc(r.p, r.n * sizeof(float)));
+        if (r.zero) ST_CUDA_OK(cudaMemset(*r.p, 0, r.n * sizeof(float)));   // padding columns must stay exactly zero
+    }
+    ST_CUDA_OK(cudaDeviceSynchronize());
+    h->maxB = B;
+    return 0;
+}
+
+static void split_params(const float* const* params, AeParams& pm, AeParams& pp) {
+    for (int l = 0; l < ST_AE_LAYERS; ++l) {
+        pm.W[l] = params[4 + 2 * l];  pm.b[l] = params[5 + 2 * l];
+        pp.W[l] = params[22 + 2 * l]; pp.b[l] = params[23 + 2 * l];
+    }
+}
+
+static int check_ptrs(st_handle* h, const void* const* p, int n, const char* what) {
+    if (!p) return st_fail_msg(h, "%s: null pointer table", what);
+    for (int i = 0; i < n; ++i)
+        if (!p[i]) return st_fail_msg(h, "%s: entry %d is null", what, i);
+    return 0;
+}
+
+extern "C" int st_init_frontend(st_handle* h, float* const* params, void* stream) {
+    if (!h) return 1;
+    if (check_ptrs(h, (const void* const*)params, 4, "st_init_frontend(params)")) return 1;
+    ST_CUDA_OK(cudaSetDevice(h->device));
+    st_launch_init_frontend(h->d, params[0], params[1], params[2], params[3], reinterpret_cast<float*>(h->win), (cudaStream_t)stream);
+    ST_LAUNCH_OK(h);
+    return 0;
+}
+
+static int forward_impl(st_handle* h, const float* x, const float* knobs, int B, const float* const* params, float* y_hat,
+                        float* mag, float* mag_hat_user, float* const* acts, cudaStream_t s) {
+    const StDims& d = h->d;
+    if (ensure_workspace(h, B)) return 1;
+    {
+        StageScope sc(h, SG_PAD_X, 1 + (d.K > 0), s);
+        st_launch_pad_scale(x, h->xpad, B, d.C, d.N, 0.5f, s);                               // x/2, conv padding
+        if (d.K > 0) ST_CUDA_OK(cudaMemcpyAsync(h->knobs_ws, knobs, (long)B * d.K * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    {
+        StageScope sc(h, SG_PACK_W, 2, s);
+        st_launch_pack_analysis(d, params[0], params[1], h->wcat, s);
+        st_launch_fold_synthesis(d, params[2], params[3], h->sfold, s);
+    }
+    ST_LAUNCH_OK(h);
+    {   // analysis: spec[(b,t), (re|im) k] = sum_n frame[(b,t), n] * wcat[k, n]
+        StageScope sc(h, SG_GEMM_ANALYSIS, 1, s);
+        GemmOperand A{h->xpad, 0, d.T, d.Cp, d.H}, W{h->wcat, d.N, 0, 0, 0};
+        st_launch_gemm(true, true, A, W, h->spec, 2L * d.Fp, B * d.T, 2 * d.Fp, d.N, 1, 0, s);
+    }
+    ST_LAUNCH_OK(h);
+    {
+        StageScope sc(h, SG_AE_FWD, 1 + (mag_hat_user != nullptr), s);
+        AeParams pm, pp;
+        split_params(params, pm, pp);
+        st_launch_ae_forward(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, acts, h->ae_grid, s);
+        if (mag_hat_user)
+            ST_CUDA_OK(cudaMemcpyAsync(mag_hat_user, h->mag_hat_ws, (long)B * d.OT * d.F * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    ST_LAUNCH_OK(h);
+    {   // synthesis: frames_out[(b,t), n] = sum_k ri[(b,t), k] * sfold[k, n]
+        StageScope sc(h, SG_GEMM_SYNTH, 1, s);
+        GemmOperand R{h->ri, 2L * d.Fp, 0, 0, 0}, S{h->sfold, d.N, 0, 0, 0};
+        st_launch_gemm(true, false, R, S, h->fo, d.N, B * d.OT, d.N, 2 * d.Fp, 1, 0, s);
+    }
+    ST_LAUNCH_OK(h);
+    {
+        StageScope sc(h, SG_OLA, 1, s);
+        st_launch_overlap_add(d, h->fo, h->xpad, B, y_hat, acts ? acts[28] : nullptr, acts ? acts[29] : nullptr, s);
+    }
+    ST_LAUNCH_OK(h);
+    h->fwdB = B;
+    return 0;
+}
+
+extern "C" int st_forward(st_handle* h, const float* x, const float* knobs, int batch, const float* const* params,
+                          float* y_hat, float* mag, float* mag_hat, float* const* acts, void* stream) {
+    if (!h) return 1;
+    if (!x || !knobs || !y_hat) return st_fail_msg(h, "st_forward: null x / knobs / y_hat");
+    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_forward(params)")) return 1;
+    if (acts && check_ptrs(h, (const void* const*)acts, ST_NUM_ACTS, "st_forward(acts)")) return 1;
+    return forward_impl(h, x, knobs, batch, params, y_hat, mag, mag_hat, acts, (cudaStream_t)stream);
+}
+
+extern "C" int st_loss(st_handle* h, const float* y_hat, const float* y, const float* mag_hat, const float* sbf,
+                       float l1_coef, int batch, float* loss, float* g_y_hat, float* g_mag_hat, void* stream) {
+    if (!h) return 1;
+    if (!y_hat || !y || !mag_hat || !loss) return st_fail_msg(h, "st_loss: null argument");
+    if (batch <= 0) return st_fail_msg(h, "st_loss: batch must be positive");
+    ST_CUDA_OK(cudaSetDevice(h->device));
+    {
+        StageScope sc(h, SG_LOSS, 1, (cudaStream_t)stream);
+        st_launch_loss(h->d, y_hat, y, mag_hat, sbf, l1_coef, batch, loss, g_y_hat, g_mag_hat, h->small + SM_LOSS,
+                       h->counters + CT_LOSS, (cudaStream_t)stream);
+    }
+    ST_LAUNCH_OK(h);
+    return 0;
+}
+
+extern "C" int st_mae(st_handle* h, const float* a, const float* b, long n, float* out, void* stream) {
+    if (!h) return 1;
+    if (!a || !b || !out || n <= 0) return st_fail_msg(h, "st_mae: bad argument");
+    ST_CUDA_OK(cudaSetDevice(h->device));
+    st_launch_mae(a, b, n, out, h->small + SM_MAE, h->counters + CT_MAE, (cudaStream_t)stream);
+    ST_LAUNCH_OK(h);
+    return 0;
+}
+
+static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat, int B,
+                         const float* const* params, float* const* grads, cudaStream_t s) {
+    const StDims& d = h->d;
+    if (B != h->fwdB || B > h->maxB)
+        return st_fail_msg(h, "st_backward: batch %d does not match the preceding st_forward (%d)", B, h->fwdB);
+    ST_CUDA_OK(cudaSetDevice(h->device));
+    // adjoint of (*2, trim [N:-N]): zero-padded 2*g
+    {
+        StageScope sc(h, SG_PAD_G, 1, s);
+        st_launch_pad_scale(g_y_hat, h->gwave, B, d.L, d.N, 2.0f, s);
+    }
+    ST_LAUNCH_OK(h);
+    GemmOperand Gf{h->gwave, 0, d.OT, d.Lp, d.H};   // gathered frames of the output gradient (adjoint of overlap-add)
+    GemmOperand S{h->sfold, d.N, 0, 0, 0}, R{h->ri, 2L * d.Fp, 0, 0, 0};
+    {   // synthesis data gradient: g_ri[(b,t), k] = sum_n gframe[(b,t), n] * sfold[k, n]
+        StageScope sc(h, SG_GEMM_SYNTH_DGRAD, 1, s);
+        st_launch_gemm(true, true, Gf, S, h->g_ri, 2L * d.Fp, B * d.OT, 2 * d.Fp, d.N, 1, 0, s);
+    }
+    ST_LAUNCH_OK(h);
+    // synthesis weight gradient (folded): G[k, n] = sum_(b,t) ri[(b,t), k] * gframe[(b,t), n]
+    const long plane = 2L * d.Fp * d.N;
+    const int Ks = B * d.OT, Ka = B * d.T;
+    int ss, sa;
+    {
+        StageScope sc(h, SG_GEMM_SYNTH_WGRAD, 1, s);
+        ss = st_launch_gemm(false, false, R, Gf, h->part_s, d.N, 2 * d.Fp, d.N, Ks,
+                            std::min(kMaxSplits, std::max(1, Ks / 256)), plane, s);
+    }
+    ST_LAUNCH_OK(h);
+    {   // both autoencoders: recompute, back-propagate, dL/d(re|im) -> g_spec, per-CTA weight-gradient partials
+        StageScope sc(h, SG_AE_BWD, 1, s);
+        AeParams pm, pp;
+        split_params(params, pm, pp);
+        st_launch_ae_backward(d, h->g, pm, pp, h->spec, h->knobs_ws, B, h->mag_hat_ws, h->phs_hat_ws, h->g_ri, g_mag_hat,
+                              g_mag, h->g_spec, h->ae_part, h->ae_grid, s);
+    }
+    ST_LAUNCH_OK(h);
+    {
+        StageScope sc(h, SG_AE_REDUCE, 1, s);
+        AeGrads gm, gp;
+        for (int l = 0; l < ST_AE_LAYERS; ++l) {
+            gm.W[l] = grads[4 + 2 * l];  gm.b[l] = grads[5 + 2 * l];
+            gp.W[l] = grads[22 + 2 * l]; gp.b[l] = grads[23 + 2 * l];
+        }
+        st_launch_ae_grad_reduce(h->g, h->ae_part, h->ae_grid, gm, gp, s);
+    }
+    ST_LAUNCH_OK(h);
+    {   // analysis weight gradient: G[(re|im) k, n] = sum_(b,t) g_spec[(b,t), k] * frame[(b,t), n]
+        StageScope sc(h, SG_GEMM_ANALYSIS_WGRAD, 1, s);
+        GemmOperand Gs{h->g_spec, 2L * d.Fp, 0, 0, 0}, Xf{h->xpad, 0, d.T, d.Cp, d.H};
+        sa = st_launch_gemm(false, false, Gs, Xf, h->part_a, d.N, 2 * d.Fp, d.N, Ka,
+                            std::min(kMaxSplits, std::max(1, Ka / 256)), plane, s);
+    }
+    ST_LAUNCH_OK(h);
+    {
+        StageScope sc(h, SG_FINALIZE, 1, s);
+        st_launch_finalize_dft_grads(d, h->part_a, h->part_s, sa, ss, grads[0], grads[1], grads[2], grads[3], s);
+    }
+    ST_LAUNCH_OK(h);
+    return 0;
+}
+
+extern "C" int st_backward(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat, int batch,
+                           const float* const* params, float* const* grads, void* stream) {
+    if (!h) return 1;
+    if (!g_y_hat) return st_fail_msg(h, "st_backward: null g_y_hat");
+    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_backward(params)")) return 1;
+    if (check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_backward(grads)")) return 1;
+    return backward_impl(h, g_y_hat, g_mag, g_mag_hat, batch, params, grads, (cudaStream_t)stream);
+}
+
+extern "C" int st_clip_grad_norm(st_handle* h, float* const* grads, float max_norm, float* total_norm, void* stream) {
+    if (!h) return 1;
+    if (check_ptrs(h, (const void* const*)grads, 4, "st_clip_grad_norm(grads)")) return 1;
+    ST_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const float* g[4] = {grads[0], grads[1], grads[2], grads[3]};
+    {
+        StageScope sc(h, SG_L1NORM, 2, s);
+        st_launch_l1_norm4(g, (long)h->d.N * h->d.N, 0, 0, 1.f, max_norm, total_norm ? total_norm : h->small + SM_TOTAL_NORM,
+                           h->small + SM_COEF, h->small + SM_NORM, h->counters + CT_NORM, s);
+        float* gw[4] = {grads[0], grads[1], grads[2], grads[3]};
+        st_launch_scale4(gw, (long)h->d.N * h->d.N, h->small + SM_COEF, s);   // torch multiplies even when coef == 1
+    }
+    ST_LAUNCH_OK(h);
+    return 0;
+}
+
+static int adam_impl(st_handle* h, float* const* params, const float* const* grads, float* const* m, float* const* v,
+                     const st_adam* hp, bool live_only, cudaStream_t s) {
+    if (hp->step < 1) return st_fail_msg(h, "st_adam_step: step must be >= 1 (got %d)", hp->step);
+    ST_CUDA_OK(cudaSetDevice(h->device));
+    const float* coef = nullptr;
+    if (hp->max_norm > 0.f) {
+        const float* g[4] = {grads[0], grads[1], grads[2], grads[3]};
+        {
+            StageScope sc(h, SG_L1NORM, 1, s);
+            st_launch_l1_norm4(g, (long)h->d.N * h->d.N, 0, 0, hp->grad_scale, hp->max_norm, h->small + SM_TOTAL_NORM,
+                               h->small + SM_COEF, h->small + SM_NORM, h->counters + CT_NORM, s);
+        }
+        ST_LAUNCH_OK(h);
+        coef = h->small + SM_COEF;
+    }
+    AdamTensors t;
+    for (int i = 0; i < ST_NUM_PARAMS; ++i) {
+        t.p[i] = params[i]; t.g[i] = grads[i]; t.m[i] = m[i]; t.v[i] = v[i];
+        t.n[i] = (live_only && i < 2) ? (long)h->d.F * h->d.N : h->numel[i];
+    }
+    // bias corrections in double, as torch does on the host for non-capturable Adam
+    const double bc1 = 1.0 - std::pow((double)hp->beta1, (double)hp->step);
+    const double bc2 = 1.0 - std::pow((double)hp->beta2, (double)hp->step);
+    AdamScalars sc;
+    sc.lr_over_bc1 = (float)((double)hp->lr / bc1);
+    sc.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+    sc.beta1 = hp->beta1; sc.beta2 = hp->beta2; sc.eps = hp->eps; sc.grad_scale = hp->grad_scale;
+    {
+        StageScope scope(h, SG_ADAM, 1, s);
+        st_launch_adam(t, live_only ? h->map_live : h->map_full, live_only ? h->n_live : h->n_full, sc, coef, s);
+    }
+    ST_LAUNCH_OK(h);
+    return 0;
+}
+
+extern "C" int st_adam_step(st_handle* h, float* const* params, const float* const* grads, float* const* exp_avg,
+                            float* const* exp_avg_sq, const st_adam* hp, void* stream) {
+    if (!h) return 1;
+    if (!hp) return st_fail_msg(h, "st_adam_step: null hyper-parameters");
+    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_adam_step(params)") ||
+        check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_adam_step(grads)") ||
+        check_ptrs(h, (const void* const*)exp_avg, ST_NUM_PARAMS, "st_adam_step(exp_avg)") ||
+        check_ptrs(h, (const void* const*)exp_avg_sq, ST_NUM_PARAMS, "st_adam_step(exp_avg_sq)"))
+        return 1;
+    return adam_impl(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/false, (cudaStream_t)stream);
+}
+
+extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch,
+                             float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                             const float* sbf, float l1_coef, const st_adam* hp, float* loss, void* stream) {
+    if (!h) return 1;
+    if (!x || !y || !knobs || !hp || !loss) return st_fail_msg(h, "st_train_step: null argument");
+    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_train_step(params)") ||
+        check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_train_step(grads)") ||
+        check_ptrs(h, (const void* const*)exp_avg, ST_NUM_PARAMS, "st_train_step(exp_avg)") ||
+        check_ptrs(h, (const void* const*)exp_avg_sq, ST_NUM_PARAMS, "st_train_step(exp_avg_sq)"))
+        return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ensure_workspace(h, batch)) return 1;
+    if (forward_impl(h, x, knobs, batch, params, h->yhat_ws, nullptr, nullptr, nullptr, s)) return 1;
+    {
+        StageScope sc(h, SG_LOSS, 1, s);
+        st_launch_loss(h->d, h->yhat_ws, y, h->mag_hat_ws, sbf, l1_coef, batch, loss, h->gy_ws, h->gmh_ws, h->small + SM_LOSS,
+                       h->counters + CT_LOSS, s);
+    }
+    ST_LAUNCH_OK(h);
+    if (backward_impl(h, h->gy_ws, nullptr, h->gmh_ws, batch, params, grads, s)) return 1;
+    // gradients of the dead analysis rows are exactly zero here, so Adam may skip them
+    return adam_impl(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/true, s);
+}
+
+extern "C" long st_debug_numel(st_handle* h, const char* name) {
+    if (!h || !name) return -1;
+    const StDims& d = h->d;
+    const long B = h->fwdB;
+    if (!strcmp(name, "spec") || !strcmp(name, "g_spec")) return B * d.T * 2 * d.Fp;
+    if (!strcmp(name, "ri") || !strcmp(name, "g_ri")) return B * d.OT * 2 * d.Fp;
+    if (!strcmp(name, "frames_out")) return B * d.OT * d.N;
+    if (!strcmp(name, "wcat") || !strcmp(name, "sfold")) return 2L * d.Fp * d.N;
+    if (!strcmp(name, "xpad")) return B * d.Cp;
+    if (!strcmp(name, "phs_hat")) return B * d.OT * d.F;
+    return -1;
+}
+
+extern "C" int st_debug_read(st_handle* h, const char* name, float* dst, long n) {
+    if (!h || !name || !dst) return 1;
+    const long have = st_debug_numel(h, name);
+    if (have < 0) return st_fail_msg(h, "st_debug_read: unknown buffer '%s'", name);
+    const float* src = !strcmp(name, "spec") ? h->spec : !strcmp(name, "g_spec") ? h->g_spec : !strcmp(name, "ri") ? h->ri
+                     : !strcmp(name, "g_ri") ? h->g_ri : !strcmp(name, "frames_out") ? h->fo : !strcmp(name, "wcat") ? h->wcat
+                     : !strcmp(name, "sfold") ? h->sfold : !strcmp(name, "xpad") ? h->xpad : h->phs_hat_ws;
+    if (!src) return st_fail_msg(h, "st_debug_read: buffer '%s' not allocated yet", name);
+    ST_CUDA_OK(cudaSetDevice(h->device));
+    ST_CUDA_OK(cudaDeviceSynchronize());
+    ST_CUDA_OK(cudaMemcpy(dst, src, std::min(n, have) * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" long st_launch_count(const st_handle* h) { return h ? h->launches : -1; }
+extern "C" int st_profile_stage_count(void) { return SG_COUNT; }
+extern "C" const char* st_profile_stage_name(int i) { return (i >= 0 && i < SG_COUNT) ? kStageNames[i] : ""; }
+
+extern "C" int st_profile(st_handle* h, int enable) {
+    if (!h) return 1;
+    h->prof_on = enable != 0;
+    return 0;
+}
+
+// Synchronises the device, adds up the event-timed milliseconds and call counts per stage since the last
+// read, and clears the record.  ms / calls: arrays of st_profile_stage_count() entries.
+extern "C" int st_profile_read(st_handle* h, float* ms, long* calls) {
+    if (!h || !ms || !calls) return 1;
+    ST_CUDA_OK(cudaSetDevice(h->device));
+    ST_CUDA_OK(cudaDeviceSynchronize());
+    for (int i = 0; i < SG_COUNT; ++i) { ms[i] = 0.f; calls[i] = 0; }
+    for (auto& e : h->prof_events) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e.second.first, e.second.second);
+        ms[e.first] += t;
+        calls[e.first] += 1;
+        cudaEventDestroy(e.second.first);
+        cudaEventDestroy(e.second.second);
+    }
+    h->prof_events.clear();
+    return 0;
+}

@@ -1,0 +1,127 @@
+// Shared declarations for the signaltrain_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define ST_NUM_PARAMS 40
+#define ST_NUM_ACTS 30
+#define ST_AE_LAYERS 9
+#define ST_AE_ROWS 64          // (batch, bin) rows per CTA tile in the autoencoder kernels
+#define ST_AE_RS 68            // smem row stride (floats) of a [feature][row] activation plane
+#define ST_AE_THREADS 256
+#define ST_MAX_TFRAMES 64      // AE kernels keep ceil(T/16) register tiles; T, OT <= 64
+
+// Geometry, device-visible.  Names follow the reference.
+struct StDims {
+    int C;    // chunk
+    int N;    // ft size (taps)
+    int H;    // hop
+    int F;    // kept bins N/2+1
+    int Fp;   // bins padded to a multiple of 8: row stride of one (re|im) half of a spectrum row
+    int T;    // analysis frames
+    int OT;   // output frames
+    int L;    // output samples (OT-1)*H - N
+    int K;    // knobs
+    int R;    // AE rank (64)
+    int Cp;   // padded input row  C + 2N
+    int Lp;   // padded output-gradient row  L + 2N = (OT-1)*H + N
+};
+
+// One autoencoder's nine Linear layers, raw reference layout W[out][in] row-major, b[out].
+struct AeParams {
+    const float* W[ST_AE_LAYERS];
+    const float* b[ST_AE_LAYERS];
+};
+struct AeGrads {
+    float* W[ST_AE_LAYERS];
+    float* b[ST_AE_LAYERS];
+};
+
+// Layer geometry computed on the host once (st_api.cu) and passed by value.
+struct AeGeom {
+    int in[ST_AE_LAYERS];      // IN_l  (layer 5 includes the K knob inputs)
+    int out[ST_AE_LAYERS];     // OUT_l
+    int inp[ST_AE_LAYERS];     // IN_l rounded up to a multiple of 4   (row stride of W[o][i] in smem)
+    int outp[ST_AE_LAYERS];    // OUT_l rounded up to 16*OPW            (row stride of Wt[i][o] in smem)
+    int opw[ST_AE_LAYERS];     // outputs per half-warp in the forward mapping (1,2,4)
+    int off_wt[ST_AE_LAYERS];  // float offsets inside the packed smem weight block
+    int off_w[ST_AE_LAYERS];
+    int off_b[ST_AE_LAYERS];
+    int wt_floats;             // size of [Wt..., b...] block
+    int w_floats;              // size of the W[o][i] block (backward only)
+    int flat_off[ST_AE_LAYERS];   // offset of layer l's weight in the flat [W1,b1,W2,b2,...] gradient vector
+    int flat_total;            // total floats in that vector
+    int opw_T;                 // outputs per half-warp for the T-wide data-gradient of layer 1
+};
+
+#define ST_CUDA_OK(call)                                                         \
+    do {                                                                         \
+        cudaError_t e__ = (call);                                                \
+        if (e__ != cudaSuccess) return st_fail_cuda(h, e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+struct st_handle;
+int st_fail_cuda(st_handle* h, cudaError_t e, const char* what, const char* file, int line);
+int st_fail_msg(st_handle* h, const char* fmt, ...);
+
+static inline int st_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ---- launchers implemented in the .cu files (all asynchronous on `s`) ----------------------
+// st_frontend.cu
+void st_launch_pad_scale(const float* src, float* dst, int rows, int len, int pad, float scale, cudaStream_t s);
+void st_launch_pack_analysis(const StDims& d, const float* Wr, const float* Wi, float* wcat, cudaStream_t s);
+void st_launch_fold_synthesis(const StDims& d, const float* Sr, const float* Si, float* sfold, cudaStream_t s);
+void st_launch_overlap_add(const StDims& d, const float* frames_out, const float* xpad, int B,
+                           float* y_hat, float* x_fwdsyn, float* y_half, cudaStream_t s);
+void st_launch_finalize_dft_grads(const StDims& d, const float* part_a, const float* part_s, int splits_a,
+                                  int splits_s, float* gWr, float* gWi, float* gSr, float* gSi, cudaStream_t s);
+void st_launch_init_frontend(const StDims& d, float* Wr, float* Wi, float* Sr, float* Si, float* scratch, cudaStream_t s);
+
+// st_gemm_simt.cu  C[M,N] (+split partials) = op(A) * op(B)
+struct GemmOperand {
+    const float* ptr;
+    long ld;      // leading dimension (floats) when not gathered
+    int g_T;      // >0: rows are overlapping frames: row r -> (r / g_T) * g_ld + (r % g_T) * g_H
+    long g_ld;
+    int g_H;
+};
+// returns the number of split-K planes actually written (<= splits)
+int st_launch_gemm(bool a_kcontig, bool b_kcontig, const GemmOperand& A, const GemmOperand& B, float* C, long ldc,
+                   int M, int N, int K, int splits, long split_stride, cudaStream_t s);
+
+// st_ae.cu
+size_t st_ae_fwd_smem(const StDims& d, const AeGeom& g);
+size_t st_ae_bwd_smem(const StDims& d, const AeGeom& g);
+int st_ae_configure(st_handle* h, const StDims& d, const AeGeom& g);
+void st_launch_ae_forward(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
+                          const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri,
+                          float* const* acts_dev, int grid, cudaStream_t s);
+void st_launch_ae_backward(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
+                           const float* knobs, int B, const float* mag_hat, const float* phs_hat, const float* g_ri,
+                           const float* g_mag_hat, const float* g_mag, float* g_spec, float* partials, int grid,
+                           cudaStream_t s);
+void st_launch_ae_grad_reduce(const AeGeom& g, const float* partials, int ncta, const AeGrads& gm, const AeGrads& gp,
+                              cudaStream_t s);
+
+// st_loss_opt.cu
+void st_launch_loss(const StDims& d, const float* y_hat, const float* y, const float* mag_hat, const float* sbf,
+                    float l1_coef, int B, float* loss, float* g_y_hat, float* g_mag_hat, float* scratch,
+                    unsigned* counter, cudaStream_t s);
+void st_launch_mae(const float* a, const float* b, long n, float* out, float* scratch, unsigned* counter, cudaStream_t s);
+void st_launch_l1_norm4(const float* const g[4], long n_each, long live_rows_a, long row_len, float grad_scale,
+                        float max_norm, float* norm_out, float* coef_out, float* scratch, unsigned* counter, cudaStream_t s);
+void st_launch_scale4(float* const g[4], long n_each, const float* coef, cudaStream_t s);
+
+struct AdamTensors {
+    float* p[ST_NUM_PARAMS];
+    const float* g[ST_NUM_PARAMS];
+    float* m[ST_NUM_PARAMS];
+    float* v[ST_NUM_PARAMS];
+    long n[ST_NUM_PARAMS];       // live elements (DFT analysis tensors: F*N, rows >= F never change)
+};
+struct AdamScalars {
+    float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, grad_scale;
+};
+void st_launch_adam(const AdamTensors& t, const int2* chunk_map, int nchunks, const AdamScalars& sc,
+                    const float* clip_coef, cudaStream_t s);
+#define ST_ADAM_CHUNK 4096

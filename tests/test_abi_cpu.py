@@ -1,0 +1,66 @@
+"""CPU-side checks of the boundary: the shared library loads and exports every symbol the header declares,
+the Python binding names the same set, and the product path refuses to run without a GPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "signaltrain_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(st_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_binding_and_library_agree():
+    from signaltrain_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    hdr = _header_symbols()
+    assert len(hdr) >= 20
+    assert hdr == _lib.exported_symbols()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in hdr:
+        assert hasattr(lib, s), s
+    lib.st_abi_version.restype = ctypes.c_int
+    assert lib.st_abi_version() == 1
+
+
+def test_sass_is_sm100a_only():
+    from signaltrain_b200 import _lib
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    import signaltrain_b200 as st
+    model = st.nn_proc.st_model(1, 4, 4)
+    x = torch.zeros(2, model.in_chunk_size)
+    k = torch.zeros(2, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.forward(x, k)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        st.loss_functions.calc_loss(torch.zeros(2, 2048), torch.zeros(2, 2048), torch.zeros(2, 9, 513))
+
+
+def test_model_surface_matches_reference_contract():
+    """attribute names, state_dict keys and shapes."""
+    import signaltrain_b200 as st
+    from oracle import st_oracle as O
+    for scale, K in ((1, 4), (2, 2), (1, 1)):
+        m = st.nn_proc.st_model(scale_factor=scale, shrink_factor=4, num_knobs=K)
+        d = O.model_dims(scale, 4, K)
+        assert (m.in_chunk_size, m.out_chunk_size, m.num_knobs) == (d.C, d.L, K)
+        assert (m.scale_factor, m.shrink_factor) == (scale, 4)
+        sd = m.state_dict()
+        assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(s)) for k, s in O.param_order(d)]
+        assert m.mpaec.dft_analysis.conv_analysis_real.weight.shape == (1024, 1, 1024)
+        assert hasattr(m, "clip_grad_norm_") and hasattr(m.mpaec, "clip_grad_norm_")
