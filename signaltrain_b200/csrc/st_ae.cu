@@ -548,9 +548,11 @@ int st_ae_configure(st_handle* h, const StDims& d, const AeGeom& g) {
     if (sf > 227 * 1024 || sb > 227 * 1024)
         return st_fail_msg(h, "autoencoder tile does not fit shared memory (fwd %zu B, bwd %zu B > 227 KiB): T=%d OT=%d too large",
                            sf, sb, d.T, d.OT);
-    cudaError_t e = cudaFuncSetAttribute(ae_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf);
+    // the attribute is per function (not per handle): always opt in to the full 227 KiB so handles with
+    // different geometries can coexist in one process
+    cudaError_t e = cudaFuncSetAttribute(ae_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return st_fail_cuda(h, e, "cudaFuncSetAttribute(ae_forward_kernel)", __FILE__, __LINE__);
-    e = cudaFuncSetAttribute(ae_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+    e = cudaFuncSetAttribute(ae_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return st_fail_cuda(h, e, "cudaFuncSetAttribute(ae_backward_kernel)", __FILE__, __LINE__);
     return 0;
 }

@@ -1,6 +1,7 @@
 """Thin host wrapper over one st_handle: torch tensors in, kernels launched on torch's current stream.
 PyTorch is used for device memory and streams only; all arithmetic of the path runs in the CUDA library."""
 import ctypes
+import weakref
 
 import numpy as np
 import torch
@@ -56,6 +57,18 @@ class Geometry:
 
 
 class Engine:
+    _registry = []          # weak references to live engines (loss_functions looks engines up by shape)
+
+    @classmethod
+    def find(cls, device, L, OT=None, F=None):
+        for ref in list(cls._registry):
+            e = ref()
+            if e is None:
+                cls._registry.remove(ref)
+            elif e.device == device and e.g.L == L and (OT is None or (e.g.OT, e.g.F) == (OT, F)):
+                return e
+        return None
+
     def __init__(self, geom: Geometry, device):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
@@ -75,6 +88,7 @@ class Engine:
         self.param_names = [self.lib.st_param_name(h, i).decode() for i in range(NUM_PARAMS)]
         self.param_numel = [self.lib.st_param_numel(h, i) for i in range(NUM_PARAMS)]
         self._table_cache = {}
+        Engine._registry.append(weakref.ref(self))
 
     def __del__(self):
         try:

@@ -12,7 +12,10 @@ def _engine_like(y_hat, mag_hat=None):
     through L and (OT, F), which are read off the tensor shapes)."""
     if not y_hat.is_cuda:
         raise RuntimeError("signaltrain_b200.loss_functions: CUDA tensors only (no CPU fallback)")
-    from .nn_proc import AsymMPAEC  # noqa: F401  (engines are shared with models when one exists)
+    dev = y_hat.device if y_hat.device.index is not None else torch.device("cuda", torch.cuda.current_device())
+    found = Engine.find(dev, int(y_hat.shape[1]), *((int(mag_hat.shape[1]), int(mag_hat.shape[2])) if mag_hat is not None else ()))
+    if found is not None:          # tensors produced by a model on this device: share its engine
+        return found
     key = (y_hat.device.index, tuple(y_hat.shape[1:]), None if mag_hat is None else tuple(mag_hat.shape[1:]))
     eng = _engines.get(key)
     if eng is None:
