@@ -162,7 +162,9 @@ def run_native(args):
     B, K, Wm = args.batch, args.steps, max(3, args.warmup)
 
     torch.manual_seed(218)
-    model = st.nn_proc.st_model(scale_factor=CHUNK_SCALE, shrink_factor=SHRINK, num_knobs=KNOBS, sr=SR).to(dev)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # stdout carries exactly one JSON line
+        model = st.nn_proc.st_model(scale_factor=CHUNK_SCALE, shrink_factor=SHRINK, num_knobs=KNOBS, sr=SR).to(dev)
     C, L = model.in_chunk_size, model.out_chunk_size
     lr_sched, _ = st.learningrate.get_1cycle_schedule(lr_max=1e-4, n_data_points=200000, epochs=1000, batch_size=200)
     trainer = FusedTrainer(model, lr_sched)

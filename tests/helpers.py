@@ -40,3 +40,12 @@ def initial_params(g, d):
 def dft_summary(a, N):
     a = np.asarray(a).reshape(N, -1)
     return a[DFT_ROWS], np.array([np.abs(a.astype(np.float64)).sum(), a.astype(np.float64).sum()])
+
+
+def assert_params_close_after_adam(got, ref, name, atol=3e-6, hard=2.5e-5, frac=2e-3):
+    """Parameters after a few Adam steps.  Adam moves every weight by ~lr per step whatever the gradient's size,
+    so a weight whose gradient is at fp32-noise level can take a step of the opposite sign in two correct
+    implementations: allow a fraction `frac` of elements to differ by up to `hard` (~ steps * 2 * lr)."""
+    diff = np.abs(np.asarray(got, dtype=np.float64) - np.asarray(ref, dtype=np.float64))
+    assert diff.max() <= hard, (name, diff.max())
+    assert (diff > atol).mean() <= frac, (name, (diff > atol).mean(), diff.max())
