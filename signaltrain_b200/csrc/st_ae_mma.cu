@@ -1,0 +1,326 @@
+// Autoencoder forward on the tensor cores (the production path; st_ae.cu's SIMT kernel serves return_acts).
+//
+// The nine Linear layers of AsymAutoEncoder (nn_proc.py:47-57,79-121) are genuine dense contractions over
+// rows = (batch, bin) pairs, but with tiny K/N (9..64).  tcgen05 would bounce every layer through
+// TMEM -> registers (bias+ELU) -> shared memory -> next MMA; instead each warp keeps its 32 rows' activations
+// in REGISTERS for the whole chain and uses warp-level mma.sync.m16n8k8 (TF32 operands, FP32 accumulate):
+//   * the C fragment of layer l (row g|g+8, cols 2t,2t+1 of n-tile j) is, element for element, the A fragment
+//     of layer l+1 for k-step j if the contraction index is permuted (col t <-> feature 8j+2t, col t+4 <->
+//     8j+2t+1); the matching B fragment is then the adjacent pair W[8n+g][8j+2t .. +1] of the reference's
+//     row-major weight: one 64-bit shared load.  No shuffles, no shared-memory round trip for activations.
+//   * fp32 fidelity: every product is 3xTF32 (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, small terms first); weights are
+//     pre-split once per CTA while staging them into shared memory.
+// One launch per autoencoder: the magnitude launch writes mag and mag_hat, the phase launch reads mag_hat and
+// finishes polar->rect (nn_proc.py:322-326).  HBM traffic stays at the algorithmic minimum (+ one re-read of the
+// spectrum, L2-resident at these sizes).
+#include <algorithm>
+
+#include "st_common.cuh"
+
+namespace {
+
+constexpr int WARPS = 4;                 // 128 threads; 32 rows per warp
+constexpr int ROWS_PER_WARP = 32;
+
+struct MmaGeom {
+    int inp[ST_AE_LAYERS];     // contraction length padded to a multiple of 8 (layer 5: 16 + 16 knob slots)
+    int outp[ST_AE_LAYERS];    // outputs padded to a multiple of 8
+    int ld[ST_AE_LAYERS];      // smem row stride: >= inp, == 8 or 24 (mod 32) -> conflict-free 64-bit fragment loads
+    int off[ST_AE_LAYERS];     // float offset of W_l inside one (hi or lo) block
+    int boff[ST_AE_LAYERS];    // float offset of bias_l inside the bias block
+    int wfloats;               // floats per (hi or lo) block
+    int bfloats;
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// ELU(alpha=1).  exp through MUFU.EX2 (__expf): abs error <= ~3e-7 on outputs in (-1, 0], far inside the 1e-5 waveform
+// budget ("precision"); expm1f would cost ~6x the instructions of the MMAs it sits between.
+__device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : __expf(z) - 1.f; }
+
+// c[mt][n][.] (+)= sum_j a[mt][j][.] * W[8n+g][8j+2t..]   for one layer; accumulators start at the bias.
+template <int KS, int NT>
+__device__ __forceinline__ void mma_layer(const float (&a)[2][KS][4], float (&c)[2][NT][4], const float* __restrict__ whi,
+                                          const float* __restrict__ wlo, int ld, const float* __restrict__ bias, int g,
+                                          int t) {
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        const float2 bb = *reinterpret_cast<const float2*>(bias + 8 * n + 2 * t);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) { c[mt][n][0] = bb.x; c[mt][n][1] = bb.y; c[mt][n][2] = bb.x; c[mt][n][3] = bb.y; }
+    }
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+        uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_tf32(a[mt][j][e], ahi[mt][e], alo[mt][e]);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const int o = (8 * n + g) * ld + 8 * j + 2 * t;
+            const float2 bh = *reinterpret_cast<const float2*>(whi + o);
+            const float2 bl = *reinterpret_cast<const float2*>(wlo + o);
+            const uint32_t bh0 = __float_as_uint(bh.x), bh1 = __float_as_uint(bh.y);
+            const uint32_t bl0 = __float_as_uint(bl.x), bl1 = __float_as_uint(bl.y);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], alo[mt], bh0, bh1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], ahi[mt], bl0, bl1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], ahi[mt], bh0, bh1);
+        }
+    }
+}
+
+// ELU, then re-label the C fragments as the next layer's A fragments (a0,a1,a2,a3 = c0,c2,c1,c3).
+template <int NT>
+__device__ __forceinline__ void to_next(const float (&c)[2][NT][4], float (&a)[2][NT][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            a[mt][n][0] = elu_f(c[mt][n][0]);
+            a[mt][n][1] = elu_f(c[mt][n][2]);
+            a[mt][n][2] = elu_f(c[mt][n][1]);
+            a[mt][n][3] = elu_f(c[mt][n][3]);
+        }
+}
+
+// Stage one AE's weights into shared memory, split into tf32 hi / lo parts, zero padded.
+__device__ void stage_weights_mma(const MmaGeom& mg, const AeGeom& g, const AeParams& p, float* whi, float* wlo, float* bias,
+                                  int tid, int nthreads) {
+    for (int l = 0; l < ST_AE_LAYERS; ++l) {
+        const int IN = g.in[l], OUT = g.out[l], ld = mg.ld[l];
+        const int total = mg.outp[l] * ld;
+        for (int idx = tid; idx < total; idx += nthreads) {
+            const int o = idx / ld, i = idx - o * ld;
+            float w = 0.f;
+            if (o < OUT && i < IN) w = p.W[l][o * IN + i];
+            uint32_t hi, lo;
+            split_tf32(w, hi, lo);
+            whi[mg.off[l] + idx] = __uint_as_float(hi);
+            wlo[mg.off[l] + idx] = __uint_as_float(lo);
+        }
+        for (int o = tid; o < mg.outp[l]; o += nthreads) bias[mg.boff[l] + o] = (o < OUT) ? p.b[l][o] : 0.f;
+    }
+}
+
+struct Rows {            // the four row slots of a thread: [mt][half]  (row = R0 + 16 mt + g + 8 half)
+    int b[2][2], f[2][2];
+    bool ok[2][2];
+};
+
+// AE = 0: magnitude autoencoder ('sf' skip-filter).  AE = 1: phase autoencoder + residual + polar->rect.
+template <int KS1, int NT9, int AE>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __restrict__ spec,
+                  const float* __restrict__ knobs, int B, float* __restrict__ mag_out, float* __restrict__ mag_hat,
+                  float* __restrict__ phs_hat, float* __restrict__ ri) {
+    extern __shared__ __align__(16) float smem[];
+    float* whi = smem;
+    float* wlo = whi + mg.wfloats;
+    float* bias = wlo + mg.wfloats;
+    stage_weights_mma(mg, g, p, whi, wlo, bias, threadIdx.x, blockDim.x);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gq = lane >> 2, t = lane & 3;
+    const long BF = (long)B * d.F;
+    const long ntiles = (BF + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
+    const int tail0 = d.T - d.OT;
+    const int rowstride = 2 * d.Fp;
+
+    for (long tile = (long)blockIdx.x * WARPS + warp; tile < ntiles; tile += (long)gridDim.x * WARPS) {
+        const long R0 = tile * ROWS_PER_WARP;
+        Rows rw;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long R = R0 + 16 * mt + gq + 8 * h;
+                rw.ok[mt][h] = R < BF;
+                const long Rc = rw.ok[mt][h] ? R : 0;
+                rw.b[mt][h] = (int)(Rc / d.F);
+                rw.f[mt][h] = (int)(Rc - (long)rw.b[mt][h] * d.F);
+            }
+        // ---- input tracks as layer-1 A fragments: a[mt][j] = {V[g][8j+2t], V[g+8][8j+2t], V[g][8j+2t+1], V[g+8][8j+2t+1]}
+        float a1[2][KS1][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int j = 0; j < KS1; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int h = e & 1, tt = 8 * j + 2 * t + (e >> 1);
+                    float v = 0.f;
+                    if (rw.ok[mt][h] && tt < d.T) {
+                        const long o = ((long)rw.b[mt][h] * d.T + tt) * rowstride + rw.f[mt][h];
+                        const float re = __ldg(spec + o), im = __ldg(spec + o + d.Fp);
+                        if (AE == 0) {
+                            v = sqrtf(re * re + im * im);                                  // nn_proc.py:309
+                            if (mag_out) mag_out[((long)rw.b[mt][h] * d.T + tt) * d.F + rw.f[mt][h]] = v;
+                        } else {
+                            v = atan2f(im, re + 1e-7f);                                    // nn_proc.py:310
+                        }
+                    }
+                    a1[mt][j][e] = v;
+                }
+        // ---- layers 1..8 (fnn_enc .. fnn_dec2), ELU after each
+        float c1[2][8][4];
+        mma_layer<KS1, 8>(a1, c1, whi + mg.off[0], wlo + mg.off[0], mg.ld[0], bias + mg.boff[0], gq, t);
+        float a2[2][8][4];
+        to_next<8>(c1, a2);
+        float c2[2][4][4];
+        mma_layer<8, 4>(a2, c2, whi + mg.off[1], wlo + mg.off[1], mg.ld[1], bias + mg.boff[1], gq, t);
+        float a3[2][4][4];
+        to_next<4>(c2, a3);
+        float c3[2][2][4];
+        mma_layer<4, 2>(a3, c3, whi + mg.off[2], wlo + mg.off[2], mg.ld[2], bias + mg.boff[2], gq, t);
+        float a4[2][2][4];
+        to_next<2>(c3, a4);
+        float c4[2][2][4];
+        mma_layer<2, 2>(a4, c4, whi + mg.off[3], wlo + mg.off[3], mg.ld[3], bias + mg.boff[3], gq, t);
+        // fnn_addknobs input: 16 features ++ knobs (torch.cat, nn_proc.py:95-96) as two extra k-steps (<=16 knobs)
+        float a5[2][4][4];
+        {
+            float tmp[2][2][4];
+            to_next<2>(c4, tmp);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) a5[mt][j][e] = tmp[mt][j][e];
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int h = e & 1, kk = 8 * s + 2 * t + (e >> 1);
+                        a5[mt][2 + s][e] = (rw.ok[mt][h] && kk < d.K) ? __ldg(knobs + (long)rw.b[mt][h] * d.K + kk) : 0.f;
+                    }
+            }
+        }
+        float c5[2][2][4];
+        mma_layer<4, 2>(a5, c5, whi + mg.off[4], wlo + mg.off[4], mg.ld[4], bias + mg.boff[4], gq, t);
+        float a6[2][2][4];
+        to_next<2>(c5, a6);
+        float c6[2][2][4];
+        mma_layer<2, 2>(a6, c6, whi + mg.off[5], wlo + mg.off[5], mg.ld[5], bias + mg.boff[5], gq, t);
+        float a7[2][2][4];
+        to_next<2>(c6, a7);
+        float c7[2][4][4];
+        mma_layer<2, 4>(a7, c7, whi + mg.off[6], wlo + mg.off[6], mg.ld[6], bias + mg.boff[6], gq, t);
+        float a8[2][4][4];
+        to_next<4>(c7, a8);
+        float c8[2][8][4];
+        mma_layer<4, 8>(a8, c8, whi + mg.off[7], wlo + mg.off[7], mg.ld[7], bias + mg.boff[7], gq, t);
+        float a9[2][8][4];
+        to_next<8>(c8, a9);
+        // ---- fnn_dec + output-side math
+        float c9[2][NT9][4];
+        mma_layer<8, NT9>(a9, c9, whi + mg.off[8], wlo + mg.off[8], mg.ld[8], bias + mg.boff[8], gq, t);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int n = 0; n < NT9; ++n)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int h = e >> 1, j = 8 * n + 2 * t + (e & 1);      // C fragment: c0,c1 row g; c2,c3 row g+8
+                    if (j >= d.OT || !rw.ok[mt][h]) continue;
+                    const float ev = elu_f(c9[mt][n][e]);
+                    const int b = rw.b[mt][h], f = rw.f[mt][h];
+                    const long os = ((long)b * d.T + tail0 + j) * rowstride + f;
+                    const float re = __ldg(spec + os), im = __ldg(spec + os + d.Fp);
+                    const long oo = ((long)b * d.OT + j) * d.F + f;
+                    if (AE == 0) {
+                        mag_hat[oo] = ev * sqrtf(re * re + im * im);                         // 'sf', nn_proc.py:115
+                    } else {
+                        const float ph = ev + atan2f(im, re + 1e-7f);                       // nn_proc.py:322
+                        const float m = mag_hat[oo];
+                        float sn, cs;
+                        sincosf(ph, &sn, &cs);
+                        phs_hat[oo] = ph;
+                        const long orr = ((long)b * d.OT + j) * rowstride + f;
+                        ri[orr] = m * cs;                                                   // nn_proc.py:325-326
+                        ri[orr + d.Fp] = m * sn;
+                    }
+                }
+    }
+}
+
+int pick_ld(int inp) {
+    int ld = inp;
+    while ((ld & 31) != 8 && (ld & 31) != 24) ++ld;
+    return ld;
+}
+
+MmaGeom build_mma_geom(const AeGeom& g) {
+    MmaGeom mg;
+    int off = 0, boff = 0;
+    for (int l = 0; l < ST_AE_LAYERS; ++l) {
+        int inp = (g.in[l] + 7) / 8 * 8;
+        if (l == 4) inp = 32;                       // 16 features + two knob k-steps
+        mg.inp[l] = inp;
+        mg.outp[l] = (g.out[l] + 7) / 8 * 8;
+        mg.ld[l] = pick_ld(inp);
+        mg.off[l] = off;
+        off += mg.outp[l] * mg.ld[l];
+        mg.boff[l] = boff;
+        boff += mg.outp[l];
+    }
+    mg.wfloats = (off + 3) / 4 * 4;
+    mg.bfloats = (boff + 3) / 4 * 4;
+    return mg;
+}
+
+template <int KS1, int NT9>
+void launch_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const AeParams& pm, const AeParams& pp, const float* spec,
+                 const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, int grid, size_t smem,
+                 cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(ae_fwd_mma_kernel<KS1, NT9, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaFuncSetAttribute(ae_fwd_mma_kernel<KS1, NT9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        configured = true;
+    }
+    ae_fwd_mma_kernel<KS1, NT9, 0><<<grid, WARPS * 32, smem, s>>>(d, g, mg, pm, spec, knobs, B, mag, mag_hat, phs_hat, ri);
+    ae_fwd_mma_kernel<KS1, NT9, 1><<<grid, WARPS * 32, smem, s>>>(d, g, mg, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri);
+}
+
+}  // namespace
+
+// mag may be a scratch buffer when the caller does not need it (it is always written).
+// Returns false when the geometry is outside what the tensor-core kernels cover (caller uses the SIMT kernel).
+bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
+                              const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, int sm_count,
+                              cudaStream_t s) {
+    if (d.T > 64 || d.OT > 64 || d.K > 16) return false;
+    const MmaGeom mg = build_mma_geom(g);
+    const size_t smem = sizeof(float) * (2L * mg.wfloats + mg.bfloats);
+    if (smem > 113 * 1024) return false;
+    const long tiles = ((long)B * d.F + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
+    const int grid = (int)std::min<long>((tiles + WARPS - 1) / WARPS, 2L * sm_count);
+    const int ks1 = d.T <= 32 ? 4 : (d.T <= 48 ? 6 : 8);
+    const int nt9 = d.OT <= 16 ? 2 : (d.OT <= 32 ? 4 : 8);
+#define ST_CASE(K, N)                                                                                                   \
+    if (ks1 == K && nt9 == N) {                                                                                         \
+        launch_pair<K, N>(d, g, mg, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, grid, smem, s);                  \
+        return true;                                                                                                    \
+    }
+    ST_CASE(4, 2) ST_CASE(4, 4) ST_CASE(6, 2) ST_CASE(6, 4) ST_CASE(6, 8) ST_CASE(8, 2) ST_CASE(8, 4) ST_CASE(8, 8)
+#undef ST_CASE
+    return false;
+}

@@ -330,10 +330,13 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
     }
     ST_LAUNCH_OK(h);
     {
-        StageScope sc(h, SG_AE_FWD, 1 + (mag_hat_user != nullptr), s);
+        StageScope sc(h, SG_AE_FWD, (acts ? 1 : 2) + (mag_hat_user != nullptr), s);
         AeParams pm, pp;
         split_params(params, pm, pp);
-        st_launch_ae_forward(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, acts, h->ae_grid, s);
+        // production path: tensor-core (mma.sync TF32x3) register-resident chain; the SIMT kernel serves return_acts
+        if (acts || !st_launch_ae_forward_mma(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri,
+                                              h->sm_count, s))
+            st_launch_ae_forward(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, acts, h->ae_grid, s);
         if (mag_hat_user)
             ST_CUDA_OK(cudaMemcpyAsync(mag_hat_user, h->mag_hat_ws, (long)B * d.OT * d.F * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }

@@ -103,6 +103,11 @@ void st_launch_ae_backward(const StDims& d, const AeGeom& g, const AeParams& pm,
 void st_launch_ae_grad_reduce(const AeGeom& g, const float* partials, int ncta, const AeGrads& gm, const AeGrads& gp,
                               cudaStream_t s);
 
+// st_ae_mma.cu (tensor-core forward; returns false if the geometry is not covered)
+bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
+                              const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, int sm_count,
+                              cudaStream_t s);
+
 // st_loss_opt.cu
 void st_launch_loss(const StDims& d, const float* y_hat, const float* y, const float* mag_hat, const float* sbf,
                     float l1_coef, int B, float* loss, float* g_y_hat, float* g_mag_hat, float* scratch,

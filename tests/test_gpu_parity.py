@@ -80,6 +80,14 @@ def test_forward_vs_oracle_and_golden(case):
     np.testing.assert_allclose(c(acts[29]), fw["y_half"], atol=WAVE_TOL)
     np.testing.assert_allclose(c(y_hat), fw["y_hat"], atol=WAVE_TOL)
     np.testing.assert_allclose(c(y_hat), g["step0/y_hat"], atol=WAVE_TOL)       # the reference itself
+    # production path (return_acts=False): tensor-core autoencoder kernels
+    y2, mag2, mh2, _ = eng.forward(_t(x), _t(knobs), _dev_params(P, d))
+    np.testing.assert_allclose(c(y2), fw["y_hat"], atol=WAVE_TOL)
+    np.testing.assert_allclose(c(y2), g["step0/y_hat"], atol=WAVE_TOL)
+    np.testing.assert_allclose(c(mag2), fw["mag"], atol=SPEC_TOL, rtol=SPEC_RTOL)
+    np.testing.assert_allclose(c(mh2), fw["mag_hat"], atol=2e-5)
+    np.testing.assert_allclose(eng.debug_read("phs_hat").reshape(fw["phs_hat"].shape)[fw["mag_hat"] > 1e-3],
+                               fw["phs_hat"][fw["mag_hat"] > 1e-3], atol=2e-3)
     np.testing.assert_allclose(c(mag_hat), g["step0/mag_hat"], atol=2e-5)
     np.testing.assert_allclose(c(mag), g["step0/mag"], atol=SPEC_TOL, rtol=SPEC_RTOL)
 
