@@ -124,6 +124,12 @@ int st_profile_read(st_handle* h, float* ms, long* calls);
 /* Test/diagnostic access to workspace buffers by name ("spec", "ri", "frames_out", "g_ri", "g_spec",
  * "wcat", "sfold").  Copies up to n floats to a HOST buffer, synchronising the device. */
 int st_debug_read(st_handle* h, const char* name, float* dst_host, long n);
+/* Test hook: C[M,N] = A*B on (hi, lo) tf32-pair operands through the tcgen05 (use_tc=1) or FFMA (use_tc=0) kernel.
+ * a_mn/b_mn: 0 = K-major [row][k], 1 = MN-major [k][row]; rows may overlap (ld < row length).  Split-K planes are
+ * written M*ldc apart; returns their number or -1 if the shape is not covered. */
+int st_debug_gemm(st_handle* h, int use_tc, int a_mn, int b_mn, const float* a_hi, const float* a_lo, long a_ld,
+                  const float* b_hi, const float* b_lo, long b_ld, float* C, long ldc, int M, int N, int K, int splits,
+                  void* stream);
 long st_debug_numel(st_handle* h, const char* name);
 
 #ifdef __cplusplus

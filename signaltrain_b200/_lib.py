@@ -51,6 +51,9 @@ _SIGNATURES = {
     "st_profile_stage_name": (ctypes.c_char_p, [ctypes.c_int]),
     "st_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "st_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_long)]),
+    "st_debug_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, c_float_p, ctypes.c_long,
+                                     c_float_p, c_float_p, ctypes.c_long, c_float_p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "st_debug_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_long]),
     "st_debug_numel": (ctypes.c_long, [ctypes.c_void_p, ctypes.c_char_p]),
 }

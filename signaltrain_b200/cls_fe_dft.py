@@ -29,11 +29,14 @@ def lsee_synthesis_window(wsz, hop):
 
 
 def ortho_dft_rows(n):
-    """Real and imaginary parts of the unitary DFT matrix exp(-2 pi i k m / n)/sqrt(n), evaluated with the
-    integer product k*m reduced mod n so every entry is accurate to double rounding."""
-    km = np.outer(np.arange(n), np.arange(n)) % n
-    ang = 2.0 * np.pi * km / n
-    return np.cos(ang) / np.sqrt(n), -np.sin(ang) / np.sqrt(n)
+    """Real and imaginary parts of the unitary DFT matrix exp(-2 pi i k m / n)/sqrt(n).
+
+    Taken from numpy's FFT of the identity, as the reference does (cls_fe_dft.py:37), rather than from cos/sin:
+    rows k = 0 and k = n/2 of the imaginary part are pure rounding residue (~1e-17), and the SIGN of that residue
+    decides whether atan2 returns +pi or -pi for those two bins (nn_proc.py:310).  Bit-identical residue is what
+    makes a model built here train exactly like one built by the reference from the same seed."""
+    f = np.fft.fft(np.eye(n), norm="ortho")
+    return f.real, f.imag
 
 
 class _FrontEnd(nn.Module):

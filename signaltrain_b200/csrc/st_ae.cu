@@ -122,7 +122,7 @@ __device__ __forceinline__ void load_tracks(const StDims& d, const float* __rest
     for (int t = tq; t < d.T; t += NT / ROWS) {
         float mg = 0.f, ph = 0.f;
         if (ok) {
-            const long o = ((long)b * d.T + t) * (2 * d.Fp) + f;
+            const long o = ((long)b * d.Tp + t) * (2 * d.Fp) + f;
             const float re = spec[o], im = spec[o + d.Fp];
             if (which != 1) mg = sqrtf(re * re + im * im);                   // nn_proc.py:309
             if (which != 0) ph = atan2f(im, re + 1e-7f);                     // nn_proc.py:310
@@ -203,7 +203,7 @@ __device__ __forceinline__ void ae_hidden_chain(const StDims& d, const AeGeom& g
 __global__ void __launch_bounds__(NT, 1)
 ae_forward_kernel(StDims d, AeGeom g, AeParams pm, AeParams pp, const float* __restrict__ spec,
                   const float* __restrict__ knobs, int B, float* __restrict__ mag, float* __restrict__ mag_hat,
-                  float* __restrict__ phs_hat, float* __restrict__ ri, ActsDev acts) {
+                  float* __restrict__ phs_hat, float* __restrict__ ri, float* __restrict__ ri_lo, ActsDev acts) {
     extern __shared__ __align__(16) float smem[];
     float* wtm = smem;
     float* wtp = wtm + g.wt_floats;
@@ -269,10 +269,10 @@ ae_forward_kernel(StDims d, AeGeom g, AeParams pm, AeParams pp, const float* __r
                     float sn, cs;
                     sincosf(ph, &sn, &cs);
                     const long oo = ((long)rm.b[r] * d.OT + j) * d.F + rm.f[r];
-                    const long or_ = ((long)rm.b[r] * d.OT + j) * (2 * d.Fp) + rm.f[r];
+                    const long or_ = ((long)rm.b[r] * d.OTp + j) * (2 * d.Fp) + rm.f[r];
                     phs_hat[oo] = ph;
-                    ri[or_] = m * cs;
-                    ri[or_ + d.Fp] = m * sn;
+                    st_split_tf32(m * cs, ri[or_], ri_lo[or_]);
+                    st_split_tf32(m * sn, ri[or_ + d.Fp], ri_lo[or_ + d.Fp]);
                     if (dump) {
                         acts.p[23][(rm.g0 + r) * d.OT + j] = e;
                         acts.p[25][oo] = ph; acts.p[26][oo] = m * cs; acts.p[27][oo] = m * sn;
@@ -352,7 +352,7 @@ ae_backward_kernel(StDims d, AeGeom g, AeParams pm, AeParams pp, const float* __
                    const float* __restrict__ knobs, int B, const float* __restrict__ mag_hat,
                    const float* __restrict__ phs_hat, const float* __restrict__ g_ri,
                    const float* __restrict__ g_mag_hat, const float* __restrict__ g_mag, float* __restrict__ g_spec,
-                   float* __restrict__ partials) {
+                   float* __restrict__ g_spec_lo, float* __restrict__ partials) {
     extern __shared__ __align__(16) float smem[];
     float* wt = smem;
     float* wb = wt + g.wt_floats;
@@ -408,7 +408,7 @@ ae_backward_kernel(StDims d, AeGeom g, AeParams pm, AeParams pp, const float* __
                         if (!rm.ok[r]) continue;
                         const float e = elu_f(f4get(z, r) + bb);
                         const long oo = ((long)rm.b[r] * d.OT + j) * d.F + rm.f[r];
-                        const long or_ = ((long)rm.b[r] * d.OT + j) * (2 * d.Fp) + rm.f[r];
+                        const long or_ = ((long)rm.b[r] * d.OTp + j) * (2 * d.Fp) + rm.f[r];
                         const float gre = g_ri[or_], gim = g_ri[or_ + d.Fp];
                         float sn, cs;
                         sincosf(phs_hat[oo], &sn, &cs);
@@ -481,7 +481,7 @@ ae_backward_kernel(StDims d, AeGeom g, AeParams pm, AeParams pp, const float* __
                 for (int r = 0; r < 4; ++r) {
                     if (!rm.ok[r]) continue;
                     float gv = f4get(gv4, r) + f4get(tl, r);
-                    const long o = ((long)rm.b[r] * d.T + t) * (2 * d.Fp) + rm.f[r];
+                    const long o = ((long)rm.b[r] * d.Tp + t) * (2 * d.Fp) + rm.f[r];
                     const float re = spec[o], im = spec[o + d.Fp];
                     if (ae == 0) {          // mag = sqrt(re^2+im^2); subgradient 0 at 0 (torch.norm backward)
                         if (g_mag) gv += g_mag[((long)rm.b[r] * d.T + t) * d.F + rm.f[r]];
@@ -493,8 +493,9 @@ ae_backward_kernel(StDims d, AeGeom g, AeParams pm, AeParams pp, const float* __
                         const float u = re + 1e-7f;
                         const float den = u * u + im * im;
                         const float s = den > 0.f ? gv / den : 0.f;
-                        g_spec[o] += -s * im;
-                        g_spec[o + d.Fp] += s * u;
+                        // second pass over this element: finish the sum and store it as the wgrad GEMM's (hi, lo) operand
+                        st_split_tf32(g_spec[o] - s * im, g_spec[o], g_spec_lo[o]);
+                        st_split_tf32(g_spec[o + d.Fp] + s * u, g_spec[o + d.Fp], g_spec_lo[o + d.Fp]);
                     }
                 }
             });
@@ -558,19 +559,19 @@ int st_ae_configure(st_handle* h, const StDims& d, const AeGeom& g) {
 }
 
 void st_launch_ae_forward(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
-                          const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri,
+                          const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo,
                           float* const* acts_host, int grid, cudaStream_t s) {
     ActsDev acts;
     for (int i = 0; i < ST_NUM_ACTS; ++i) acts.p[i] = acts_host ? acts_host[i] : nullptr;
-    ae_forward_kernel<<<grid, NT, st_ae_fwd_smem(d, g), s>>>(d, g, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, acts);
+    ae_forward_kernel<<<grid, NT, st_ae_fwd_smem(d, g), s>>>(d, g, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, acts);
 }
 
 void st_launch_ae_backward(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
                            const float* knobs, int B, const float* mag_hat, const float* phs_hat, const float* g_ri,
-                           const float* g_mag_hat, const float* g_mag, float* g_spec, float* partials, int grid,
-                           cudaStream_t s) {
+                           const float* g_mag_hat, const float* g_mag, float* g_spec, float* g_spec_lo, float* partials,
+                           int grid, cudaStream_t s) {
     ae_backward_kernel<<<grid, NT, st_ae_bwd_smem(d, g), s>>>(d, g, pm, pp, spec, knobs, B, mag_hat, phs_hat, g_ri,
-                                                               g_mag_hat, g_mag, g_spec, partials);
+                                                               g_mag_hat, g_mag, g_spec, g_spec_lo, partials);
 }
 
 void st_launch_ae_grad_reduce(const AeGeom& g, const float* partials, int ncta, const AeGrads& gm, const AeGrads& gp,

@@ -128,7 +128,7 @@ template <int KS1, int NT9, int AE>
 __global__ void __launch_bounds__(WARPS * 32, 2)
 ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __restrict__ spec,
                   const float* __restrict__ knobs, int B, float* __restrict__ mag_out, float* __restrict__ mag_hat,
-                  float* __restrict__ phs_hat, float* __restrict__ ri) {
+                  float* __restrict__ phs_hat, float* __restrict__ ri, float* __restrict__ ri_lo) {
     extern __shared__ __align__(16) float smem[];
     float* whi = smem;
     float* wlo = whi + mg.wfloats;
@@ -167,7 +167,7 @@ ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
                     const int h = e & 1, tt = 8 * j + 2 * t + (e >> 1);
                     float v = 0.f;
                     if (rw.ok[mt][h] && tt < d.T) {
-                        const long o = ((long)rw.b[mt][h] * d.T + tt) * rowstride + rw.f[mt][h];
+                        const long o = ((long)rw.b[mt][h] * d.Tp + tt) * rowstride + rw.f[mt][h];
                         const float re = __ldg(spec + o), im = __ldg(spec + o + d.Fp);
                         if (AE == 0) {
                             v = sqrtf(re * re + im * im);                                  // nn_proc.py:309
@@ -242,7 +242,7 @@ ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
                     if (j >= d.OT || !rw.ok[mt][h]) continue;
                     const float ev = elu_f(c9[mt][n][e]);
                     const int b = rw.b[mt][h], f = rw.f[mt][h];
-                    const long os = ((long)b * d.T + tail0 + j) * rowstride + f;
+                    const long os = ((long)b * d.Tp + tail0 + j) * rowstride + f;
                     const float re = __ldg(spec + os), im = __ldg(spec + os + d.Fp);
                     const long oo = ((long)b * d.OT + j) * d.F + f;
                     if (AE == 0) {
@@ -253,9 +253,9 @@ ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
                         float sn, cs;
                         sincosf(ph, &sn, &cs);
                         phs_hat[oo] = ph;
-                        const long orr = ((long)b * d.OT + j) * rowstride + f;
-                        ri[orr] = m * cs;                                                   // nn_proc.py:325-326
-                        ri[orr + d.Fp] = m * sn;
+                        const long orr = ((long)b * d.OTp + j) * rowstride + f;
+                        st_split_tf32(m * cs, ri[orr], ri_lo[orr]);                         // nn_proc.py:325-326
+                        st_split_tf32(m * sn, ri[orr + d.Fp], ri_lo[orr + d.Fp]);
                     }
                 }
     }
@@ -288,16 +288,16 @@ MmaGeom build_mma_geom(const AeGeom& g) {
 
 template <int KS1, int NT9>
 void launch_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const AeParams& pm, const AeParams& pp, const float* spec,
-                 const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, int grid, size_t smem,
-                 cudaStream_t s) {
+                 const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo, int grid,
+                 size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(ae_fwd_mma_kernel<KS1, NT9, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         cudaFuncSetAttribute(ae_fwd_mma_kernel<KS1, NT9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         configured = true;
     }
-    ae_fwd_mma_kernel<KS1, NT9, 0><<<grid, WARPS * 32, smem, s>>>(d, g, mg, pm, spec, knobs, B, mag, mag_hat, phs_hat, ri);
-    ae_fwd_mma_kernel<KS1, NT9, 1><<<grid, WARPS * 32, smem, s>>>(d, g, mg, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri);
+    ae_fwd_mma_kernel<KS1, NT9, 0><<<grid, WARPS * 32, smem, s>>>(d, g, mg, pm, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo);
+    ae_fwd_mma_kernel<KS1, NT9, 1><<<grid, WARPS * 32, smem, s>>>(d, g, mg, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo);
 }
 
 }  // namespace
@@ -305,8 +305,8 @@ void launch_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const AePa
 // mag may be a scratch buffer when the caller does not need it (it is always written).
 // Returns false when the geometry is outside what the tensor-core kernels cover (caller uses the SIMT kernel).
 bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
-                              const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, int sm_count,
-                              cudaStream_t s) {
+                              const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo,
+                              int sm_count, cudaStream_t s) {
     if (d.T > 64 || d.OT > 64 || d.K > 16) return false;
     const MmaGeom mg = build_mma_geom(g);
     const size_t smem = sizeof(float) * (2L * mg.wfloats + mg.bfloats);
@@ -317,7 +317,7 @@ bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& 
     const int nt9 = d.OT <= 16 ? 2 : (d.OT <= 32 ? 4 : 8);
 #define ST_CASE(K, N)                                                                                                   \
     if (ks1 == K && nt9 == N) {                                                                                         \
-        launch_pair<K, N>(d, g, mg, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, grid, smem, s);                  \
+        launch_pair<K, N>(d, g, mg, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, grid, smem, s);                  \
         return true;                                                                                                    \
     }
     ST_CASE(4, 2) ST_CASE(4, 4) ST_CASE(6, 2) ST_CASE(6, 4) ST_CASE(6, 8) ST_CASE(8, 2) ST_CASE(8, 4) ST_CASE(8, 8)

@@ -2,6 +2,7 @@
 // forward / loss / backward / clip / Adam.  Host code only orchestrates; all arithmetic is in the kernels.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <string>
@@ -20,8 +21,12 @@ struct st_handle {
     int fwdB = 0;                 // batch of the last st_forward (st_backward must match)
     int ae_grid = 0;
     // workspace (device)
-    float *xpad = nullptr, *wcat = nullptr, *sfold = nullptr, *spec = nullptr, *ri = nullptr, *fo = nullptr;
-    float *mag_hat_ws = nullptr, *phs_hat_ws = nullptr, *gwave = nullptr, *g_ri = nullptr, *g_spec = nullptr;
+    // GEMM operands are kept as exact tf32 (hi, lo) pairs: *_lo is the residual of the buffer of the same name
+    float *xpad = nullptr, *xpad_lo = nullptr, *wcat = nullptr, *wcat_lo = nullptr, *sfold = nullptr, *sfold_lo = nullptr;
+    float *spec = nullptr, *ri = nullptr, *ri_lo = nullptr, *fo = nullptr;
+    float *mag_hat_ws = nullptr, *phs_hat_ws = nullptr, *gwave = nullptr, *gwave_lo = nullptr, *g_ri = nullptr;
+    float *g_spec = nullptr, *g_spec_lo = nullptr;
+    bool use_tc = true;           // tcgen05/TMA GEMMs (falls back to the FFMA GEMM per call when a shape is not covered)
     float *part_a = nullptr, *part_s = nullptr, *ae_part = nullptr;
     float *yhat_ws = nullptr, *gy_ws = nullptr, *gmh_ws = nullptr;   // fused train step only
     float* knobs_ws = nullptr;    // copy of the forward's knobs (the backward recomputes the AE chain)
@@ -157,8 +162,15 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     StDims& d = h->d;
-    d.C = C; d.N = N; d.H = H; d.F = N / 2 + 1; d.Fp = round_up(d.F, 8); d.T = T; d.OT = OT; d.L = L; d.K = K; d.R = 64;
+    d.C = C; d.N = N; d.H = H; d.F = N / 2 + 1; d.T = T; d.OT = OT; d.L = L; d.K = K; d.R = 64;
+    // 2*Fp is a GEMM N (analysis, synthesis dgrad) and K (synthesis) extent: a multiple of 32 with a divisor in [128, 256]
+    // that is a multiple of 16, so the tcgen05 tiles cover it exactly
+    d.Fp = round_up(d.F, 16);
+    while (st_tc_pick_bn(2 * d.Fp) < 128) d.Fp += 16;
     d.Cp = C + 2 * N; d.Lp = L + 2 * N;
+    d.Tp = (d.Cp + H - 1) / H; d.OTp = (d.Lp + H - 1) / H;
+    d.Sx = d.Tp * H; d.Sg = d.OTp * H;
+    if (const char* e = getenv("ST_DISABLE_TCGEN05")) h->use_tc = !(e[0] == '1');
     build_geom(d, h->g);
     if (st_ae_configure(h, d, h->g)) {
         snprintf(g_create_err, sizeof(g_create_err), "%s", h->err);
@@ -190,6 +202,8 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     if ((e = cudaMemset(h->counters, 0, CT_COUNT * sizeof(unsigned))) != cudaSuccess) return fail(e, "cudaMemset(counters)");
     if ((e = cudaMalloc(&h->wcat, 2L * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(wcat)");
     if ((e = cudaMalloc(&h->sfold, 2L * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(sfold)");
+    if ((e = cudaMalloc(&h->wcat_lo, 2L * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(wcat_lo)");
+    if ((e = cudaMalloc(&h->sfold_lo, 2L * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(sfold_lo)");
     if ((e = cudaMalloc(&h->part_a, (long)kMaxSplits * 2 * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(part_a)");
     if ((e = cudaMalloc(&h->part_s, (long)kMaxSplits * 2 * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(part_s)");
     // windows for st_init_frontend: hamming (cls_fe_dft.py:38) and the Griffin-Lim LSEE window (:133-163)
@@ -224,8 +238,9 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
 }
 
 static void free_batch_buffers(st_handle* h) {
-    float** bufs[] = {&h->xpad, &h->spec, &h->ri, &h->fo, &h->mag_hat_ws, &h->phs_hat_ws, &h->gwave, &h->g_ri,
-                      &h->g_spec, &h->ae_part, &h->yhat_ws, &h->gy_ws, &h->gmh_ws, &h->knobs_ws};
+    float** bufs[] = {&h->xpad, &h->xpad_lo, &h->spec, &h->ri, &h->ri_lo, &h->fo, &h->mag_hat_ws, &h->phs_hat_ws, &h->gwave,
+                      &h->gwave_lo, &h->g_ri, &h->g_spec, &h->g_spec_lo, &h->ae_part, &h->yhat_ws, &h->gy_ws, &h->gmh_ws,
+                      &h->knobs_ws};
     for (float** b : bufs) {
         if (*b) cudaFree(*b);
         *b = nullptr;
@@ -241,6 +256,8 @@ extern "C" void st_destroy(st_handle* h) {
     if (h->counters) cudaFree(h->counters);
     if (h->wcat) cudaFree(h->wcat);
     if (h->sfold) cudaFree(h->sfold);
+    if (h->wcat_lo) cudaFree(h->wcat_lo);
+    if (h->sfold_lo) cudaFree(h->sfold_lo);
     if (h->part_a) cudaFree(h->part_a);
     if (h->part_s) cudaFree(h->part_s);
     if (h->win) cudaFree(h->win);
@@ -265,15 +282,18 @@ static int ensure_workspace(st_handle* h, int B) {
     ST_CUDA_OK(cudaDeviceSynchronize());
     free_batch_buffers(h);
     const StDims& d = h->d;
-    const long BT = (long)B * d.T, BO = (long)B * d.OT;
+    const long BT = (long)B * d.Tp, BO = (long)B * d.OTp;      // frame rows incl. the dummy rows of the uniform-stride view
     const long tiles = ((long)B * d.F + ST_AE_ROWS - 1) / ST_AE_ROWS;
     h->ae_grid = (int)std::min<long>(tiles, h->sm_count);
     struct { float** p; long n; bool zero; } req[] = {
-        {&h->xpad, (long)B * d.Cp, false},       {&h->spec, BT * 2 * d.Fp, true},   {&h->ri, BO * 2 * d.Fp, true},
-        {&h->fo, BO * d.N, false},               {&h->mag_hat_ws, BO * d.F, false}, {&h->phs_hat_ws, BO * d.F, false},
-        {&h->gwave, (long)B * d.Lp, false},      {&h->g_ri, BO * 2 * d.Fp, true},   {&h->g_spec, BT * 2 * d.Fp, true},
+        {&h->xpad, (long)B * d.Sx + d.N, true},    {&h->xpad_lo, (long)B * d.Sx + d.N, true},
+        {&h->spec, BT * 2 * d.Fp, true},           {&h->ri, BO * 2 * d.Fp, true},           {&h->ri_lo, BO * 2 * d.Fp, true},
+        {&h->fo, BO * d.N, false},                 {&h->mag_hat_ws, (long)B * d.OT * d.F, false},
+        {&h->phs_hat_ws, (long)B * d.OT * d.F, false},
+        {&h->gwave, (long)B * d.Sg + d.N, true},   {&h->gwave_lo, (long)B * d.Sg + d.N, true},
+        {&h->g_ri, BO * 2 * d.Fp, true},           {&h->g_spec, BT * 2 * d.Fp, true},       {&h->g_spec_lo, BT * 2 * d.Fp, true},
         {&h->ae_part, (long)h->sm_count * 2 * h->g.flat_total, true},
-        {&h->yhat_ws, (long)B * d.L, false},     {&h->gy_ws, (long)B * d.L, false}, {&h->gmh_ws, BO * d.F, false},
+        {&h->yhat_ws, (long)B * d.L, false},     {&h->gy_ws, (long)B * d.L, false}, {&h->gmh_ws, (long)B * d.OT * d.F, false},
         {&h->knobs_ws, (long)B * std::max(d.K, 1), false},
     };
     for (auto& r : req) {
@@ -314,19 +334,28 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
     if (ensure_workspace(h, B)) return 1;
     {
         StageScope sc(h, SG_PAD_X, 1 + (d.K > 0), s);
-        st_launch_pad_scale(x, h->xpad, B, d.C, d.N, 0.5f, s);                               // x/2, conv padding
+        // x/2 with the conv padding, as (hi, lo), window stride Sx = Tp*H (frame (b,t) = row b*Tp+t of a stride-H view)
+        st_launch_pad_split(x, h->xpad, h->xpad_lo, B, d.C, d.N, d.Sx, 0.5f, s);
         if (d.K > 0) ST_CUDA_OK(cudaMemcpyAsync(h->knobs_ws, knobs, (long)B * d.K * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     {
         StageScope sc(h, SG_PACK_W, 2, s);
-        st_launch_pack_analysis(d, params[0], params[1], h->wcat, s);
-        st_launch_fold_synthesis(d, params[2], params[3], h->sfold, s);
+        st_launch_pack_analysis(d, params[0], params[1], h->wcat, h->wcat_lo, s);
+        st_launch_fold_synthesis(d, params[2], params[3], h->sfold, h->sfold_lo, s);
     }
     ST_LAUNCH_OK(h);
+    const int MT = B * d.Tp, MO = B * d.OTp, F2 = 2 * d.Fp;
     {   // analysis: spec[(b,t), (re|im) k] = sum_n frame[(b,t), n] * wcat[k, n]
         StageScope sc(h, SG_GEMM_ANALYSIS, 1, s);
-        GemmOperand A{h->xpad, 0, d.T, d.Cp, d.H}, W{h->wcat, d.N, 0, 0, 0};
-        st_launch_gemm(true, true, A, W, h->spec, 2L * d.Fp, B * d.T, 2 * d.Fp, d.N, 1, 0, s);
+        int r = -1;
+        if (h->use_tc) {
+            TcOperand A{h->xpad, h->xpad_lo, MT, d.N, d.H}, W{h->wcat, h->wcat_lo, F2, d.N, d.N};
+            r = st_launch_gemm_tc(false, false, A, W, h->spec, F2, MT, F2, d.N, 1, 0, h->sm_count, s);
+        }
+        if (r < 0) {
+            GemmOperand A{h->xpad, h->xpad_lo, d.H}, W{h->wcat, h->wcat_lo, d.N};
+            st_launch_gemm(true, true, A, W, h->spec, F2, MT, F2, d.N, 1, 0, s);
+        }
     }
     ST_LAUNCH_OK(h);
     {
@@ -335,21 +364,29 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         split_params(params, pm, pp);
         // production path: tensor-core (mma.sync TF32x3) register-resident chain; the SIMT kernel serves return_acts
         if (acts || !st_launch_ae_forward_mma(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri,
-                                              h->sm_count, s))
-            st_launch_ae_forward(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, acts, h->ae_grid, s);
+                                              h->ri_lo, h->sm_count, s))
+            st_launch_ae_forward(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo, acts,
+                                 h->ae_grid, s);
         if (mag_hat_user)
             ST_CUDA_OK(cudaMemcpyAsync(mag_hat_user, h->mag_hat_ws, (long)B * d.OT * d.F * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     ST_LAUNCH_OK(h);
     {   // synthesis: frames_out[(b,t), n] = sum_k ri[(b,t), k] * sfold[k, n]
         StageScope sc(h, SG_GEMM_SYNTH, 1, s);
-        GemmOperand R{h->ri, 2L * d.Fp, 0, 0, 0}, S{h->sfold, d.N, 0, 0, 0};
-        st_launch_gemm(true, false, R, S, h->fo, d.N, B * d.OT, d.N, 2 * d.Fp, 1, 0, s);
+        int r = -1;
+        if (h->use_tc) {
+            TcOperand R{h->ri, h->ri_lo, MO, F2, F2}, S{h->sfold, h->sfold_lo, F2, d.N, d.N};
+            r = st_launch_gemm_tc(false, true, R, S, h->fo, d.N, MO, d.N, F2, 1, 0, h->sm_count, s);
+        }
+        if (r < 0) {
+            GemmOperand R{h->ri, h->ri_lo, F2}, S{h->sfold, h->sfold_lo, d.N};
+            st_launch_gemm(true, false, R, S, h->fo, d.N, MO, d.N, F2, 1, 0, s);
+        }
     }
     ST_LAUNCH_OK(h);
     {
         StageScope sc(h, SG_OLA, 1, s);
-        st_launch_overlap_add(d, h->fo, h->xpad, B, y_hat, acts ? acts[28] : nullptr, acts ? acts[29] : nullptr, s);
+        st_launch_overlap_add(d, h->fo, x, B, y_hat, acts ? acts[28] : nullptr, acts ? acts[29] : nullptr, s);
     }
     ST_LAUNCH_OK(h);
     h->fwdB = B;
@@ -398,24 +435,37 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
     // adjoint of (*2, trim [N:-N]): zero-padded 2*g
     {
         StageScope sc(h, SG_PAD_G, 1, s);
-        st_launch_pad_scale(g_y_hat, h->gwave, B, d.L, d.N, 2.0f, s);
+        // adjoint of (*2, trim [N:-N]): zero-padded 2*g, window stride Sg = OTp*H
+        st_launch_pad_split(g_y_hat, h->gwave, h->gwave_lo, B, d.L, d.N, d.Sg, 2.0f, s);
     }
     ST_LAUNCH_OK(h);
-    GemmOperand Gf{h->gwave, 0, d.OT, d.Lp, d.H};   // gathered frames of the output gradient (adjoint of overlap-add)
-    GemmOperand S{h->sfold, d.N, 0, 0, 0}, R{h->ri, 2L * d.Fp, 0, 0, 0};
-    {   // synthesis data gradient: g_ri[(b,t), k] = sum_n gframe[(b,t), n] * sfold[k, n]
+    const int MT = B * d.Tp, MO = B * d.OTp, F2 = 2 * d.Fp;
+    const long plane = (long)F2 * d.N;
+    {   // synthesis data gradient: g_ri[(b,t), k] = sum_n gframe[(b,t), n] * sfold[k, n]   (gframe = adjoint of overlap-add)
         StageScope sc(h, SG_GEMM_SYNTH_DGRAD, 1, s);
-        st_launch_gemm(true, true, Gf, S, h->g_ri, 2L * d.Fp, B * d.OT, 2 * d.Fp, d.N, 1, 0, s);
+        int r = -1;
+        if (h->use_tc) {
+            TcOperand G{h->gwave, h->gwave_lo, MO, d.N, d.H}, S{h->sfold, h->sfold_lo, F2, d.N, d.N};
+            r = st_launch_gemm_tc(false, false, G, S, h->g_ri, F2, MO, F2, d.N, 1, 0, h->sm_count, s);
+        }
+        if (r < 0) {
+            GemmOperand G{h->gwave, h->gwave_lo, d.H}, S{h->sfold, h->sfold_lo, d.N};
+            st_launch_gemm(true, true, G, S, h->g_ri, F2, MO, F2, d.N, 1, 0, s);
+        }
     }
     ST_LAUNCH_OK(h);
-    // synthesis weight gradient (folded): G[k, n] = sum_(b,t) ri[(b,t), k] * gframe[(b,t), n]
-    const long plane = 2L * d.Fp * d.N;
-    const int Ks = B * d.OT, Ka = B * d.T;
-    int ss, sa;
-    {
+    int ss = -1, sa = -1;
+    {   // synthesis weight gradient (folded): G[k, n] = sum_(b,t) ri[(b,t), k] * gframe[(b,t), n]
         StageScope sc(h, SG_GEMM_SYNTH_WGRAD, 1, s);
-        ss = st_launch_gemm(false, false, R, Gf, h->part_s, d.N, 2 * d.Fp, d.N, Ks,
-                            std::min(kMaxSplits, std::max(1, Ks / 256)), plane, s);
+        if (h->use_tc) {
+            TcOperand R{h->ri, h->ri_lo, MO, F2, F2}, G{h->gwave, h->gwave_lo, MO, d.N, d.H};
+            ss = st_launch_gemm_tc(true, true, R, G, h->part_s, d.N, F2, d.N, MO, std::min(kMaxSplits, std::max(1, MO / 512)), plane,
+                                   h->sm_count, s);
+        }
+        if (ss < 0) {
+            GemmOperand R{h->ri, h->ri_lo, F2}, G{h->gwave, h->gwave_lo, d.H};
+            ss = st_launch_gemm(false, false, R, G, h->part_s, d.N, F2, d.N, MO, std::min(kMaxSplits, std::max(1, MO / 256)), plane, s);
+        }
     }
     ST_LAUNCH_OK(h);
     {   // both autoencoders: recompute, back-propagate, dL/d(re|im) -> g_spec, per-CTA weight-gradient partials
@@ -423,7 +473,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         AeParams pm, pp;
         split_params(params, pm, pp);
         st_launch_ae_backward(d, h->g, pm, pp, h->spec, h->knobs_ws, B, h->mag_hat_ws, h->phs_hat_ws, h->g_ri, g_mag_hat,
-                              g_mag, h->g_spec, h->ae_part, h->ae_grid, s);
+                              g_mag, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_grid, s);
     }
     ST_LAUNCH_OK(h);
     {
@@ -438,9 +488,15 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
     ST_LAUNCH_OK(h);
     {   // analysis weight gradient: G[(re|im) k, n] = sum_(b,t) g_spec[(b,t), k] * frame[(b,t), n]
         StageScope sc(h, SG_GEMM_ANALYSIS_WGRAD, 1, s);
-        GemmOperand Gs{h->g_spec, 2L * d.Fp, 0, 0, 0}, Xf{h->xpad, 0, d.T, d.Cp, d.H};
-        sa = st_launch_gemm(false, false, Gs, Xf, h->part_a, d.N, 2 * d.Fp, d.N, Ka,
-                            std::min(kMaxSplits, std::max(1, Ka / 256)), plane, s);
+        if (h->use_tc) {
+            TcOperand Gs{h->g_spec, h->g_spec_lo, MT, F2, F2}, X{h->xpad, h->xpad_lo, MT, d.N, d.H};
+            sa = st_launch_gemm_tc(true, true, Gs, X, h->part_a, d.N, F2, d.N, MT, std::min(kMaxSplits, std::max(1, MT / 512)), plane,
+                                   h->sm_count, s);
+        }
+        if (sa < 0) {
+            GemmOperand Gs{h->g_spec, h->g_spec_lo, F2}, X{h->xpad, h->xpad_lo, d.H};
+            sa = st_launch_gemm(false, false, Gs, X, h->part_a, d.N, F2, d.N, MT, std::min(kMaxSplits, std::max(1, MT / 256)), plane, s);
+        }
     }
     ST_LAUNCH_OK(h);
     {
@@ -552,11 +608,11 @@ extern "C" long st_debug_numel(st_handle* h, const char* name) {
     if (!h || !name) return -1;
     const StDims& d = h->d;
     const long B = h->fwdB;
-    if (!strcmp(name, "spec") || !strcmp(name, "g_spec")) return B * d.T * 2 * d.Fp;
-    if (!strcmp(name, "ri") || !strcmp(name, "g_ri")) return B * d.OT * 2 * d.Fp;
-    if (!strcmp(name, "frames_out")) return B * d.OT * d.N;
+    if (!strcmp(name, "spec") || !strcmp(name, "g_spec")) return B * d.Tp * 2 * d.Fp;
+    if (!strcmp(name, "ri") || !strcmp(name, "g_ri")) return B * d.OTp * 2 * d.Fp;
+    if (!strcmp(name, "frames_out")) return B * d.OTp * d.N;
     if (!strcmp(name, "wcat") || !strcmp(name, "sfold")) return 2L * d.Fp * d.N;
-    if (!strcmp(name, "xpad")) return B * d.Cp;
+    if (!strcmp(name, "xpad")) return B * d.Sx;
     if (!strcmp(name, "phs_hat")) return B * d.OT * d.F;
     return -1;
 }
@@ -602,4 +658,26 @@ extern "C" int st_profile_read(st_handle* h, float* ms, long* calls) {
     }
     h->prof_events.clear();
     return 0;
+}
+
+// Test hook: one GEMM on caller-provided (hi, lo) operands through either implementation.
+//   a_mn / b_mn: 0 = K-major ([rows = M or N][K], leading dim ld), 1 = MN-major ([rows = K][M or N]).
+//   use_tc: 1 = tcgen05/TMA kernel, 0 = FFMA kernel.  Returns the number of split planes written into C
+//   (plane stride = M * ldc), or -1.
+extern "C" int st_debug_gemm(st_handle* h, int use_tc, int a_mn, int b_mn, const float* a_hi, const float* a_lo, long a_ld,
+                             const float* b_hi, const float* b_lo, long b_ld, float* C, long ldc, int M, int N, int K,
+                             int splits, void* stream) {
+    if (!h) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaSetDevice(h->device) != cudaSuccess) return -1;
+    int r;
+    if (use_tc) {
+        TcOperand A{a_hi, a_lo, a_mn ? K : M, a_mn ? M : K, a_ld}, B{b_hi, b_lo, b_mn ? K : N, b_mn ? N : K, b_ld};
+        r = st_launch_gemm_tc(a_mn != 0, b_mn != 0, A, B, C, ldc, M, N, K, splits, (long)M * ldc, h->sm_count, s);
+    } else {
+        GemmOperand A{a_hi, a_lo, a_ld}, B{b_hi, b_lo, b_ld};
+        r = st_launch_gemm(!a_mn, !b_mn, A, B, C, ldc, M, N, K, splits, (long)M * ldc, s);
+    }
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return r;
 }

@@ -25,6 +25,14 @@ struct StDims {
     int R;    // AE rank (64)
     int Cp;   // padded input row  C + 2N
     int Lp;   // padded output-gradient row  L + 2N = (OT-1)*H + N
+    // Frame rows are addressed with a UNIFORM stride so that "all frames of all windows" is one 2-D tensor (TMA map with
+    // overlapping rows, row stride H): window b starts at b*Sx in the padded-input buffer, Sx = Tp*H >= Cp, and frame
+    // (b, t) is row b*Tp + t.  Rows t in [T, Tp) are dummies: computed where cheaper than masking, never consumed, and
+    // kept exactly zero in every buffer that feeds a reduction over rows.
+    int Tp;   // ceil(Cp / H)
+    int OTp;  // ceil(Lp / H)
+    int Sx;   // Tp * H   (stride between windows in the padded-input buffer)
+    int Sg;   // OTp * H  (same for the padded output-gradient buffer)
 };
 
 // One autoencoder's nine Linear layers, raw reference layout W[out][in] row-major, b[out].
@@ -66,12 +74,25 @@ int st_fail_msg(st_handle* h, const char* fmt, ...);
 
 static inline int st_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+#ifdef __CUDACC__
+// Exact two-term tf32 split: hi = rna_tf32(x) (low 13 mantissa bits zero), lo = rna_tf32(x - hi).
+__device__ __forceinline__ void st_split_tf32(float x, float& hi, float& lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+    lo = __uint_as_float(l);
+}
+#endif
+
 // ---- launchers implemented in the .cu files (all asynchronous on `s`) ----------------------
 // st_frontend.cu
-void st_launch_pad_scale(const float* src, float* dst, int rows, int len, int pad, float scale, cudaStream_t s);
-void st_launch_pack_analysis(const StDims& d, const float* Wr, const float* Wi, float* wcat, cudaStream_t s);
-void st_launch_fold_synthesis(const StDims& d, const float* Sr, const float* Si, float* sfold, cudaStream_t s);
-void st_launch_overlap_add(const StDims& d, const float* frames_out, const float* xpad, int B,
+// Every buffer that is a GEMM operand is stored as an exact tf32 pair (hi, lo): x = hi + lo up to 2^-22 relative.
+void st_launch_pad_split(const float* src, float* dst_hi, float* dst_lo, int rows, int len, int pad, int dst_stride, float scale,
+                         cudaStream_t s);
+void st_launch_pack_analysis(const StDims& d, const float* Wr, const float* Wi, float* wcat_hi, float* wcat_lo, cudaStream_t s);
+void st_launch_fold_synthesis(const StDims& d, const float* Sr, const float* Si, float* sfold_hi, float* sfold_lo, cudaStream_t s);
+void st_launch_overlap_add(const StDims& d, const float* frames_out, const float* x, int B,
                            float* y_hat, float* x_fwdsyn, float* y_half, cudaStream_t s);
 void st_launch_finalize_dft_grads(const StDims& d, const float* part_a, const float* part_s, int splits_a,
                                   int splits_s, float* gWr, float* gWi, float* gSr, float* gSi, cudaStream_t s);
@@ -79,34 +100,43 @@ void st_launch_init_frontend(const StDims& d, float* Wr, float* Wi, float* Sr, f
 
 // st_gemm_simt.cu  C[M,N] (+split partials) = op(A) * op(B)
 struct GemmOperand {
-    const float* ptr;
-    long ld;      // leading dimension (floats) when not gathered
-    int g_T;      // >0: rows are overlapping frames: row r -> (r / g_T) * g_ld + (r % g_T) * g_H
-    long g_ld;
-    int g_H;
+    const float* ptr;   // hi part (or the plain value when lo == nullptr)
+    const float* lo;    // lo part, added on load
+    long ld;            // leading dimension in floats; rows may overlap (frames: ld = hop)
 };
 // returns the number of split-K planes actually written (<= splits)
 int st_launch_gemm(bool a_kcontig, bool b_kcontig, const GemmOperand& A, const GemmOperand& B, float* C, long ldc,
                    int M, int N, int K, int splits, long split_stride, cudaStream_t s);
+
+// st_gemm_tc.cu  tcgen05 / TMA path.  Operand = exact (hi, lo) tf32 pair, 2-D row-major view (rows may overlap).
+struct TcOperand {
+    const float* hi;
+    const float* lo;
+    long rows, cols, ld;
+};
+int st_tc_pick_bn(int n);
+// returns split planes written, or -1 when the shape is not covered (caller falls back to st_launch_gemm)
+int st_launch_gemm_tc(bool a_mn_major, bool b_mn_major, const TcOperand& A, const TcOperand& B, float* C, long ldc, int M,
+                      int N, int K, int splits, long split_stride, int sm_count, cudaStream_t s);
 
 // st_ae.cu
 size_t st_ae_fwd_smem(const StDims& d, const AeGeom& g);
 size_t st_ae_bwd_smem(const StDims& d, const AeGeom& g);
 int st_ae_configure(st_handle* h, const StDims& d, const AeGeom& g);
 void st_launch_ae_forward(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
-                          const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri,
+                          const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri_hi, float* ri_lo,
                           float* const* acts_dev, int grid, cudaStream_t s);
 void st_launch_ae_backward(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
                            const float* knobs, int B, const float* mag_hat, const float* phs_hat, const float* g_ri,
-                           const float* g_mag_hat, const float* g_mag, float* g_spec, float* partials, int grid,
-                           cudaStream_t s);
+                           const float* g_mag_hat, const float* g_mag, float* g_spec_hi, float* g_spec_lo, float* partials,
+                           int grid, cudaStream_t s);
 void st_launch_ae_grad_reduce(const AeGeom& g, const float* partials, int ncta, const AeGrads& gm, const AeGrads& gp,
                               cudaStream_t s);
 
 // st_ae_mma.cu (tensor-core forward; returns false if the geometry is not covered)
 bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
-                              const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, int sm_count,
-                              cudaStream_t s);
+                              const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri_hi, float* ri_lo,
+                              int sm_count, cudaStream_t s);
 
 // st_loss_opt.cu
 void st_launch_loss(const StDims& d, const float* y_hat, const float* y, const float* mag_hat, const float* sbf,

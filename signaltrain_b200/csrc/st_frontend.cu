@@ -7,29 +7,34 @@ namespace {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
-// dst[r, :] = [0]*pad ++ scale*src[r, :len] ++ [0]*pad          (len, pad multiples of 4)
-// Used for x/2 (nn_proc.py:307 + Conv1d padding=N, cls_fe_dft.py:28) and for 2*dL/dy_hat (adjoint of the
-// [N:-N] trim, cls_fe_dft.py:113, and of the final *2, nn_proc.py:340).
-__global__ void pad_scale_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int len, int pad,
-                                 float scale) {
-    const int plen4 = (len + 2 * pad) >> 2;
-    const long total = (long)rows * plen4;
+// dst[r, :] = [0]*pad ++ scale*src[r, :len] ++ [0]*(stride-pad-len), written as an exact tf32 pair (hi, lo).
+// Used for x/2 (nn_proc.py:307 + Conv1d padding=N, cls_fe_dft.py:28) and for 2*dL/dy_hat (adjoint of the [N:-N] trim,
+// cls_fe_dft.py:113, and of the final *2, nn_proc.py:340).  The row stride is Tp*H (resp. OTp*H) so that frame (b, t)
+// starts at (b*Tp + t)*H: one uniform-stride 2-D view over all frames of all windows.
+__global__ void pad_split_kernel(const float* __restrict__ src, float* __restrict__ dst_hi, float* __restrict__ dst_lo,
+                                 int rows, int len, int pad, int stride, float scale) {
+    const int s4 = stride >> 2;
+    const long total = (long)rows * s4;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / plen4);
-        const int c = (int)(i - (long)r * plen4) << 2;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int r = (int)(i / s4);
+        const int c = (int)(i - (long)r * s4) << 2;
+        float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
         if (c >= pad && c < pad + len) {
-            v = ld4(src + (long)r * len + (c - pad));
-            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+            const float4 v = ld4(src + (long)r * len + (c - pad));
+            st_split_tf32(v.x * scale, hi.x, lo.x);
+            st_split_tf32(v.y * scale, hi.y, lo.y);
+            st_split_tf32(v.z * scale, hi.z, lo.z);
+            st_split_tf32(v.w * scale, hi.w, lo.w);
         }
-        st4(dst + (long)r * (len + 2 * pad) + c, v);
+        st4(dst_hi + (long)r * stride + c, hi);
+        st4(dst_lo + (long)r * stride + c, lo);
     }
 }
 
 // wcat[2Fp][N]: rows [0,F) = Wr[0:F], rows [Fp,Fp+F) = Wi[0:F], padding rows zero.
 // (only bins [:F] of the conv output are kept, cls_fe_dft.py:55-56)
 __global__ void pack_analysis_kernel(StDims d, const float* __restrict__ Wr, const float* __restrict__ Wi,
-                                     float* __restrict__ wcat) {
+                                     float* __restrict__ wcat, float* __restrict__ wcat_lo) {
     const int n4 = d.N >> 2;
     const long total = 2L * d.Fp * n4;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -39,7 +44,10 @@ __global__ void pack_analysis_kernel(StDims d, const float* __restrict__ Wr, con
         const int k = row - half * d.Fp;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k < d.F) v = ld4((half ? Wi : Wr) + (long)k * d.N + c);
-        st4(wcat + (long)row * d.N + c, v);
+        float4 hi, lo;
+        st_split_tf32(v.x, hi.x, lo.x); st_split_tf32(v.y, hi.y, lo.y); st_split_tf32(v.z, hi.z, lo.z); st_split_tf32(v.w, hi.w, lo.w);
+        st4(wcat + (long)row * d.N + c, hi);
+        st4(wcat_lo + (long)row * d.N + c, lo);
     }
 }
 
@@ -47,7 +55,7 @@ __global__ void pack_analysis_kernel(StDims d, const float* __restrict__ Wr, con
 //   rows [0,F):      Sr[k] + (1<=k<=F-2 ? Sr[N-k] : 0)
 //   rows [Fp,Fp+F):  Si[k] - (1<=k<=F-2 ? Si[N-k] : 0)
 __global__ void fold_synthesis_kernel(StDims d, const float* __restrict__ Sr, const float* __restrict__ Si,
-                                      float* __restrict__ sfold) {
+                                      float* __restrict__ sfold, float* __restrict__ sfold_lo) {
     const int n4 = d.N >> 2;
     const long total = 2L * d.Fp * n4;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -65,14 +73,17 @@ __global__ void fold_synthesis_kernel(StDims d, const float* __restrict__ Sr, co
                 v.x += sg * m.x; v.y += sg * m.y; v.z += sg * m.z; v.w += sg * m.w;
             }
         }
-        st4(sfold + (long)row * d.N + c, v);
+        float4 hi, lo;
+        st_split_tf32(v.x, hi.x, lo.x); st_split_tf32(v.y, hi.y, lo.y); st_split_tf32(v.z, hi.z, lo.z); st_split_tf32(v.w, hi.w, lo.w);
+        st4(sfold + (long)row * d.N + c, hi);
+        st4(sfold_lo + (long)row * d.N + c, lo);
     }
 }
 
 // Overlap-add of the per-frame synthesis output (ConvTranspose1d stride H, cls_fe_dft.py:112), trim
 // [N:-N] (:113), add the input residual and undo the /2 (nn_proc.py:332,340).
-//   frames_out (B*OT, N)   xpad (B, Cp) holds x/2   ->   y_hat (B, L)
-__global__ void overlap_add_kernel(StDims d, const float* __restrict__ fo, const float* __restrict__ xpad, int B,
+//   frames_out (B*OTp, N)   x (B, C)   ->   y_hat (B, L)
+__global__ void overlap_add_kernel(StDims d, const float* __restrict__ fo, const float* __restrict__ x, int B,
                                    float* __restrict__ y_hat, float* __restrict__ x_fwdsyn, float* __restrict__ y_half) {
     const int l4 = d.L >> 2;
     const long total = (long)B * l4;
@@ -87,10 +98,11 @@ __global__ void overlap_add_kernel(StDims d, const float* __restrict__ fo, const
         if (t_hi > d.OT - 1) t_hi = d.OT - 1;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = t_lo; t <= t_hi; ++t) {
-            const float4 v = ld4(fo + ((long)b * d.OT + t) * d.N + (j + d.N - t * d.H));
+            const float4 v = ld4(fo + ((long)b * d.OTp + t) * d.N + (j + d.N - t * d.H));
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-        const float4 xr = ld4(xpad + (long)b * d.Cp + d.N + (d.C - d.L) + j);
+        float4 xr = ld4(x + (long)b * d.C + (d.C - d.L) + j);
+        xr.x *= 0.5f; xr.y *= 0.5f; xr.z *= 0.5f; xr.w *= 0.5f;
         if (x_fwdsyn) st4(x_fwdsyn + (long)b * d.L + j, acc);
         float4 yh = make_float4(acc.x + xr.x, acc.y + xr.y, acc.z + xr.z, acc.w + xr.w);
         if (y_half) st4(y_half + (long)b * d.L + j, yh);
@@ -171,19 +183,20 @@ inline int grid_for(long items, int threads) {
 
 }  // namespace
 
-void st_launch_pad_scale(const float* src, float* dst, int rows, int len, int pad, float scale, cudaStream_t s) {
-    const long items = (long)rows * ((len + 2 * pad) >> 2);
-    pad_scale_kernel<<<grid_for(items, 256), 256, 0, s>>>(src, dst, rows, len, pad, scale);
+void st_launch_pad_split(const float* src, float* dst_hi, float* dst_lo, int rows, int len, int pad, int stride, float scale,
+                         cudaStream_t s) {
+    const long items = (long)rows * (stride >> 2);
+    pad_split_kernel<<<grid_for(items, 256), 256, 0, s>>>(src, dst_hi, dst_lo, rows, len, pad, stride, scale);
 }
-void st_launch_pack_analysis(const StDims& d, const float* Wr, const float* Wi, float* wcat, cudaStream_t s) {
-    pack_analysis_kernel<<<grid_for(2L * d.Fp * (d.N >> 2), 256), 256, 0, s>>>(d, Wr, Wi, wcat);
+void st_launch_pack_analysis(const StDims& d, const float* Wr, const float* Wi, float* wcat, float* wcat_lo, cudaStream_t s) {
+    pack_analysis_kernel<<<grid_for(2L * d.Fp * (d.N >> 2), 256), 256, 0, s>>>(d, Wr, Wi, wcat, wcat_lo);
 }
-void st_launch_fold_synthesis(const StDims& d, const float* Sr, const float* Si, float* sfold, cudaStream_t s) {
-    fold_synthesis_kernel<<<grid_for(2L * d.Fp * (d.N >> 2), 256), 256, 0, s>>>(d, Sr, Si, sfold);
+void st_launch_fold_synthesis(const StDims& d, const float* Sr, const float* Si, float* sfold, float* sfold_lo, cudaStream_t s) {
+    fold_synthesis_kernel<<<grid_for(2L * d.Fp * (d.N >> 2), 256), 256, 0, s>>>(d, Sr, Si, sfold, sfold_lo);
 }
-void st_launch_overlap_add(const StDims& d, const float* fo, const float* xpad, int B, float* y_hat, float* x_fwdsyn,
+void st_launch_overlap_add(const StDims& d, const float* fo, const float* x, int B, float* y_hat, float* x_fwdsyn,
                            float* y_half, cudaStream_t s) {
-    overlap_add_kernel<<<grid_for((long)B * (d.L >> 2), 256), 256, 0, s>>>(d, fo, xpad, B, y_hat, x_fwdsyn, y_half);
+    overlap_add_kernel<<<grid_for((long)B * (d.L >> 2), 256), 256, 0, s>>>(d, fo, x, B, y_hat, x_fwdsyn, y_half);
 }
 void st_launch_finalize_dft_grads(const StDims& d, const float* pa, const float* ps, int sa, int ss, float* gWr,
                                   float* gWi, float* gSr, float* gSi, cudaStream_t s) {

@@ -1,12 +1,11 @@
-// FP32 FFMA GEMM with frame-gather operands (exact-fp32 path for the five front-end contractions).
+// FP32 FFMA GEMM (fallback for shapes the tcgen05 path does not cover, and its cross-check in the tests).
 //
 //   C[M,N] = op(A) * op(B),   fp32 in / fp32 accumulate, 128x128x8 tiles, 256 threads, 8x8 per thread,
 //   register-prefetched double-buffered shared memory, optional split-K into separate partial planes.
 //
 // An operand is either "k-contiguous"  X[row][k]  (row = m or n)  or "row-contiguous"  X[k][row].
-// Rows of an operand may be GATHERED overlapping frames of a padded waveform
-//   row r -> base (r / g_T) * g_ld + (r % g_T) * g_H
-// which is how Conv1d(stride=hop) (cls_fe_dft.py:28-31,55-56) and ConvTranspose1d(stride=hop)
+// Rows of an operand may OVERLAP (leading dimension = hop < row length): frame (b, t) of the padded waveform is row
+// b*Tp + t of a uniform-stride view, which is how Conv1d(stride=hop) (cls_fe_dft.py:28-31,55-56) and ConvTranspose1d(stride=hop)
 // (cls_fe_dft.py:78-82,112) and their weight/data gradients become plain GEMMs without im2col.
 #include "st_common.cuh"
 
@@ -14,12 +13,13 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 8, LDS = BM + 4;
 
-__device__ __forceinline__ long op_row_base(const GemmOperand& o, int r) {
-    if (o.g_T > 0) {
-        const int b = r / o.g_T;
-        return (long)b * o.g_ld + (long)(r - b * o.g_T) * o.g_H;
+__device__ __forceinline__ float4 op_load4(const GemmOperand& o, long off) {
+    float4 v = *reinterpret_cast<const float4*>(o.ptr + off);
+    if (o.lo) {
+        const float4 l = *reinterpret_cast<const float4*>(o.lo + off);
+        v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
     }
-    return (long)r * o.ld;
+    return v;
 }
 
 // Fetch this thread's float4 of a 128(rows) x 8(k) operand tile.
@@ -28,10 +28,10 @@ __device__ __forceinline__ float4 tile_fetch(const GemmOperand& o, int row0, int
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (KC) {
         const int r = row0 + (tid >> 1), k = k0 + ((tid & 1) << 2);
-        if (r < rows && k < kend) v = *reinterpret_cast<const float4*>(o.ptr + op_row_base(o, r) + k);
+        if (r < rows && k < kend) v = op_load4(o, (long)r * o.ld + k);
     } else {
         const int k = k0 + (tid >> 5), r = row0 + ((tid & 31) << 2);
-        if (k < kend && r < rows) v = *reinterpret_cast<const float4*>(o.ptr + op_row_base(o, k) + r);
+        if (k < kend && r < rows) v = op_load4(o, (long)k * o.ld + r);
     }
     return v;
 }

@@ -1,0 +1,372 @@
+// tcgen05 GEMM for the five front-end contractions (analysis, synthesis, and their data / weight gradients).
+//
+//   C[M,N] (+ split-K planes) = A * B    fp32 in, fp32 out, "3xTF32": every operand is carried as an exact pair
+//   x = hi + lo of tf32-representable fp32 words (written by the producing kernel), and
+//       A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi            (three kind::tf32 UMMAs per k-step, fp32 accumulate in TMEM)
+//   which restores fp32-level accuracy (the dropped lo*lo term is 2^-22 relative) -- single-pass TF32 misses the 1e-5
+//   waveform bar by 40x.
+//
+// Blackwell structure (one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer : cp.async.bulk.tensor.2d tiles of A_hi/A_lo/B_hi/B_lo -> 128B-swizzled smem ring, mbarrier tx
+//   warp 1      MMA issuer   : one elected thread issues tcgen05.mma (M=128, N=BN<=256, K=8) from smem descriptors into a
+//                              double-buffered TMEM accumulator; tcgen05.commit releases smem stages / publishes the tile
+//   warps 2..5  epilogue     : tcgen05.ld (32 lanes x 32b) -> registers -> vectorised global stores, overlapping the next
+//                              tile's MMAs
+// Operands may be K-major ([row][k], one 128-row x 32-float box per stage) or MN-major ([k][row], 32x32 boxes); the frame
+// gather of Conv1d / ConvTranspose1d (cls_fe_dft.py:28-31,78-82) is a 2-D tensor map whose row stride is the hop (rows
+// overlap), so frames are never materialised.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdio>
+
+#include "st_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BKF = 32;                 // floats per k-block = one 128-byte swizzle span
+constexpr int NTHREADS = 192;
+constexpr uint32_t A_BYTES = BM * 128;  // one (hi or lo) A tile per stage
+constexpr int TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 6000000000LL) __trap();      // ~3 s at 2 GHz
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+//   K-major  tile [rows][32 floats]:  SBO = 1024 B (8 rows x 128 B), LBO unused (1)
+//   MN-major tile, 32-column slabs of [32 k-rows][128 B]: LBO = 4096 B (next slab), SBO = 1024 B (next 8 k-rows)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, bool mn_major) {
+    uint64_t d = (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(mn_major ? (4096 >> 4) : 1) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TcParams {
+    float* C;
+    long ldc;
+    int M, N, BN;
+    int tiles_m, tiles_n, splits;
+    int kb_total, kb_per_split;    // k-blocks of 32
+    long split_stride;
+    int stages;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+    const uint32_t stage_bytes = 2u * (A_BYTES + b_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;                     // [stages]  TMA -> MMA
+    uint64_t* empty = bars + p.stages;         // [stages]  MMA -> TMA
+    uint64_t* tfull = bars + 2 * p.stages;     // [2]       MMA -> epilogue
+    uint64_t* tempty = tfull + 2;              // [2]       epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_work = p.tiles_m * p.tiles_n * p.splits;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int split = w % p.splits, tt = w / p.splits;
+                const int m0 = (tt / p.tiles_n) * BM, n0 = (tt % p.tiles_n) * p.BN;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sA_hi = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sA_lo = sA_hi + A_BYTES;
+                    uint8_t* sB_hi = sA_lo + A_BYTES;
+                    uint8_t* sB_lo = sB_hi + b_bytes;
+                    mbar_expect_tx(&full[stage], stage_bytes);
+                    const int k0 = kb * BKF;
+                    if (!A_MN) {
+                        tma_load_2d(sA_hi, &tmAh, &full[stage], k0, m0);
+                        tma_load_2d(sA_lo, &tmAl, &full[stage], k0, m0);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < BM / 32; ++g) {
+                            tma_load_2d(sA_hi + g * 4096, &tmAh, &full[stage], m0 + 32 * g, k0);
+                            tma_load_2d(sA_lo + g * 4096, &tmAl, &full[stage], m0 + 32 * g, k0);
+                        }
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sB_hi, &tmBh, &full[stage], k0, n0);
+                        tma_load_2d(sB_lo, &tmBl, &full[stage], k0, n0);
+                    } else {
+                        for (int g = 0; g < p.BN / 32; ++g) {
+                            tma_load_2d(sB_hi + g * 4096, &tmBh, &full[stage], n0 + 32 * g, k0);
+                            tma_load_2d(sB_lo + g * 4096, &tmBl, &full[stage], n0 + 32 * g, k0);
+                        }
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=b=TF32 [7,10),[10,13), majors [15],[16],
+            // N>>3 [17,23), M>>4 [24,29)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase[2] = {0, 0};
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int split = w % p.splits;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                mbar_wait(&tempty[acc], acc_phase[acc] ^ 1);          // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+                uint32_t accumulate = 0;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sA_hi = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sA_lo = sA_hi + A_BYTES, sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + b_bytes;
+#pragma unroll
+                    for (int ks = 0; ks < BKF / 8; ++ks) {
+                        const uint32_t ao = A_MN ? ks * 1024 : ks * 32;      // next 8 k: 8 rows of 128 B | 32 B inside the span
+                        const uint32_t bo = B_MN ? ks * 1024 : ks * 32;
+                        const uint64_t ah = make_desc(sA_hi + ao, A_MN), al = make_desc(sA_lo + ao, A_MN);
+                        const uint64_t bh = make_desc(sB_hi + bo, B_MN), bl = make_desc(sB_lo + bo, B_MN);
+                        umma_tf32(tmem_d, al, bh, idesc, accumulate);
+                        umma_tf32(tmem_d, ah, bl, idesc, 1u);
+                        umma_tf32(tmem_d, ah, bh, idesc, 1u);
+                        accumulate = 1u;
+                    }
+                    umma_commit(&empty[stage]);                        // smem stage reusable once these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);                              // accumulator complete -> epilogue
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ epilogue ====================================
+        const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+        int acc = 0;
+        uint32_t acc_phase[2] = {0, 0};
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int split = w % p.splits, tt = w / p.splits;
+            const int m0 = (tt / p.tiles_n) * BM, n0 = (tt % p.tiles_n) * p.BN;
+            mbar_wait(&tfull[acc], acc_phase[acc]);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + 32 * q + lane;
+            float* crow = p.C + (long)split * p.split_stride + (long)row * p.ldc + n0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.BN);
+            for (int c = 0; c < p.BN; c += 32) {
+                float v0[16], v1[16];
+                tmem_ld16(taddr + c, v0);
+                const bool two = c + 16 < p.BN;
+                if (two) tmem_ld16(taddr + c + 16, v1);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < p.M) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (n0 + c + 4 * i < p.N)
+                            *reinterpret_cast<float4*>(crow + c + 4 * i) = make_float4(v0[4 * i], v0[4 * i + 1], v0[4 * i + 2], v0[4 * i + 3]);
+                    if (two) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (n0 + c + 16 + 4 * i < p.N)
+                                *reinterpret_cast<float4*>(crow + c + 16 + 4 * i) =
+                                    make_float4(v1[4 * i], v1[4 * i + 1], v1[4 * i + 2], v1[4 * i + 3]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc_phase[acc] ^= 1;
+            acc ^= 1;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major view: element (r, c) at base + r*ld + c; rows may overlap (ld < cols).  Box = {32 floats, box_rows}.
+bool make_map(CUtensorMap* tm, const float* base, long rows, long cols, long ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <bool A_MN, bool B_MN>
+cudaError_t launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcParams& p,
+                   int grid, size_t smem, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    gemm_tc_kernel<A_MN, B_MN><<<grid, NTHREADS, smem, s>>>(ah, al, bh, bl, p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// Largest multiple of 16 in [64, 256] that divides n (0 if none).
+int st_tc_pick_bn(int n) {
+    for (int bn = 256; bn >= 64; bn -= 16)
+        if (n % bn == 0) return bn;
+    return 0;
+}
+
+// A: K-major -> A.rows = M, A.cols = K;  MN-major -> A.rows = K, A.cols = M.   Same for B with N.
+// Returns the number of split-K planes written, or -1 if this shape cannot take the tensor-core path.
+int st_launch_gemm_tc(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand& B, float* C, long ldc, int M, int N, int K,
+                      int splits, long split_stride, int sm_count, cudaStream_t s) {
+    const int BN = st_tc_pick_bn(N);
+    if (BN == 0 || (b_mn && (BN % 32))) return -1;
+    if ((A.ld & 3) || (B.ld & 3) || (ldc & 3) || (N & 3)) return -1;
+    if (!a_mn && (K % BKF)) return -1;           // K-major operands are not zero-filled along K by a row bound
+    if (!b_mn && (K % BKF)) return -1;
+    TcParams p;
+    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.BN = BN;
+    p.tiles_m = (M + BM - 1) / BM;
+    p.tiles_n = N / BN;
+    p.kb_total = (K + BKF - 1) / BKF;
+    if (splits < 1) splits = 1;
+    p.kb_per_split = (p.kb_total + splits - 1) / splits;
+    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.split_stride = split_stride;
+    const size_t stage_bytes = 2 * ((size_t)A_BYTES + (size_t)BN * 128);
+    p.stages = (int)std::min<size_t>(4, (227 * 1024 - 2048) / stage_bytes);
+    if (p.stages < 2) return -1;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+    CUtensorMap ah, al, bh, bl;
+    const int abox = a_mn ? 32 : BM, bbox = b_mn ? 32 : BN;
+    if (!make_map(&ah, A.hi, A.rows, A.cols, A.ld, abox) || !make_map(&al, A.lo, A.rows, A.cols, A.ld, abox) ||
+        !make_map(&bh, B.hi, B.rows, B.cols, B.ld, bbox) || !make_map(&bl, B.lo, B.rows, B.cols, B.ld, bbox))
+        return -1;
+    const int work = p.tiles_m * p.tiles_n * p.splits;
+    const int grid = std::min(work, sm_count);
+    cudaError_t e;
+    if (!a_mn && !b_mn) e = launch<false, false>(ah, al, bh, bl, p, grid, smem, s);
+    else if (!a_mn && b_mn) e = launch<false, true>(ah, al, bh, bl, p, grid, smem, s);
+    else if (a_mn && !b_mn) e = launch<true, false>(ah, al, bh, bl, p, grid, smem, s);
+    else e = launch<true, true>(ah, al, bh, bl, p, grid, smem, s);
+    return e == cudaSuccess ? p.splits : -1;
+}

@@ -228,6 +228,16 @@ class Engine:
         self._ok(self.lib.st_profile_read(self.h, ms, calls), "st_profile_read")
         return {self.lib.st_profile_stage_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(n)}
 
+    def debug_gemm(self, use_tc, a_mn, b_mn, a_hi, a_lo, a_ld, b_hi, b_lo, b_ld, M, N, K, splits=1):
+        """Test hook (st_debug_gemm): returns the (planes, M, N) tensor of split-K planes."""
+        planes = max(1, splits)
+        C = torch.full((planes, M, N), float("nan"), device=self.device, dtype=torch.float32)
+        r = self.lib.st_debug_gemm(self.h, int(use_tc), int(a_mn), int(b_mn), _ptr(a_hi), _ptr(a_lo), a_ld, _ptr(b_hi), _ptr(b_lo),
+                                   b_ld, _ptr(C), N, M, N, K, splits, self._stream())
+        if r < 0:
+            raise RuntimeError("signaltrain_b200: st_debug_gemm: shape not covered or launch failed")
+        return C[:r]
+
     def debug_read(self, name):
         n = self.lib.st_debug_numel(self.h, name.encode())
         if n < 0:
