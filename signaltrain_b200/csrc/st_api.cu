@@ -350,7 +350,7 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         int r = -1;
         if (h->use_tc) {
             TcOperand A{h->xpad, h->xpad_lo, MT, d.N, d.H}, W{h->wcat, h->wcat_lo, F2, d.N, d.N};
-            r = st_launch_gemm_tc(false, false, A, W, h->spec, F2, MT, F2, d.N, 1, 0, h->sm_count, s);
+            r = st_launch_gemm_tc(false, false, A, W, h->spec, F2, MT, F2, d.N, 1, 0, /*promote=*/true, h->sm_count, s);
         }
         if (r < 0) {
             GemmOperand A{h->xpad, h->xpad_lo, d.H}, W{h->wcat, h->wcat_lo, d.N};
@@ -376,7 +376,7 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         int r = -1;
         if (h->use_tc) {
             TcOperand R{h->ri, h->ri_lo, MO, F2, F2}, S{h->sfold, h->sfold_lo, F2, d.N, d.N};
-            r = st_launch_gemm_tc(false, true, R, S, h->fo, d.N, MO, d.N, F2, 1, 0, h->sm_count, s);
+            r = st_launch_gemm_tc(false, true, R, S, h->fo, d.N, MO, d.N, F2, 1, 0, /*promote=*/true, h->sm_count, s);
         }
         if (r < 0) {
             GemmOperand R{h->ri, h->ri_lo, F2}, S{h->sfold, h->sfold_lo, d.N};
@@ -446,7 +446,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         int r = -1;
         if (h->use_tc) {
             TcOperand G{h->gwave, h->gwave_lo, MO, d.N, d.H}, S{h->sfold, h->sfold_lo, F2, d.N, d.N};
-            r = st_launch_gemm_tc(false, false, G, S, h->g_ri, F2, MO, F2, d.N, 1, 0, h->sm_count, s);
+            r = st_launch_gemm_tc(false, false, G, S, h->g_ri, F2, MO, F2, d.N, 1, 0, /*promote=*/false, h->sm_count, s);
         }
         if (r < 0) {
             GemmOperand G{h->gwave, h->gwave_lo, d.H}, S{h->sfold, h->sfold_lo, d.N};
@@ -460,7 +460,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         if (h->use_tc) {
             TcOperand R{h->ri, h->ri_lo, MO, F2, F2}, G{h->gwave, h->gwave_lo, MO, d.N, d.H};
             ss = st_launch_gemm_tc(true, true, R, G, h->part_s, d.N, F2, d.N, MO, std::min(kMaxSplits, std::max(1, MO / 512)), plane,
-                                   h->sm_count, s);
+                                   /*promote=*/false, h->sm_count, s);
         }
         if (ss < 0) {
             GemmOperand R{h->ri, h->ri_lo, F2}, G{h->gwave, h->gwave_lo, d.H};
@@ -491,7 +491,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         if (h->use_tc) {
             TcOperand Gs{h->g_spec, h->g_spec_lo, MT, F2, F2}, X{h->xpad, h->xpad_lo, MT, d.N, d.H};
             sa = st_launch_gemm_tc(true, true, Gs, X, h->part_a, d.N, F2, d.N, MT, std::min(kMaxSplits, std::max(1, MT / 512)), plane,
-                                   h->sm_count, s);
+                                   /*promote=*/false, h->sm_count, s);
         }
         if (sa < 0) {
             GemmOperand Gs{h->g_spec, h->g_spec_lo, F2}, X{h->xpad, h->xpad_lo, d.H};
@@ -664,7 +664,7 @@ extern "C" int st_profile_read(st_handle* h, float* ms, long* calls) {
 //   a_mn / b_mn: 0 = K-major ([rows = M or N][K], leading dim ld), 1 = MN-major ([rows = K][M or N]).
 //   use_tc: 1 = tcgen05/TMA kernel, 0 = FFMA kernel.  Returns the number of split planes written into C
 //   (plane stride = M * ldc), or -1.
-extern "C" int st_debug_gemm(st_handle* h, int use_tc, int a_mn, int b_mn, const float* a_hi, const float* a_lo, long a_ld,
+extern "C" int st_debug_gemm(st_handle* h, int use_tc /*0 FFMA, 1 tcgen05, 2 tcgen05 promoted*/, int a_mn, int b_mn, const float* a_hi, const float* a_lo, long a_ld,
                              const float* b_hi, const float* b_lo, long b_ld, float* C, long ldc, int M, int N, int K,
                              int splits, void* stream) {
     if (!h) return -1;
@@ -673,7 +673,7 @@ extern "C" int st_debug_gemm(st_handle* h, int use_tc, int a_mn, int b_mn, const
     int r;
     if (use_tc) {
         TcOperand A{a_hi, a_lo, a_mn ? K : M, a_mn ? M : K, a_ld}, B{b_hi, b_lo, b_mn ? K : N, b_mn ? N : K, b_ld};
-        r = st_launch_gemm_tc(a_mn != 0, b_mn != 0, A, B, C, ldc, M, N, K, splits, (long)M * ldc, h->sm_count, s);
+        r = st_launch_gemm_tc(a_mn != 0, b_mn != 0, A, B, C, ldc, M, N, K, splits, (long)M * ldc, use_tc == 2, h->sm_count, s);
     } else {
         GemmOperand A{a_hi, a_lo, a_ld}, B{b_hi, b_lo, b_ld};
         r = st_launch_gemm(!a_mn, !b_mn, A, B, C, ldc, M, N, K, splits, (long)M * ldc, s);

@@ -116,8 +116,9 @@ struct TcOperand {
 };
 int st_tc_pick_bn(int n);
 // returns split planes written, or -1 when the shape is not covered (caller falls back to st_launch_gemm)
+// promote: start a fresh TMEM accumulator every k-block and sum the partials in fp32 registers (forward GEMMs)
 int st_launch_gemm_tc(bool a_mn_major, bool b_mn_major, const TcOperand& A, const TcOperand& B, float* C, long ldc, int M,
-                      int N, int K, int splits, long split_stride, int sm_count, cudaStream_t s);
+                      int N, int K, int splits, long split_stride, bool promote, int sm_count, cudaStream_t s);
 
 // st_ae.cu
 size_t st_ae_fwd_smem(const StDims& d, const AeGeom& g);

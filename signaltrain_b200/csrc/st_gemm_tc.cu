@@ -10,8 +10,11 @@
 //   warp 0      TMA producer : cp.async.bulk.tensor.2d tiles of A_hi/A_lo/B_hi/B_lo -> 128B-swizzled smem ring, mbarrier tx
 //   warp 1      MMA issuer   : one elected thread issues tcgen05.mma (M=128, N=BN<=256, K=8) from smem descriptors into a
 //                              double-buffered TMEM accumulator; tcgen05.commit releases smem stages / publishes the tile
-//   warps 2..5  epilogue     : tcgen05.ld (32 lanes x 32b) -> registers -> vectorised global stores, overlapping the next
-//                              tile's MMAs
+//   warps 2..9  epilogue     : tcgen05.ld (32 lanes x 32b) -> fp32 registers -> vectorised global stores.  TMEM accumulation
+//                              rounds toward zero at every MMA step (measured: 7e-6 relative after K=1024), so for the two
+//                              forward GEMMs (1e-5 waveform budget) the issuer starts a fresh TMEM accumulator every k-block
+//                              and these warps add the 12-step partial sums in round-to-nearest fp32 registers
+//                              ("promoted accumulation"); the gradient GEMMs accumulate all of K in TMEM.
 // Operands may be K-major ([row][k], one 128-row x 32-float box per stage) or MN-major ([k][row], 32x32 boxes); the frame
 // gather of Conv1d / ConvTranspose1d (cls_fe_dft.py:28-31,78-82) is a 2-D tensor map whose row stride is the hop (rows
 // overlap), so frames are never materialised.
@@ -26,7 +29,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BKF = 32;                 // floats per k-block = one 128-byte swizzle span
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;           // 1 TMA warp + 1 MMA warp + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
 constexpr uint32_t A_BYTES = BM * 128;  // one (hi or lo) A tile per stage
 constexpr int TMEM_COLS = 512;
 
@@ -69,15 +73,17 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
 }
 
 // Shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-//   K-major  tile [rows][32 floats]:  SBO = 1024 B (8 rows x 128 B), LBO unused (1)
-//   MN-major tile, 32-column slabs of [32 k-rows][128 B]: LBO = 4096 B (next slab), SBO = 1024 B (next 8 k-rows)
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64).
+//   K-major  tile [rows][32 floats], SWIZZLE_128B (type 2): 8-row x 128 B atoms, SBO = 1024 B, LBO unused (1)
+//   MN-major tile, 32-column slabs of [32 k-rows][128 B].  32-bit MN-major operands only exist in the
+//   SWIZZLE_128B_BASE32B layout (type 1: 32-byte swizzle atoms, 4-row x 128 B atoms; TMA: SWIZZLE_128B_ATOM_32B):
+//   SBO = 512 B (next 4 k-rows), LBO = 4096 B (next 32-column slab)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, bool mn_major) {
     uint64_t d = (uint64_t)((addr >> 4) & 0x3FFF);
     d |= (uint64_t)(mn_major ? (4096 >> 4) : 1) << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((mn_major ? 512 : 1024) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(mn_major ? 1 : 2) << 61;
     return d;
 }
 
@@ -92,15 +98,10 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
 }
 
 struct TcParams {
@@ -109,6 +110,7 @@ struct TcParams {
     int M, N, BN;
     int tiles_m, tiles_n, splits;
     int kb_total, kb_per_split;    // k-blocks of 32
+    int kb_per_chunk;              // k-blocks accumulated in TMEM before promotion to fp32 registers
     long split_stride;
     int stages;
 };
@@ -131,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -202,73 +204,87 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 const int split = w % p.splits;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-                mbar_wait(&tempty[acc], acc_phase[acc] ^ 1);          // epilogue has drained this accumulator
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
-                uint32_t accumulate = 0;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                for (int kc = kb0; kc < kb1; kc += p.kb_per_chunk) {
+                    const int kce = min(kb1, kc + p.kb_per_chunk);
+                    mbar_wait(&tempty[acc], acc_phase[acc] ^ 1);          // epilogue has drained this accumulator
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t sA_hi = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t sA_lo = sA_hi + A_BYTES, sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + b_bytes;
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+                    uint32_t accumulate = 0;
+                    for (int kb = kc; kb < kce; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sA_hi = smem_u32(smem + (size_t)stage * stage_bytes);
+                        const uint32_t sA_lo = sA_hi + A_BYTES, sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + b_bytes;
 #pragma unroll
-                    for (int ks = 0; ks < BKF / 8; ++ks) {
-                        const uint32_t ao = A_MN ? ks * 1024 : ks * 32;      // next 8 k: 8 rows of 128 B | 32 B inside the span
-                        const uint32_t bo = B_MN ? ks * 1024 : ks * 32;
-                        const uint64_t ah = make_desc(sA_hi + ao, A_MN), al = make_desc(sA_lo + ao, A_MN);
-                        const uint64_t bh = make_desc(sB_hi + bo, B_MN), bl = make_desc(sB_lo + bo, B_MN);
-                        umma_tf32(tmem_d, al, bh, idesc, accumulate);
-                        umma_tf32(tmem_d, ah, bl, idesc, 1u);
-                        umma_tf32(tmem_d, ah, bh, idesc, 1u);
-                        accumulate = 1u;
+                        for (int ks = 0; ks < BKF / 8; ++ks) {
+                            const uint32_t ao = A_MN ? ks * 1024 : ks * 32;   // next 8 k: 8 rows of 128 B | 32 B inside the span
+                            const uint32_t bo = B_MN ? ks * 1024 : ks * 32;
+                            const uint64_t ah = make_desc(sA_hi + ao, A_MN), al = make_desc(sA_lo + ao, A_MN);
+                            const uint64_t bh = make_desc(sB_hi + bo, B_MN), bl = make_desc(sB_lo + bo, B_MN);
+                            umma_tf32(tmem_d, al, bh, idesc, accumulate);
+                            umma_tf32(tmem_d, ah, bl, idesc, 1u);
+                            umma_tf32(tmem_d, ah, bh, idesc, 1u);
+                            accumulate = 1u;
+                        }
+                        umma_commit(&empty[stage]);                        // smem stage reusable once these MMAs retire
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&empty[stage]);                        // smem stage reusable once these MMAs retire
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    umma_commit(&tfull[acc]);                              // partial accumulator complete -> epilogue
+                    acc_phase[acc] ^= 1;
+                    acc ^= 1;
                 }
-                umma_commit(&tfull[acc]);                              // accumulator complete -> epilogue
-                acc_phase[acc] ^= 1;
-                acc ^= 1;
             }
         }
         __syncwarp();
     } else {
         // ================================ epilogue ====================================
         const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;              // which half of the tile's columns this warp owns
+        const int ncols = p.BN >> 1;                   // multiple of 8, <= 128
         int acc = 0;
         uint32_t acc_phase[2] = {0, 0};
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
             const int split = w % p.splits, tt = w / p.splits;
-            const int m0 = (tt / p.tiles_n) * BM, n0 = (tt % p.tiles_n) * p.BN;
-            mbar_wait(&tfull[acc], acc_phase[acc]);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int row = m0 + 32 * q + lane;
-            float* crow = p.C + (long)split * p.split_stride + (long)row * p.ldc + n0;
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.BN);
-            for (int c = 0; c < p.BN; c += 32) {
-                float v0[16], v1[16];
-                tmem_ld16(taddr + c, v0);
-                const bool two = c + 16 < p.BN;
-                if (two) tmem_ld16(taddr + c + 16, v1);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < p.M) {
+            const int m0 = (tt / p.tiles_n) * BM, n0 = (tt % p.tiles_n) * p.BN + half * ncols;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+            float sum[128];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (n0 + c + 4 * i < p.N)
-                            *reinterpret_cast<float4*>(crow + c + 4 * i) = make_float4(v0[4 * i], v0[4 * i + 1], v0[4 * i + 2], v0[4 * i + 3]);
-                    if (two) {
+            for (int i = 0; i < 128; ++i) sum[i] = 0.f;
+            for (int kc = kb0; kc < kb1; kc += p.kb_per_chunk) {
+                mbar_wait(&tfull[acc], acc_phase[acc]);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.BN + half * ncols);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (n0 + c + 16 + 4 * i < p.N)
-                                *reinterpret_cast<float4*>(crow + c + 16 + 4 * i) =
-                                    make_float4(v1[4 * i], v1[4 * i + 1], v1[4 * i + 2], v1[4 * i + 3]);
+                for (int c = 0; c < 128; c += 32) {
+                    if (c < ncols) {
+                        uint32_t r[4][8];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (c + 8 * u < ncols) tmem_ld8(taddr + c + 8 * u, r[u]);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (c + 8 * u < ncols) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) sum[c + 8 * u + i] += __uint_as_float(r[u][i]);
+                            }
                     }
                 }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            acc_phase[acc] ^= 1;
-            acc ^= 1;
+            const int row = m0 + 32 * q + lane;
+            if (row < p.M) {
+                float* crow = p.C + (long)split * p.split_stride + (long)row * p.ldc + n0;
+#pragma unroll
+                for (int c = 0; c < 128; c += 4)
+                    if (c < ncols && n0 + c < p.N)
+                        *reinterpret_cast<float4*>(crow + c) = make_float4(sum[c], sum[c + 1], sum[c + 2], sum[c + 3]);
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -299,7 +315,7 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 row-major view: element (r, c) at base + r*ld + c; rows may overlap (ld < cols).  Box = {32 floats, box_rows}.
-bool make_map(CUtensorMap* tm, const float* base, long rows, long cols, long ld, int box_rows) {
+bool make_map(CUtensorMap* tm, const float* base, long rows, long cols, long ld, int box_rows, bool mn_major) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -307,7 +323,8 @@ bool make_map(CUtensorMap* tm, const float* base, long rows, long cols, long ld,
     cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -337,7 +354,7 @@ int st_tc_pick_bn(int n) {
 // A: K-major -> A.rows = M, A.cols = K;  MN-major -> A.rows = K, A.cols = M.   Same for B with N.
 // Returns the number of split-K planes written, or -1 if this shape cannot take the tensor-core path.
 int st_launch_gemm_tc(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand& B, float* C, long ldc, int M, int N, int K,
-                      int splits, long split_stride, int sm_count, cudaStream_t s) {
+                      int splits, long split_stride, bool promote, int sm_count, cudaStream_t s) {
     const int BN = st_tc_pick_bn(N);
     if (BN == 0 || (b_mn && (BN % 32))) return -1;
     if ((A.ld & 3) || (B.ld & 3) || (ldc & 3) || (N & 3)) return -1;
@@ -352,14 +369,15 @@ int st_launch_gemm_tc(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand&
     p.kb_per_split = (p.kb_total + splits - 1) / splits;
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.split_stride = split_stride;
+    p.kb_per_chunk = promote ? 1 : p.kb_per_split;
     const size_t stage_bytes = 2 * ((size_t)A_BYTES + (size_t)BN * 128);
     p.stages = (int)std::min<size_t>(4, (227 * 1024 - 2048) / stage_bytes);
     if (p.stages < 2) return -1;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
     CUtensorMap ah, al, bh, bl;
     const int abox = a_mn ? 32 : BM, bbox = b_mn ? 32 : BN;
-    if (!make_map(&ah, A.hi, A.rows, A.cols, A.ld, abox) || !make_map(&al, A.lo, A.rows, A.cols, A.ld, abox) ||
-        !make_map(&bh, B.hi, B.rows, B.cols, B.ld, bbox) || !make_map(&bl, B.lo, B.rows, B.cols, B.ld, bbox))
+    if (!make_map(&ah, A.hi, A.rows, A.cols, A.ld, abox, a_mn) || !make_map(&al, A.lo, A.rows, A.cols, A.ld, abox, a_mn) ||
+        !make_map(&bh, B.hi, B.rows, B.cols, B.ld, bbox, b_mn) || !make_map(&bl, B.lo, B.rows, B.cols, B.ld, bbox, b_mn))
         return -1;
     const int work = p.tiles_m * p.tiles_n * p.splits;
     const int grid = std::min(work, sm_count);

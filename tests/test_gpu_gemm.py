@@ -60,7 +60,16 @@ def test_tcgen05_gemm(a_mn, b_mn, M, N, K, a_ld, b_ld, splits):
     out = eng.debug_gemm(1, a_mn, b_mn, ah, al, a_ld, bh, bl, b_ld, M, N, K, splits).sum(0).cpu().numpy()
     scale = np.abs(ref).max()
     err = np.abs(out - ref).max() / scale
-    assert np.isfinite(out).all()
-    assert err < 2e-6, err                                   # fp32-level: 3xTF32, fp32 accumulate
     simt = eng.debug_gemm(0, a_mn, b_mn, ah, al, a_ld, bh, bl, b_ld, M, N, K, splits).sum(0).cpu().numpy()
-    assert np.abs(simt - ref).max() / scale < 2e-6
+    err_simt = np.abs(simt - ref).max() / scale
+    bad = np.argwhere(~(np.abs(out - ref) < 1e-4 * scale))
+    print(f"\nGEMM a_mn={a_mn} b_mn={b_mn} M={M} N={N} K={K}: tc err {err:.3e}  simt err {err_simt:.3e}  bad {len(bad)}/{out.size}"
+          f" first bad {bad[:4].tolist()} rows-with-bad {np.unique(bad[:, 0])[:12].tolist()} cols-with-bad {np.unique(bad[:, 1])[:12].tolist()}")
+    assert np.isfinite(out).all()
+    assert err_simt < 2e-6
+    assert err < 3e-5, err              # TMEM accumulation rounds toward zero at every MMA step
+    # promoted accumulation (fresh TMEM accumulator per k-block, partials summed in fp32 registers): fp32-level
+    acc = eng.debug_gemm(2, a_mn, b_mn, ah, al, a_ld, bh, bl, b_ld, M, N, K, splits).sum(0).cpu().numpy()
+    err_acc = np.abs(acc - ref).max() / scale
+    print(f"     promoted: err {err_acc:.3e}")
+    assert err_acc < 2e-6, err_acc
