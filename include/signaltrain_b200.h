@@ -77,6 +77,12 @@ int st_forward(st_handle* h, const float* x, const float* knobs, int batch,
                const float* const* params, float* y_hat, float* mag, float* mag_hat,
                float* const* acts, void* stream);
 
+/* model.train() / model.eval() + torch.no_grad(): when training (the default) st_forward also saves the autoencoders'
+ * hidden activations (~1.3 KB per (window, bin)) for the following st_backward; switch it off for validation / inference
+ * (train.py:39-48, utils/predict_long.py:66) to skip those writes.  st_backward after a non-training forward still works
+ * (it recomputes the chain with the slower SIMT kernels). */
+int st_set_training(st_handle* h, int on);
+
 /* loss_functions.calc_loss(y_hat, y, mag_hat, scale_by_freq=..., l1_lambda): loss_functions.py:26-43,
  * branches :34 (scale_by_freq NULL: l1_coef*mean|mag_hat|) and :36 (l1_coef*mean|mag_hat*s|; the caller
  * passes l1_coef = l1_lambda/10 as the reference does).  scale_by_freq is F floats (the reference

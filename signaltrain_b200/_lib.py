@@ -46,6 +46,7 @@ _SIGNATURES = {
     "st_train_step": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p, ctypes.c_float,
                                      ctypes.POINTER(StAdam), c_float_p, ctypes.c_void_p]),
+    "st_set_training": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "st_launch_count": (ctypes.c_long, [ctypes.c_void_p]),
     "st_profile_stage_count": (ctypes.c_int, []),
     "st_profile_stage_name": (ctypes.c_char_p, [ctypes.c_int]),

@@ -1,0 +1,733 @@
+// Autoencoders on the tensor cores (production path; st_ae.cu's SIMT kernels serve return_acts and act as cross-check).
+//
+// The nine Linear layers of AsymAutoEncoder (nn_proc.py:47-57,79-121) are dense contractions over rows = (batch, bin)
+// pairs with tiny K/N (9..64).  Each WARP owns 32 rows (two m16 tiles) and walks the whole chain with warp-level
+// mma.sync.m16n8k8 (TF32 operands, FP32 accumulate, 3xTF32 split for fp32 fidelity: a_lo*w_hi + a_hi*w_lo + a_hi*w_hi):
+//   * activations live in a per-warp shared-memory tile [32 rows][feature] (row stride 68 -> conflict-free fragment
+//     loads); a layer reads its A fragments from it, keeps ALL its outputs in accumulator registers, then overwrites
+//     the tile in place -- no block-wide barrier anywhere in the chain, only __syncwarp;
+//   * weights are staged once per CTA in their reference layout W[out][in] (row stride in+4 -> conflict-free B
+//     fragments) and split into tf32 hi/lo on the fly;
+//   * the k loop of every layer is a real loop (compact code: the first, fully unrolled version of this kernel was
+//     I-cache bound, see profiles/), the n loop is unrolled over the accumulators.
+// Forward: one launch per autoencoder (the phase launch consumes mag_hat and finishes polar->rect, nn_proc.py:322-326).
+// When training, the forward also saves the eight hidden activations + the last ELU output per row (272+16 floats);
+// the backward kernels read them back instead of recomputing the chain.
+#include <algorithm>
+
+#include "st_common.cuh"
+
+namespace {
+
+constexpr int RS = 68;                   // activation tile row stride (floats): 4*odd -> conflict-free A fragments
+constexpr int ROWS_PER_WARP = 32;
+constexpr int FWD_WARPS = 12;
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// ELU(alpha=1).  exp through MUFU.EX2 (__expf): abs error <= ~3e-7 on outputs in (-1, 0], far inside the 1e-5 waveform
+// budget ("precision"); expm1f would cost several times the instructions of the MMAs it sits between.
+__device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : __expf(z) - 1.f; }
+
+// c[mt][n][.] = bias + sum_k act[row][k] * W[8n+g..][k]   for the warp's 32 rows; k loop rolled, n unrolled.
+//   A fragment (m16 x k8): a0 (row g, k t), a1 (row g+8, k t), a2 (row g, k t+4), a3 (row g+8, k t+4)
+//   B fragment (k8 x n8):  b0 (k t, n g), b1 (k t+4, n g)      with B[k][n] = W[n][k]
+//   C fragment (m16 x n8): c0 (row g, n 2t), c1 (row g, n 2t+1), c2 (row g+8, n 2t), c3 (row g+8, n 2t+1)
+template <int NT>
+__device__ __forceinline__ void layer_mma(const float* __restrict__ act, int ksteps, const float* __restrict__ W, int ld,
+                                          const float* __restrict__ bias, float (&c)[2][NT][4], int g, int t) {
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        float2 bb = make_float2(0.f, 0.f);
+        if (bias) bb = *reinterpret_cast<const float2*>(bias + 8 * n + 2 * t);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) { c[mt][n][0] = bb.x; c[mt][n][1] = bb.y; c[mt][n][2] = bb.x; c[mt][n][3] = bb.y; }
+    }
+#pragma unroll 1
+    for (int j = 0; j < ksteps; ++j) {
+        uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const float* ap = act + (16 * mt + g) * RS + 8 * j + t;
+            split_tf32(ap[0], ahi[mt][0], alo[mt][0]);
+            split_tf32(ap[8 * RS], ahi[mt][1], alo[mt][1]);
+            split_tf32(ap[4], ahi[mt][2], alo[mt][2]);
+            split_tf32(ap[8 * RS + 4], ahi[mt][3], alo[mt][3]);
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const float* wp = W + (8 * n + g) * ld + 8 * j + t;
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(wp[0], bh0, bl0);
+            split_tf32(wp[4], bh1, bl1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], alo[mt], bh0, bh1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], ahi[mt], bl0, bl1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], ahi[mt], bh0, bh1);
+        }
+    }
+}
+
+// ELU the accumulators and overwrite the warp's activation tile (columns [0, 8*NT)).
+template <int NT>
+__device__ __forceinline__ void store_act(float* __restrict__ act, const float (&c)[2][NT][4], int g, int t) {
+    __syncwarp();          // every lane has finished reading the previous contents
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            float* p = act + (16 * mt + g) * RS + 8 * n + 2 * t;
+            *reinterpret_cast<float2*>(p) = make_float2(elu_f(c[mt][n][0]), elu_f(c[mt][n][1]));
+            *reinterpret_cast<float2*>(p + 8 * RS) = make_float2(elu_f(c[mt][n][2]), elu_f(c[mt][n][3]));
+        }
+    __syncwarp();
+}
+
+// Copy columns [0, width) of the warp's tile to the saved-activation record of each row (coalesced float4 rows).
+__device__ __forceinline__ void save_tile(const float* __restrict__ act, float* __restrict__ save, long R0, long BF, int ss,
+                                          int soff, int width, int lane) {
+    const int w4 = width >> 2;
+    for (int idx = lane; idx < ROWS_PER_WARP * w4; idx += 32) {
+        const int r = idx / w4, c4 = idx - r * w4;
+        if (R0 + r < BF)
+            *reinterpret_cast<float4*>(save + (R0 + r) * ss + soff + 4 * c4) = *reinterpret_cast<const float4*>(act + r * RS + 4 * c4);
+    }
+}
+
+struct MmaGeom {
+    int ks[ST_AE_LAYERS];      // k-steps of 8 (layer 5: 2 + 2 knob steps)
+    int outp[ST_AE_LAYERS];    // outputs padded to a multiple of 8
+    int ld[ST_AE_LAYERS];      // smem row stride of W_l: 8*ks + 4
+    int off[ST_AE_LAYERS];     // float offset of W_l in the weight block
+    int boff[ST_AE_LAYERS];    // float offset of bias_l in the bias block
+    int soff[ST_AE_LAYERS];    // offset of layer l's output inside a saved-activation record
+    int wfloats, bfloats;
+    int soff_v;                // offset of the input track (mag or phase, 8*ks[0] columns) inside a record
+    int ss;                    // saved-activation record length (floats)
+};
+
+// Stage one AE's weights (reference layout W[out][in], zero padded) and biases.
+__device__ void stage_weights_mma(const MmaGeom& mg, const AeGeom& g, const AeParams& p, float* w, float* bias, int tid,
+                                  int nthreads) {
+    for (int l = 0; l < ST_AE_LAYERS; ++l) {
+        const int IN = g.in[l], OUT = g.out[l], ld = mg.ld[l];
+        const int total = mg.outp[l] * ld;
+        for (int idx = tid; idx < total; idx += nthreads) {
+            const int o = idx / ld, i = idx - o * ld;
+            w[mg.off[l] + idx] = (o < OUT && i < IN) ? p.W[l][o * IN + i] : 0.f;
+        }
+        for (int o = tid; o < mg.outp[l]; o += nthreads) bias[mg.boff[l] + o] = (o < OUT) ? p.b[l][o] : 0.f;
+    }
+}
+
+// AE = 0: magnitude autoencoder ('sf' skip-filter).  AE = 1: phase autoencoder + residual + polar->rect.
+template <int NT9, int AE>
+__global__ void __launch_bounds__(FWD_WARPS * 32, 1)
+ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __restrict__ spec,
+                  const float* __restrict__ knobs, int B, float* __restrict__ mag_out, float* __restrict__ mag_hat,
+                  float* __restrict__ phs_hat, float* __restrict__ ri, float* __restrict__ ri_lo, float* __restrict__ save) {
+    extern __shared__ __align__(16) float smem[];
+    float* W = smem;
+    float* bias = W + mg.wfloats;
+    float* acts = bias + mg.bfloats;
+    stage_weights_mma(mg, g, p, W, bias, threadIdx.x, blockDim.x);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gq = lane >> 2, t = lane & 3;
+    float* act = acts + warp * (ROWS_PER_WARP * RS);
+    const long BF = (long)B * d.F;
+    const long ntiles = (BF + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
+    const int tail0 = d.T - d.OT;
+    const int rowstride = 2 * d.Fp;
+    const int kcols = 8 * mg.ks[0];
+
+    for (long tile = (long)blockIdx.x * FWD_WARPS + warp; tile < ntiles; tile += (long)gridDim.x * FWD_WARPS) {
+        const long R0 = tile * ROWS_PER_WARP;
+        // ---- input tracks: lane <-> row (coalesced along the bin axis), columns = time frames
+        {
+            const long R = R0 + lane;
+            const bool ok = R < BF;
+            const int b = ok ? (int)(R / d.F) : 0;
+            const int f = ok ? (int)(R - (long)b * d.F) : 0;
+            const float* sp = spec + (long)b * d.Tp * rowstride + f;
+            float* mo = (AE == 0 && mag_out) ? mag_out + (long)b * d.T * d.F + f : nullptr;
+            __syncwarp();
+#pragma unroll 2
+            for (int tt = 0; tt < kcols; ++tt) {
+                float v = 0.f;
+                if (ok && tt < d.T) {
+                    const float re = __ldg(sp + (long)tt * rowstride), im = __ldg(sp + (long)tt * rowstride + d.Fp);
+                    if (AE == 0) {
+                        v = sqrtf(re * re + im * im);                                      // nn_proc.py:309
+                        if (mo) mo[(long)tt * d.F] = v;
+                    } else {
+                        v = atan2f(im, re + 1e-7f);                                        // nn_proc.py:310
+                    }
+                }
+                act[lane * RS + tt] = v;
+            }
+            __syncwarp();
+            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff_v, kcols, lane);
+        }
+        // ---- fnn_enc .. fnn_enc4
+        {
+            float c[2][8][4];
+            layer_mma<8>(act, mg.ks[0], W + mg.off[0], mg.ld[0], bias + mg.boff[0], c, gq, t);
+            store_act<8>(act, c, gq, t);
+            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[0], 64, lane);
+        }
+        {
+            float c[2][4][4];
+            layer_mma<4>(act, 8, W + mg.off[1], mg.ld[1], bias + mg.boff[1], c, gq, t);
+            store_act<4>(act, c, gq, t);
+            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[1], 32, lane);
+        }
+        {
+            float c[2][2][4];
+            layer_mma<2>(act, 4, W + mg.off[2], mg.ld[2], bias + mg.boff[2], c, gq, t);
+            store_act<2>(act, c, gq, t);
+            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[2], 16, lane);
+        }
+        {
+            float c[2][2][4];
+            layer_mma<2>(act, 2, W + mg.off[3], mg.ld[3], bias + mg.boff[3], c, gq, t);
+            store_act<2>(act, c, gq, t);
+        }
+        // ---- knob concat (torch.cat, nn_proc.py:95-96): columns 16..31 = knobs, zero padded
+        {
+            const long R = R0 + lane;
+            const bool ok = R < BF;
+            const float* kp = knobs + (ok ? R / d.F : 0) * d.K;
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) act[lane * RS + 16 + kk] = (ok && kk < d.K) ? __ldg(kp + kk) : 0.f;
+            __syncwarp();
+            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[3], 32, lane);     // h4 ++ knobs: fnn_addknobs' input
+        }
+        {
+            float c[2][2][4];
+            layer_mma<2>(act, 4, W + mg.off[4], mg.ld[4], bias + mg.boff[4], c, gq, t);
+            store_act<2>(act, c, gq, t);
+            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[4], 16, lane);
+        }
+        {
+            float c[2][2][4];
+            layer_mma<2>(act, 2, W + mg.off[5], mg.ld[5], bias + mg.boff[5], c, gq, t);
+            store_act<2>(act, c, gq, t);
+            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[5], 16, lane);
+        }
+        {
+            float c[2][4][4];
+            layer_mma<4>(act, 2, W + mg.off[6], mg.ld[6], bias + mg.boff[6], c, gq, t);
+            store_act<4>(act, c, gq, t);
+            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[6], 32, lane);
+        }
+        {
+            float c[2][8][4];
+            layer_mma<8>(act, 4, W + mg.off[7], mg.ld[7], bias + mg.boff[7], c, gq, t);
+            store_act<8>(act, c, gq, t);
+            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[7], 64, lane);
+        }
+        // ---- fnn_dec; ELU'd outputs go through the tile so the output-side math runs lane <-> row (coalesced, and one
+        //      copy of the transcendental code instead of one per accumulator register)
+        {
+            float c9[2][NT9][4];
+            layer_mma<NT9>(act, 8, W + mg.off[8], mg.ld[8], bias + mg.boff[8], c9, gq, t);
+            store_act<NT9>(act, c9, gq, t);
+        }
+        {
+            const long R = R0 + lane;
+            if (R < BF) {
+                const int b = (int)(R / d.F), f = (int)(R - (long)b * d.F);
+                const float* sp = spec + ((long)b * d.Tp + tail0) * rowstride + f;
+#pragma unroll 1
+                for (int j = 0; j < d.OT; ++j) {
+                    const float ev = act[lane * RS + j];
+                    const float re = __ldg(sp + (long)j * rowstride), im = __ldg(sp + (long)j * rowstride + d.Fp);
+                    const long oo = ((long)b * d.OT + j) * d.F + f;
+                    if (save) save[R * mg.ss + mg.soff[8] + j] = ev;
+                    if (AE == 0) {
+                        mag_hat[oo] = ev * sqrtf(re * re + im * im);                         // 'sf', nn_proc.py:115
+                    } else {
+                        const float ph = ev + atan2f(im, re + 1e-7f);                       // nn_proc.py:322
+                        const float m = mag_hat[oo];
+                        float sn, cs;
+                        sincosf(ph, &sn, &cs);
+                        phs_hat[oo] = ph;
+                        const long orr = ((long)b * d.OTp + j) * rowstride + f;
+                        st_split_tf32(m * cs, ri[orr], ri_lo[orr]);                         // nn_proc.py:325-326
+                        st_split_tf32(m * sn, ri[orr + d.Fp], ri_lo[orr + d.Fp]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------------
+constexpr int BWD_WARPS = 8;
+constexpr int CTA_ROWS = BWD_WARPS * ROWS_PER_WARP;     // 256 rows per CTA tile
+
+__device__ __forceinline__ float elu_grad(float h) { return h > 0.f ? 1.f : h + 1.f; }   // dELU/dz through the output h
+
+// Data gradient of one layer for the warp's own 32 rows:  c[row][i] = sum_o gz[row][o] * W[o][i]
+//   B fragment (k8 x n8) with B[k = o][n = i] = W[o][i]:  b0 = W[(8j+t)*ld + 8n+g],  b1 = W[(8j+t+4)*ld + 8n+g]
+template <int NT>
+__device__ __forceinline__ void layer_mma_T(const float* __restrict__ gz, int ksteps, const float* __restrict__ W, int ld,
+                                            float (&c)[2][NT][4], int g, int t) {
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) c[mt][n][0] = c[mt][n][1] = c[mt][n][2] = c[mt][n][3] = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < ksteps; ++j) {
+        uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const float* ap = gz + (16 * mt + g) * RS + 8 * j + t;
+            split_tf32(ap[0], ahi[mt][0], alo[mt][0]);
+            split_tf32(ap[8 * RS], ahi[mt][1], alo[mt][1]);
+            split_tf32(ap[4], ahi[mt][2], alo[mt][2]);
+            split_tf32(ap[8 * RS + 4], ahi[mt][3], alo[mt][3]);
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const float* wp = W + (8 * j + t) * ld + 8 * n + g;
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(wp[0], bh0, bl0);
+            split_tf32(wp[4 * ld], bh1, bl1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], alo[mt], bh0, bh1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], ahi[mt], bl0, bl1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], ahi[mt], bh0, bh1);
+        }
+    }
+}
+
+// gz_{l-1} = (data gradient) * ELU'(h_{l-1});  h_{l-1} is read from the saved records (columns hbase .. hbase+8*NT).
+template <int NT>
+__device__ __forceinline__ void store_gz(float* __restrict__ dst, const float (&c)[2][NT][4], const float* __restrict__ save,
+                                         long R0, long BF, int ss, int hbase, int g, int t) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long R = R0 + 16 * mt + g + 8 * h;
+            const bool ok = R < BF;
+            const float* hp = save + (ok ? R : 0) * ss + hbase + 2 * t;
+            float* p = dst + (16 * mt + g + 8 * h) * RS + 2 * t;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                float2 hh = make_float2(0.f, 0.f);
+                if (ok) hh = __ldg(reinterpret_cast<const float2*>(hp + 8 * n));
+                *reinterpret_cast<float2*>(p + 8 * n) =
+                    make_float2(c[mt][n][2 * h] * elu_grad(hh.x), c[mt][n][2 * h + 1] * elu_grad(hh.y));
+            }
+        }
+}
+
+// Weight gradient of one layer, this warp's (mo, ni) output tiles, reduction over the CTA tile's 256 rows:
+//   dW[o][i] += sum_rows gz[row][o] * h[row][i]
+//   A = gz^T from the shared plane (m = o, k = row):  a0 (m g, k t) = P[(8ks+t)*RS + 16mo+g], a1 (m g+8, k t),
+//                                                     a2 (m g, k t+4), a3 (m g+8, k t+4)
+//   B = h from the saved records (k = row, n = i):    b0 (k t, n g) = S[(R0+8ks+t)*ss + hbase + 8ni+g], b1 (k t+4, n g)
+// Pair p = warp + 8q -> (mo = p % MB, ni = p / MB); MB divides 8, so all of a warp's pairs share mo (one A fragment).
+template <int NPW>
+__device__ __forceinline__ void wgrad_mma(float (&acc)[NPW][4], const float* __restrict__ plane, int MB, int NB,
+                                          const float* __restrict__ save, long R0c, long BF, int ss, int hbase, int warp, int g,
+                                          int t) {
+    const int P = MB * NB;
+    if (warp >= P) return;
+    const int mo = warp % MB;
+    float tmp[2][NPW][4];
+#pragma unroll
+    for (int par = 0; par < 2; ++par)
+#pragma unroll
+        for (int q = 0; q < NPW; ++q) tmp[par][q][0] = tmp[par][q][1] = tmp[par][q][2] = tmp[par][q][3] = 0.f;
+    const float* pa = plane + t * RS + 16 * mo + g;
+#pragma unroll 1
+    for (int ks2 = 0; ks2 < CTA_ROWS / 16; ++ks2) {
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+            const int ks = 2 * ks2 + par;
+            uint32_t ahi[4], alo[4];
+            const float* ap = pa + 8 * ks * RS;
+            split_tf32(ap[0], ahi[0], alo[0]);
+            split_tf32(ap[8], ahi[1], alo[1]);
+            split_tf32(ap[4 * RS], ahi[2], alo[2]);
+            split_tf32(ap[4 * RS + 8], ahi[3], alo[3]);
+            const long r0 = R0c + 8 * ks + t, r1 = r0 + 4;
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) {
+                const int pidx = warp + 8 * q;
+                if (pidx < P) {
+                    const int ni = pidx / MB;
+                    const float v0 = r0 < BF ? __ldg(save + r0 * ss + hbase + 8 * ni + g) : 0.f;
+                    const float v1 = r1 < BF ? __ldg(save + r1 * ss + hbase + 8 * ni + g) : 0.f;
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split_tf32(v0, bh0, bl0);
+                    split_tf32(v1, bh1, bl1);
+                    mma_tf32(tmp[par][q], alo, bh0, bh1);
+                    mma_tf32(tmp[par][q], ahi, bl0, bl1);
+                    mma_tf32(tmp[par][q], ahi, bh0, bh1);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NPW; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[q][e] += tmp[0][q][e] + tmp[1][q][e];
+}
+
+template <int NPW>
+__device__ __forceinline__ void wgrad_flush(const float (&acc)[NPW][4], float* __restrict__ dst, int MB, int NB, int OUT, int IN,
+                                            int warp, int g, int t) {
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) {
+        const int pidx = warp + 8 * q;
+        if (pidx >= MB * NB) continue;
+        const int mo = pidx % MB, ni = pidx / MB;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int o = 16 * mo + g + 8 * (e >> 1), i = 8 * ni + 2 * t + (e & 1);
+            if (o < OUT && i < IN) dst[o * IN + i] = acc[q][e];
+        }
+    }
+}
+
+// Bias gradient: column sums of the plane over the CTA tile's rows; output o is owned by warp o % 8.
+__device__ __forceinline__ void bias_grad(float* __restrict__ db, const float* __restrict__ plane, int outp, int warp, int lane) {
+    for (int o = warp; o < outp; o += BWD_WARPS) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < CTA_ROWS / 32; ++q) s += plane[(lane + 32 * q) * RS + o];
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+        if (lane == 0) db[o] += s;
+    }
+}
+
+// AE = 0: magnitude autoencoder, AE = 1: phase autoencoder.  NT1 = n-tiles of the input track (4: T <= 32, 8: T <= 64).
+template <int NT1, int AE>
+__global__ void __launch_bounds__(BWD_WARPS * 32, 1)
+ae_bwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __restrict__ spec, int B,
+                  const float* __restrict__ save, const float* __restrict__ mag_hat, const float* __restrict__ phs_hat,
+                  const float* __restrict__ g_ri, const float* __restrict__ g_mag_hat, const float* __restrict__ g_mag,
+                  float* __restrict__ tail_ws, float* __restrict__ g_spec, float* __restrict__ g_spec_lo,
+                  float* __restrict__ partials) {
+    extern __shared__ __align__(16) float smem[];
+    float* W = smem;
+    float* bias = W + mg.wfloats;                      // staged but unused here (keeps one staging routine)
+    float* plane0 = bias + mg.bfloats;
+    float* plane1 = plane0 + CTA_ROWS * RS;
+    float* dbias = plane1 + CTA_ROWS * RS;             // [9][64]
+    stage_weights_mma(mg, g, p, W, bias, threadIdx.x, blockDim.x);
+    for (int i = threadIdx.x; i < ST_AE_LAYERS * 64; i += blockDim.x) dbias[i] = 0.f;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gq = lane >> 2, t = lane & 3;
+    const long BF = (long)B * d.F;
+    const long nct = (BF + CTA_ROWS - 1) / CTA_ROWS;
+    const int tail0 = d.T - d.OT;
+    const int rowstride = 2 * d.Fp;
+    const int ss = mg.ss;
+    const int ks1 = mg.ks[0];
+    float* my0 = plane0 + warp * ROWS_PER_WARP * RS;
+    float* my1 = plane1 + warp * ROWS_PER_WARP * RS;
+
+    // persistent weight-gradient accumulators: [pairs of this warp][C fragment]
+    float a1[4][4], a2[2][4], a3[1][4], a4[1][4], a5[1][4], a6[1][4], a7[1][4], a8[2][4], a9[1][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a1[q][e] = 0.f;
+        a2[0][e] = a2[1][e] = a8[0][e] = a8[1][e] = 0.f;
+        a3[0][e] = a4[0][e] = a5[0][e] = a6[0][e] = a7[0][e] = a9[0][e] = 0.f;
+    }
+
+    for (long ct = blockIdx.x; ct < nct; ct += gridDim.x) {
+        const long R0c = ct * CTA_ROWS, R0 = R0c + warp * ROWS_PER_WARP;
+        // ---- output side: gz9 into plane0 (own rows), skip/residual gradient to tail_ws.  lane <-> row.
+        {
+            const long R = R0 + lane;
+            const bool ok = R < BF;
+            const int b = ok ? (int)(R / d.F) : 0, f = ok ? (int)(R - (long)b * d.F) : 0;
+            const float* rec = save + (ok ? R : 0) * ss;
+#pragma unroll 1
+            for (int j = 0; j < mg.outp[8]; ++j) {
+                float gz = 0.f;
+                if (ok && j < d.OT) {
+                    const float e9 = __ldg(rec + mg.soff[8] + j);
+                    const long oo = ((long)b * d.OT + j) * d.F + f;
+                    const long orr = ((long)b * d.OTp + j) * rowstride + f;
+                    const float gre = __ldg(g_ri + orr), gim = __ldg(g_ri + orr + d.Fp);
+                    float sn, cs;
+                    sincosf(__ldg(phs_hat + oo), &sn, &cs);
+                    if (AE == 0) {   // an = mag_hat (cos, sin);  mag_hat = ELU(d) * v_tail     (nn_proc.py:115, 325-326)
+                        float gm = gre * cs + gim * sn;
+                        if (g_mag_hat) gm += __ldg(g_mag_hat + oo);
+                        gz = gm * __ldg(rec + mg.soff_v + tail0 + j) * elu_grad(e9);
+                        tail_ws[oo] = gm * e9;
+                    } else {         // phs_hat = ELU(d) + phs_tail                              (nn_proc.py:322)
+                        const float gp = __ldg(mag_hat + oo) * (gim * cs - gre * sn);
+                        gz = gp * elu_grad(e9);
+                        tail_ws[oo] = gp;
+                    }
+                }
+                my0[lane * RS + j] = gz;
+            }
+        }
+        __syncthreads();
+        // ---- layer 9 (fnn_dec): OUT = OT (<= 16), IN = 64
+        wgrad_mma<1>(a9, plane0, 1, 8, save, R0c, BF, ss, mg.soff[7], warp, gq, t);
+        bias_grad(dbias + 8 * 64, plane0, mg.outp[8], warp, lane);
+        {
+            float c[2][8][4];
+            layer_mma_T<8>(my0, mg.outp[8] / 8, W + mg.off[8], mg.ld[8], c, gq, t);
+            store_gz<8>(my1, c, save, R0, BF, ss, mg.soff[7], gq, t);
+        }
+        __syncthreads();
+        // ---- layer 8 (fnn_dec2): 64 <- 32
+        wgrad_mma<2>(a8, plane1, 4, 4, save, R0c, BF, ss, mg.soff[6], warp, gq, t);
+        bias_grad(dbias + 7 * 64, plane1, 64, warp, lane);
+        {
+            float c[2][4][4];
+            layer_mma_T<4>(my1, 8, W + mg.off[7], mg.ld[7], c, gq, t);
+            store_gz<4>(my0, c, save, R0, BF, ss, mg.soff[6], gq, t);
+        }
+        __syncthreads();
+        // ---- layer 7 (fnn_dec3): 32 <- 16
+        wgrad_mma<1>(a7, plane0, 2, 2, save, R0c, BF, ss, mg.soff[5], warp, gq, t);
+        bias_grad(dbias + 6 * 64, plane0, 32, warp, lane);
+        {
+            float c[2][2][4];
+            layer_mma_T<2>(my0, 4, W + mg.off[6], mg.ld[6], c, gq, t);
+            store_gz<2>(my1, c, save, R0, BF, ss, mg.soff[5], gq, t);
+        }
+        __syncthreads();
+        // ---- layer 6 (fnn_dec4): 16 <- 16
+        wgrad_mma<1>(a6, plane1, 1, 2, save, R0c, BF, ss, mg.soff[4], warp, gq, t);
+        bias_grad(dbias + 5 * 64, plane1, 16, warp, lane);
+        {
+            float c[2][2][4];
+            layer_mma_T<2>(my1, 2, W + mg.off[5], mg.ld[5], c, gq, t);
+            store_gz<2>(my0, c, save, R0, BF, ss, mg.soff[4], gq, t);
+        }
+        __syncthreads();
+        // ---- layer 5 (fnn_addknobs): 16 <- 16 + knobs (the h4 slot of the record holds h4 ++ knobs, 32 wide)
+        wgrad_mma<1>(a5, plane0, 1, 4, save, R0c, BF, ss, mg.soff[3], warp, gq, t);
+        bias_grad(dbias + 4 * 64, plane0, 16, warp, lane);
+        {
+            float c[2][2][4];                                   // only the 16 non-knob inputs carry gradient
+            layer_mma_T<2>(my0, 2, W + mg.off[4], mg.ld[4], c, gq, t);
+            store_gz<2>(my1, c, save, R0, BF, ss, mg.soff[3], gq, t);
+        }
+        __syncthreads();
+        // ---- layer 4 (fnn_enc4): 16 <- 16
+        wgrad_mma<1>(a4, plane1, 1, 2, save, R0c, BF, ss, mg.soff[2], warp, gq, t);
+        bias_grad(dbias + 3 * 64, plane1, 16, warp, lane);
+        {
+            float c[2][2][4];
+            layer_mma_T<2>(my1, 2, W + mg.off[3], mg.ld[3], c, gq, t);
+            store_gz<2>(my0, c, save, R0, BF, ss, mg.soff[2], gq, t);
+        }
+        __syncthreads();
+        // ---- layer 3 (fnn_enc3): 16 <- 32
+        wgrad_mma<1>(a3, plane0, 1, 4, save, R0c, BF, ss, mg.soff[1], warp, gq, t);
+        bias_grad(dbias + 2 * 64, plane0, 16, warp, lane);
+        {
+            float c[2][4][4];
+            layer_mma_T<4>(my0, 2, W + mg.off[2], mg.ld[2], c, gq, t);
+            store_gz<4>(my1, c, save, R0, BF, ss, mg.soff[1], gq, t);
+        }
+        __syncthreads();
+        // ---- layer 2 (fnn_enc2): 32 <- 64
+        wgrad_mma<2>(a2, plane1, 2, 8, save, R0c, BF, ss, mg.soff[0], warp, gq, t);
+        bias_grad(dbias + 1 * 64, plane1, 32, warp, lane);
+        {
+            float c[2][8][4];
+            layer_mma_T<8>(my1, 4, W + mg.off[1], mg.ld[1], c, gq, t);
+            store_gz<8>(my0, c, save, R0, BF, ss, mg.soff[0], gq, t);
+        }
+        __syncthreads();
+        // ---- layer 1 (fnn_enc): 64 <- T.  Data gradient = dL/d(track), turned into dL/d(re, im).
+        wgrad_mma<4>(a1, plane0, 4, ks1, save, R0c, BF, ss, mg.soff_v, warp, gq, t);
+        bias_grad(dbias + 0 * 64, plane0, 64, warp, lane);
+        {
+            float c[2][NT1][4];
+            layer_mma_T<NT1>(my0, 8, W + mg.off[0], mg.ld[0], c, gq, t);
+            // through the (own rows of the) other plane so the output-side math runs lane <-> row with one code copy
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int n = 0; n < NT1; ++n) {
+                    float* q = my1 + (16 * mt + gq) * RS + 8 * n + 2 * t;
+                    *reinterpret_cast<float2*>(q) = make_float2(c[mt][n][0], c[mt][n][1]);
+                    *reinterpret_cast<float2*>(q + 8 * RS) = make_float2(c[mt][n][2], c[mt][n][3]);
+                }
+            __syncwarp();
+            const long R = R0 + lane;
+            if (R < BF) {
+                const int b = (int)(R / d.F), f = (int)(R - (long)b * d.F);
+                const float* rec = save + R * ss + mg.soff_v;
+#pragma unroll 1
+                for (int tt = 0; tt < d.T; ++tt) {
+                    float gv = my1[lane * RS + tt];
+                    if (tt >= tail0) gv += tail_ws[((long)b * d.OT + (tt - tail0)) * d.F + f];
+                    const long o = ((long)b * d.Tp + tt) * rowstride + f;
+                    const float re = __ldg(spec + o), im = __ldg(spec + o + d.Fp);
+                    if (AE == 0) {          // mag = sqrt(re^2+im^2); subgradient 0 at 0 (torch.norm backward)
+                        if (g_mag) gv += __ldg(g_mag + ((long)b * d.T + tt) * d.F + f);
+                        const float m = __ldg(rec + tt);
+                        const float sc = m > 0.f ? gv / m : 0.f;
+                        g_spec[o] = sc * re;
+                        g_spec[o + d.Fp] = sc * im;
+                    } else {                // phs = atan2(im, re + 1e-7); second pass: finish the sum, store (hi, lo)
+                        const float u = re + 1e-7f;
+                        const float den = u * u + im * im;
+                        const float sc = den > 0.f ? gv / den : 0.f;
+                        st_split_tf32(g_spec[o] - sc * im, g_spec[o], g_spec_lo[o]);
+                        st_split_tf32(g_spec[o + d.Fp] + sc * u, g_spec[o + d.Fp], g_spec_lo[o + d.Fp]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- flush this CTA's partial gradients (summed over CTAs in fixed order by ae_grad_reduce_kernel)
+    float* dst = partials + ((long)blockIdx.x * 2 + AE) * g.flat_total;
+    wgrad_flush<4>(a1, dst + g.flat_off[0], 4, ks1, 64, d.T, warp, gq, t);
+    wgrad_flush<2>(a2, dst + g.flat_off[1], 2, 8, 32, 64, warp, gq, t);
+    wgrad_flush<1>(a3, dst + g.flat_off[2], 1, 4, 16, 32, warp, gq, t);
+    wgrad_flush<1>(a4, dst + g.flat_off[3], 1, 2, 16, 16, warp, gq, t);
+    wgrad_flush<1>(a5, dst + g.flat_off[4], 1, 4, 16, 16 + d.K, warp, gq, t);
+    wgrad_flush<1>(a6, dst + g.flat_off[5], 1, 2, 16, 16, warp, gq, t);
+    wgrad_flush<1>(a7, dst + g.flat_off[6], 2, 2, 32, 16, warp, gq, t);
+    wgrad_flush<2>(a8, dst + g.flat_off[7], 4, 4, 64, 32, warp, gq, t);
+    wgrad_flush<1>(a9, dst + g.flat_off[8], 1, 8, d.OT, 64, warp, gq, t);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ST_AE_LAYERS * 64; i += blockDim.x) {
+        const int l = i >> 6, o = i & 63;
+        if (o < g.out[l]) dst[g.flat_off[l] + g.out[l] * g.in[l] + o] = dbias[i];
+    }
+}
+
+
+MmaGeom build_mma_geom(const AeGeom& g, int nt9) {
+    MmaGeom mg;
+    int off = 0, boff = 0;
+    const int soff[ST_AE_LAYERS] = {0, 64, 96, 112, 144, 160, 176, 208, 272};   // h1..h8 (h4 slot 32 wide: ++knobs), e9
+    for (int l = 0; l < ST_AE_LAYERS; ++l) {
+        mg.ks[l] = (l == 4) ? 4 : (g.in[l] + 7) / 8;     // layer 5: 16 features + 16 knob slots
+        mg.outp[l] = (l == 8) ? 8 * nt9 : (g.out[l] + 7) / 8 * 8;
+        mg.ld[l] = 8 * mg.ks[l] + 4;
+        mg.off[l] = off;
+        off += mg.outp[l] * mg.ld[l];
+        mg.boff[l] = boff;
+        boff += mg.outp[l];
+        mg.soff[l] = soff[l];
+    }
+    mg.wfloats = (off + 3) / 4 * 4;
+    mg.bfloats = (boff + 3) / 4 * 4;
+    mg.soff_v = 272 + 8 * nt9;
+    mg.ss = mg.soff_v + 8 * mg.ks[0];
+    return mg;
+}
+
+template <int NT9>
+void launch_fwd_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const AeParams& pm, const AeParams& pp, const float* spec,
+                     const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo, float* save_m,
+                     float* save_p, int grid, size_t smem, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(ae_fwd_mma_kernel<NT9, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(ae_fwd_mma_kernel<NT9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured = true;
+    }
+    ae_fwd_mma_kernel<NT9, 0><<<grid, FWD_WARPS * 32, smem, s>>>(d, g, mg, pm, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m);
+    ae_fwd_mma_kernel<NT9, 1><<<grid, FWD_WARPS * 32, smem, s>>>(d, g, mg, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_p);
+}
+
+}  // namespace
+
+int st_ae_mma_record_floats(const StDims& d) { return 272 + 8 * (d.OT <= 16 ? 2 : (d.OT <= 32 ? 4 : 8)) + (d.T + 7) / 8 * 8; }
+
+// save_m / save_p: NULL (inference) or B*F records of st_ae_mma_record_floats() floats each (training).
+// Returns false when the geometry is outside what the tensor-core kernels cover (caller uses the SIMT kernel).
+bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
+                              const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo,
+                              float* save_m, float* save_p, int sm_count, cudaStream_t s) {
+    if (d.T > 64 || d.OT > 64 || d.K > 16) return false;
+    const int nt9 = d.OT <= 16 ? 2 : (d.OT <= 32 ? 4 : 8);
+    const MmaGeom mg = build_mma_geom(g, nt9);
+    const size_t smem = sizeof(float) * ((size_t)mg.wfloats + mg.bfloats + (size_t)FWD_WARPS * ROWS_PER_WARP * RS);
+    if (smem > 227 * 1024) return false;
+    const long tiles = ((long)B * d.F + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
+    const int grid = (int)std::min<long>((tiles + FWD_WARPS - 1) / FWD_WARPS, sm_count);
+    if (nt9 == 2) launch_fwd_pair<2>(d, g, mg, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m, save_p, grid, smem, s);
+    else if (nt9 == 4) launch_fwd_pair<4>(d, g, mg, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m, save_p, grid, smem, s);
+    else launch_fwd_pair<8>(d, g, mg, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m, save_p, grid, smem, s);
+    return true;
+}
+
+namespace {
+template <int NT1>
+void launch_bwd_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const AeParams& pm, const AeParams& pp, const float* spec,
+                     int B, const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat, const float* g_ri,
+                     const float* g_mag_hat, const float* g_mag, float* tail_ws, float* g_spec, float* g_spec_lo, float* partials,
+                     int grid, size_t smem, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(ae_bwd_mma_kernel<NT1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(ae_bwd_mma_kernel<NT1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured = true;
+    }
+    ae_bwd_mma_kernel<NT1, 0><<<grid, BWD_WARPS * 32, smem, s>>>(d, g, mg, pm, spec, B, save_m, mag_hat, phs_hat, g_ri, g_mag_hat,
+                                                                 g_mag, tail_ws, g_spec, g_spec_lo, partials);
+    ae_bwd_mma_kernel<NT1, 1><<<grid, BWD_WARPS * 32, smem, s>>>(d, g, mg, pp, spec, B, save_p, mag_hat, phs_hat, g_ri, g_mag_hat,
+                                                                 g_mag, tail_ws, g_spec, g_spec_lo, partials);
+}
+}  // namespace
+
+// Tensor-core backward of both autoencoders from the records saved by st_launch_ae_forward_mma.  Writes g_spec (hi, lo)
+// and one partial-gradient vector per CTA into `partials` ([grid][2][flat_total]); returns the grid size (0 if the
+// geometry is not covered and the caller must use the SIMT kernel).
+int st_launch_ae_backward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, int B,
+                              const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat,
+                              const float* g_ri, const float* g_mag_hat, const float* g_mag, float* tail_ws, float* g_spec,
+                              float* g_spec_lo, float* partials, int sm_count, cudaStream_t s) {
+    if (d.T > 64 || d.OT > 16 || d.K > 16) return 0;
+    const MmaGeom mg = build_mma_geom(g, 2);
+    const size_t smem = sizeof(float) * ((size_t)mg.wfloats + mg.bfloats + 2 * (size_t)CTA_ROWS * RS + ST_AE_LAYERS * 64);
+    if (smem > 227 * 1024) return 0;
+    const long nct = ((long)B * d.F + CTA_ROWS - 1) / CTA_ROWS;
+    const int grid = (int)std::min<long>(nct, sm_count);
+    if (mg.ks[0] <= 4)
+        launch_bwd_pair<4>(d, g, mg, pm, pp, spec, B, save_m, save_p, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, tail_ws, g_spec,
+                           g_spec_lo, partials, grid, smem, s);
+    else
+        launch_bwd_pair<8>(d, g, mg, pm, pp, spec, B, save_m, save_p, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, tail_ws, g_spec,
+                           g_spec_lo, partials, grid, smem, s);
+    return grid;
+}

@@ -29,7 +29,12 @@ struct st_handle {
     bool use_tc = true;           // tcgen05/TMA GEMMs (falls back to the FFMA GEMM per call when a shape is not covered)
     float *part_a = nullptr, *part_s = nullptr, *ae_part = nullptr;
     float *yhat_ws = nullptr, *gy_ws = nullptr, *gmh_ws = nullptr;   // fused train step only
-    float* knobs_ws = nullptr;    // copy of the forward's knobs (the backward recomputes the AE chain)
+    float* knobs_ws = nullptr;    // copy of the forward's knobs (the SIMT backward recomputes the AE chain)
+    float *ae_save_m = nullptr, *ae_save_p = nullptr;   // per-row activation records written by the tensor-core forward
+    float* tail_ws = nullptr;     // skip / residual gradient scratch of the tensor-core backward
+    bool training = true;         // st_set_training: save activations in st_forward for a following st_backward
+    bool have_saves = false;      // the last forward wrote ae_save_*
+    bool use_mma_bwd = true;
     float* small = nullptr;       // reduction scratch + scalar outputs
     unsigned* counters = nullptr;
     double* win = nullptr;        // [hamming | GLA] in double, for st_init_frontend
@@ -171,6 +176,7 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     d.Tp = (d.Cp + H - 1) / H; d.OTp = (d.Lp + H - 1) / H;
     d.Sx = d.Tp * H; d.Sg = d.OTp * H;
     if (const char* e = getenv("ST_DISABLE_TCGEN05")) h->use_tc = !(e[0] == '1');
+    if (const char* e = getenv("ST_DISABLE_MMA_BACKWARD")) h->use_mma_bwd = !(e[0] == '1');
     build_geom(d, h->g);
     if (st_ae_configure(h, d, h->g)) {
         snprintf(g_create_err, sizeof(g_create_err), "%s", h->err);
@@ -240,7 +246,7 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
 static void free_batch_buffers(st_handle* h) {
     float** bufs[] = {&h->xpad, &h->xpad_lo, &h->spec, &h->ri, &h->ri_lo, &h->fo, &h->mag_hat_ws, &h->phs_hat_ws, &h->gwave,
                       &h->gwave_lo, &h->g_ri, &h->g_spec, &h->g_spec_lo, &h->ae_part, &h->yhat_ws, &h->gy_ws, &h->gmh_ws,
-                      &h->knobs_ws};
+                      &h->knobs_ws, &h->ae_save_m, &h->ae_save_p, &h->tail_ws};
     for (float** b : bufs) {
         if (*b) cudaFree(*b);
         *b = nullptr;
@@ -295,6 +301,9 @@ static int ensure_workspace(st_handle* h, int B) {
         {&h->ae_part, (long)h->sm_count * 2 * h->g.flat_total, true},
         {&h->yhat_ws, (long)B * d.L, false},     {&h->gy_ws, (long)B * d.L, false}, {&h->gmh_ws, (long)B * d.OT * d.F, false},
         {&h->knobs_ws, (long)B * std::max(d.K, 1), false},
+        {&h->ae_save_m, (long)B * d.F * st_ae_mma_record_floats(d), false},
+        {&h->ae_save_p, (long)B * d.F * st_ae_mma_record_floats(d), false},
+        {&h->tail_ws, (long)B * d.OT * d.F, false},
     };
     for (auto& r : req) {
         ST_CUDA_OK(cudaMalloc(r.p, r.n * sizeof(float)));
@@ -363,10 +372,15 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         AeParams pm, pp;
         split_params(params, pm, pp);
         // production path: tensor-core (mma.sync TF32x3) register-resident chain; the SIMT kernel serves return_acts
+        const bool save = h->training && h->use_mma_bwd;
+        h->have_saves = false;
         if (acts || !st_launch_ae_forward_mma(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri,
-                                              h->ri_lo, h->sm_count, s))
+                                              h->ri_lo, save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr,
+                                              h->sm_count, s))
             st_launch_ae_forward(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo, acts,
                                  h->ae_grid, s);
+        else
+            h->have_saves = save;
         if (mag_hat_user)
             ST_CUDA_OK(cudaMemcpyAsync(mag_hat_user, h->mag_hat_ws, (long)B * d.OT * d.F * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
@@ -468,12 +482,21 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         }
     }
     ST_LAUNCH_OK(h);
-    {   // both autoencoders: recompute, back-propagate, dL/d(re|im) -> g_spec, per-CTA weight-gradient partials
-        StageScope sc(h, SG_AE_BWD, 1, s);
+    int part_ctas = h->ae_grid;
+    {   // both autoencoders: back-propagate, dL/d(re|im) -> g_spec, per-CTA weight-gradient partials.  Tensor-core path
+        // from the saved activations when the forward wrote them; otherwise the SIMT kernel recomputes the chain.
+        StageScope sc(h, SG_AE_BWD, 2, s);
         AeParams pm, pp;
         split_params(params, pm, pp);
-        st_launch_ae_backward(d, h->g, pm, pp, h->spec, h->knobs_ws, B, h->mag_hat_ws, h->phs_hat_ws, h->g_ri, g_mag_hat,
-                              g_mag, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_grid, s);
+        int gr = 0;
+        if (h->have_saves)
+            gr = st_launch_ae_backward_mma(d, h->g, pm, pp, h->spec, B, h->ae_save_m, h->ae_save_p, h->mag_hat_ws, h->phs_hat_ws,
+                                           h->g_ri, g_mag_hat, g_mag, h->tail_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->sm_count, s);
+        if (gr > 0)
+            part_ctas = gr;
+        else
+            st_launch_ae_backward(d, h->g, pm, pp, h->spec, h->knobs_ws, B, h->mag_hat_ws, h->phs_hat_ws, h->g_ri, g_mag_hat,
+                                  g_mag, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_grid, s);
     }
     ST_LAUNCH_OK(h);
     {
@@ -483,7 +506,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
             gm.W[l] = grads[4 + 2 * l];  gm.b[l] = grads[5 + 2 * l];
             gp.W[l] = grads[22 + 2 * l]; gp.b[l] = grads[23 + 2 * l];
         }
-        st_launch_ae_grad_reduce(h->g, h->ae_part, h->ae_grid, gm, gp, s);
+        st_launch_ae_grad_reduce(h->g, h->ae_part, part_ctas, gm, gp, s);
     }
     ST_LAUNCH_OK(h);
     {   // analysis weight gradient: G[(re|im) k, n] = sum_(b,t) g_spec[(b,t), k] * frame[(b,t), n]
@@ -628,6 +651,12 @@ extern "C" int st_debug_read(st_handle* h, const char* name, float* dst, long n)
     ST_CUDA_OK(cudaSetDevice(h->device));
     ST_CUDA_OK(cudaDeviceSynchronize());
     ST_CUDA_OK(cudaMemcpy(dst, src, std::min(n, have) * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int st_set_training(st_handle* h, int on) {
+    if (!h) return 1;
+    h->training = on != 0;
     return 0;
 }
 

@@ -134,10 +134,16 @@ void st_launch_ae_backward(const StDims& d, const AeGeom& g, const AeParams& pm,
 void st_launch_ae_grad_reduce(const AeGeom& g, const float* partials, int ncta, const AeGrads& gm, const AeGrads& gp,
                               cudaStream_t s);
 
-// st_ae_mma.cu (tensor-core forward; returns false if the geometry is not covered)
+// st_ae_mma.cu (tensor-core autoencoders; return false if the geometry is not covered)
+int st_ae_mma_record_floats(const StDims& d);      // floats per row of the saved-activation record
 bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
                               const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri_hi, float* ri_lo,
-                              int sm_count, cudaStream_t s);
+                              float* save_m, float* save_p, int sm_count, cudaStream_t s);
+
+int st_launch_ae_backward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, int B,
+                              const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat,
+                              const float* g_ri, const float* g_mag_hat, const float* g_mag, float* tail_ws, float* g_spec_hi,
+                              float* g_spec_lo, float* partials, int sm_count, cudaStream_t s);
 
 // st_loss_opt.cu
 void st_launch_loss(const StDims& d, const float* y_hat, const float* y, const float* mag_hat, const float* sbf,

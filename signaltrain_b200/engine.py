@@ -131,6 +131,9 @@ class Engine:
             _check(t, "front-end weight", (self.g.N, 1, self.g.N), self.device)
         self._ok(self.lib.st_init_frontend(self.h, tab, self._stream()), "st_init_frontend")
 
+    def set_training(self, on):
+        self._ok(self.lib.st_set_training(self.h, int(bool(on))), "st_set_training")
+
     def forward(self, x, knobs, params, return_acts=False):
         g = self.g
         if x.dim() != 2 or x.shape[1] != g.C:

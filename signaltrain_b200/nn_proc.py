@@ -43,8 +43,9 @@ class AsymAutoEncoder(nn.Module):
 
 class _MPAECFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mpaec, return_acts, x, knobs, *params):
+    def forward(ctx, mpaec, return_acts, need_grad, x, knobs, *params):
         eng = mpaec._engine_for(x)
+        eng.set_training(need_grad)        # saves the autoencoder activations for backward only when one can follow
         y_hat, mag, mag_hat, acts = eng.forward(x, knobs, [p.detach() for p in params], return_acts)
         ctx.mpaec, ctx.eng = mpaec, eng
         ctx.ticket = mpaec._new_ticket()
@@ -65,7 +66,7 @@ class _MPAECFunction(torch.autograd.Function):
         grads = [torch.empty_like(p) for p in ctx.params]
         eng.backward(g_y.contiguous(), None if g_mag is None else g_mag.contiguous(),
                      None if g_mag_hat is None else g_mag_hat.contiguous(), [p.detach() for p in ctx.params], grads)
-        return (None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None) + tuple(grads)
 
 
 class AsymMPAEC(nn.Module):
@@ -141,7 +142,8 @@ class AsymMPAEC(nn.Module):
         params = self.ordered_parameters()
         if x_cuda.dtype != torch.float32:
             raise RuntimeError(f"signaltrain_b200: float32 only (got {x_cuda.dtype}); .double()/.half() models are not supported")
-        outs = _MPAECFunction.apply(self, bool(return_acts), x_cuda.contiguous(), knobs_cuda.contiguous(), *params)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        outs = _MPAECFunction.apply(self, bool(return_acts), need_grad, x_cuda.contiguous(), knobs_cuda.contiguous(), *params)
         if return_acts:
             return outs[0], outs[1], outs[2], list(outs[3:])
         return outs[0], outs[1], outs[2]
