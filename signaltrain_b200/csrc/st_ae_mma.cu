@@ -323,38 +323,49 @@ __device__ __forceinline__ void layer_mma_T(const float* __restrict__ gz, int ks
     }
 }
 
-// gz_{l-1} = (data gradient) * ELU'(h_{l-1});  h_{l-1} is read from the saved records (columns hbase .. hbase+8*NT).
+// gz_{l-1} = (data gradient) * ELU'(h_{l-1});  h_{l-1} (own rows) is read from the staged plane `hp`, the result
+// overwrites it in place (the caller has synchronised the CTA: nobody else reads these rows any more).
 template <int NT>
-__device__ __forceinline__ void store_gz(float* __restrict__ dst, const float (&c)[2][NT][4], const float* __restrict__ save,
-                                         long R0, long BF, int ss, int hbase, int g, int t) {
+__device__ __forceinline__ void store_gz(float* __restrict__ hp, const float (&c)[2][NT][4], int g, int t) {
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const long R = R0 + 16 * mt + g + 8 * h;
-            const bool ok = R < BF;
-            const float* hp = save + (ok ? R : 0) * ss + hbase + 2 * t;
-            float* p = dst + (16 * mt + g + 8 * h) * RS + 2 * t;
+            float* p = hp + (16 * mt + g + 8 * h) * RS + 2 * t;
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
-                float2 hh = make_float2(0.f, 0.f);
-                if (ok) hh = __ldg(reinterpret_cast<const float2*>(hp + 8 * n));
+                const float2 hh = *reinterpret_cast<const float2*>(p + 8 * n);
                 *reinterpret_cast<float2*>(p + 8 * n) =
                     make_float2(c[mt][n][2 * h] * elu_grad(hh.x), c[mt][n][2 * h + 1] * elu_grad(hh.y));
             }
         }
 }
 
+// Asynchronously stage columns [hbase, hbase + 4*w4) of the CTA tile's saved records into a plane (cp.async, 16 B per
+// request, rows past the end of the batch zero-filled).
+__device__ __forceinline__ void stage_h_async(float* __restrict__ plane, const float* __restrict__ save, long R0c, long BF, int ss,
+                                              int hbase, int w4, int tid) {
+    for (int idx = tid; idx < CTA_ROWS * w4; idx += BWD_WARPS * 32) {
+        const int r = idx / w4, c4 = idx - r * w4;
+        const bool ok = R0c + r < BF;
+        const float* src = save + (ok ? (R0c + r) : 0) * ss + hbase + 4 * c4;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(plane + r * RS + 4 * c4);
+        const int bytes = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_h_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Weight gradient of one layer, this warp's (mo, ni) output tiles, reduction over the CTA tile's 256 rows:
 //   dW[o][i] += sum_rows gz[row][o] * h[row][i]
-//   A = gz^T from the shared plane (m = o, k = row):  a0 (m g, k t) = P[(8ks+t)*RS + 16mo+g], a1 (m g+8, k t),
-//                                                     a2 (m g, k t+4), a3 (m g+8, k t+4)
-//   B = h from the saved records (k = row, n = i):    b0 (k t, n g) = S[(R0+8ks+t)*ss + hbase + 8ni+g], b1 (k t+4, n g)
+//   A = gz^T from the gz plane (m = o, k = row):  a0 (m g, k t) = G[(8ks+t)*RS + 16mo+g], a1 (m g+8, k t),
+//                                                 a2 (m g, k t+4), a3 (m g+8, k t+4)
+//   B = h from the staged plane (k = row, n = i): b0 (k t, n g) = H[(8ks+t)*RS + 8ni+g], b1 (k t+4, n g)
 // Pair p = warp + 8q -> (mo = p % MB, ni = p / MB); MB divides 8, so all of a warp's pairs share mo (one A fragment).
 template <int NPW>
-__device__ __forceinline__ void wgrad_mma(float (&acc)[NPW][4], const float* __restrict__ plane, int MB, int NB,
-                                          const float* __restrict__ save, long R0c, long BF, int ss, int hbase, int warp, int g,
-                                          int t) {
+__device__ __forceinline__ void wgrad_mma(float (&acc)[NPW][4], const float* __restrict__ gzp, const float* __restrict__ hpl,
+                                          int MB, int NB, int warp, int g, int t) {
     const int P = MB * NB;
     if (warp >= P) return;
     const int mo = warp % MB;
@@ -363,7 +374,8 @@ __device__ __forceinline__ void wgrad_mma(float (&acc)[NPW][4], const float* __r
     for (int par = 0; par < 2; ++par)
 #pragma unroll
         for (int q = 0; q < NPW; ++q) tmp[par][q][0] = tmp[par][q][1] = tmp[par][q][2] = tmp[par][q][3] = 0.f;
-    const float* pa = plane + t * RS + 16 * mo + g;
+    const float* pa = gzp + t * RS + 16 * mo + g;
+    const float* pb = hpl + t * RS + g;
 #pragma unroll 1
     for (int ks2 = 0; ks2 < CTA_ROWS / 16; ++ks2) {
 #pragma unroll
@@ -375,17 +387,15 @@ __device__ __forceinline__ void wgrad_mma(float (&acc)[NPW][4], const float* __r
             split_tf32(ap[8], ahi[1], alo[1]);
             split_tf32(ap[4 * RS], ahi[2], alo[2]);
             split_tf32(ap[4 * RS + 8], ahi[3], alo[3]);
-            const long r0 = R0c + 8 * ks + t, r1 = r0 + 4;
+            const float* bp = pb + 8 * ks * RS;
 #pragma unroll
             for (int q = 0; q < NPW; ++q) {
                 const int pidx = warp + 8 * q;
                 if (pidx < P) {
                     const int ni = pidx / MB;
-                    const float v0 = r0 < BF ? __ldg(save + r0 * ss + hbase + 8 * ni + g) : 0.f;
-                    const float v1 = r1 < BF ? __ldg(save + r1 * ss + hbase + 8 * ni + g) : 0.f;
                     uint32_t bh0, bl0, bh1, bl1;
-                    split_tf32(v0, bh0, bl0);
-                    split_tf32(v1, bh1, bl1);
+                    split_tf32(bp[8 * ni], bh0, bl0);
+                    split_tf32(bp[4 * RS + 8 * ni], bh1, bl1);
                     mma_tf32(tmp[par][q], alo, bh0, bh1);
                     mma_tf32(tmp[par][q], ahi, bl0, bl1);
                     mma_tf32(tmp[par][q], ahi, bh0, bh1);
@@ -498,91 +508,57 @@ ae_bwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
                 my0[lane * RS + j] = gz;
             }
         }
-        __syncthreads();
-        // ---- layer 9 (fnn_dec): OUT = OT (<= 16), IN = 64
-        wgrad_mma<1>(a9, plane0, 1, 8, save, R0c, BF, ss, mg.soff[7], warp, gq, t);
-        bias_grad(dbias + 8 * 64, plane0, mg.outp[8], warp, lane);
-        {
-            float c[2][8][4];
-            layer_mma_T<8>(my0, mg.outp[8] / 8, W + mg.off[8], mg.ld[8], c, gq, t);
-            store_gz<8>(my1, c, save, R0, BF, ss, mg.soff[7], gq, t);
+        // One layer step:  gz_l lives in `cur` (all 256 rows).  (1) start staging h_{l-1} into `nxt` (cp.async);
+        // (2) the data-gradient MMAs of the warp's own rows overlap that load; (3) wait + CTA barrier; (4) weight / bias
+        // gradient over all rows (A: cur, B: nxt); (5) CTA barrier; (6) gz_{l-1} = c * ELU'(h_{l-1}) overwrites the
+        // warp's own rows of `nxt`; (7) CTA barrier.  `cur` and `nxt` then swap roles.
+#define ST_BWD_LAYER(L, NPW_, ACC, CUR, NXT, MYCUR, MYNXT, MB_, NB_, OUTP_, HBASE_, HW4_, NT_, KS_)                          \
+        __syncthreads();                                                                                                    \
+        stage_h_async(NXT, save, R0c, BF, ss, HBASE_, HW4_, threadIdx.x);                                                   \
+        {                                                                                                                   \
+            float c[2][NT_][4];                                                                                             \
+            layer_mma_T<NT_>(MYCUR, KS_, W + mg.off[L], mg.ld[L], c, gq, t);                                                \
+            stage_h_wait();                                                                                                 \
+            __syncthreads();                                                                                                \
+            wgrad_mma<NPW_>(ACC, CUR, NXT, MB_, NB_, warp, gq, t);                                                          \
+            bias_grad(dbias + L * 64, CUR, OUTP_, warp, lane);                                                              \
+            __syncthreads();                                                                                                \
+            store_gz<NT_>(MYNXT, c, gq, t);                                                                                 \
         }
-        __syncthreads();
-        // ---- layer 8 (fnn_dec2): 64 <- 32
-        wgrad_mma<2>(a8, plane1, 4, 4, save, R0c, BF, ss, mg.soff[6], warp, gq, t);
-        bias_grad(dbias + 7 * 64, plane1, 64, warp, lane);
-        {
-            float c[2][4][4];
-            layer_mma_T<4>(my1, 8, W + mg.off[7], mg.ld[7], c, gq, t);
-            store_gz<4>(my0, c, save, R0, BF, ss, mg.soff[6], gq, t);
-        }
-        __syncthreads();
-        // ---- layer 7 (fnn_dec3): 32 <- 16
-        wgrad_mma<1>(a7, plane0, 2, 2, save, R0c, BF, ss, mg.soff[5], warp, gq, t);
-        bias_grad(dbias + 6 * 64, plane0, 32, warp, lane);
-        {
-            float c[2][2][4];
-            layer_mma_T<2>(my0, 4, W + mg.off[6], mg.ld[6], c, gq, t);
-            store_gz<2>(my1, c, save, R0, BF, ss, mg.soff[5], gq, t);
-        }
-        __syncthreads();
-        // ---- layer 6 (fnn_dec4): 16 <- 16
-        wgrad_mma<1>(a6, plane1, 1, 2, save, R0c, BF, ss, mg.soff[4], warp, gq, t);
-        bias_grad(dbias + 5 * 64, plane1, 16, warp, lane);
-        {
-            float c[2][2][4];
-            layer_mma_T<2>(my1, 2, W + mg.off[5], mg.ld[5], c, gq, t);
-            store_gz<2>(my0, c, save, R0, BF, ss, mg.soff[4], gq, t);
-        }
-        __syncthreads();
-        // ---- layer 5 (fnn_addknobs): 16 <- 16 + knobs (the h4 slot of the record holds h4 ++ knobs, 32 wide)
-        wgrad_mma<1>(a5, plane0, 1, 4, save, R0c, BF, ss, mg.soff[3], warp, gq, t);
-        bias_grad(dbias + 4 * 64, plane0, 16, warp, lane);
-        {
-            float c[2][2][4];                                   // only the 16 non-knob inputs carry gradient
-            layer_mma_T<2>(my0, 2, W + mg.off[4], mg.ld[4], c, gq, t);
-            store_gz<2>(my1, c, save, R0, BF, ss, mg.soff[3], gq, t);
-        }
-        __syncthreads();
-        // ---- layer 4 (fnn_enc4): 16 <- 16
-        wgrad_mma<1>(a4, plane1, 1, 2, save, R0c, BF, ss, mg.soff[2], warp, gq, t);
-        bias_grad(dbias + 3 * 64, plane1, 16, warp, lane);
-        {
-            float c[2][2][4];
-            layer_mma_T<2>(my1, 2, W + mg.off[3], mg.ld[3], c, gq, t);
-            store_gz<2>(my0, c, save, R0, BF, ss, mg.soff[2], gq, t);
-        }
-        __syncthreads();
-        // ---- layer 3 (fnn_enc3): 16 <- 32
-        wgrad_mma<1>(a3, plane0, 1, 4, save, R0c, BF, ss, mg.soff[1], warp, gq, t);
-        bias_grad(dbias + 2 * 64, plane0, 16, warp, lane);
-        {
-            float c[2][4][4];
-            layer_mma_T<4>(my0, 2, W + mg.off[2], mg.ld[2], c, gq, t);
-            store_gz<4>(my1, c, save, R0, BF, ss, mg.soff[1], gq, t);
-        }
-        __syncthreads();
-        // ---- layer 2 (fnn_enc2): 32 <- 64
-        wgrad_mma<2>(a2, plane1, 2, 8, save, R0c, BF, ss, mg.soff[0], warp, gq, t);
-        bias_grad(dbias + 1 * 64, plane1, 32, warp, lane);
-        {
-            float c[2][8][4];
-            layer_mma_T<8>(my1, 4, W + mg.off[1], mg.ld[1], c, gq, t);
-            store_gz<8>(my0, c, save, R0, BF, ss, mg.soff[0], gq, t);
-        }
-        __syncthreads();
+        // layer 9 (fnn_dec):      OT(<=16) <- 64 ;  h8 is 64 wide
+        ST_BWD_LAYER(8, 1, a9, plane0, plane1, my0, my1, 1, 8, mg.outp[8], mg.soff[7], 16, 8, mg.outp[8] / 8)
+        // layer 8 (fnn_dec2):     64 <- 32
+        ST_BWD_LAYER(7, 2, a8, plane1, plane0, my1, my0, 4, 4, 64, mg.soff[6], 8, 4, 8)
+        // layer 7 (fnn_dec3):     32 <- 16
+        ST_BWD_LAYER(6, 1, a7, plane0, plane1, my0, my1, 2, 2, 32, mg.soff[5], 4, 2, 4)
+        // layer 6 (fnn_dec4):     16 <- 16
+        ST_BWD_LAYER(5, 1, a6, plane1, plane0, my1, my0, 1, 2, 16, mg.soff[4], 4, 2, 2)
+        // layer 5 (fnn_addknobs): 16 <- 16 + knobs (record slot of h4 is 32 wide: h4 ++ knobs); only h4 carries gradient
+        ST_BWD_LAYER(4, 1, a5, plane0, plane1, my0, my1, 1, 4, 16, mg.soff[3], 8, 2, 2)
+        // layer 4 (fnn_enc4):     16 <- 16
+        ST_BWD_LAYER(3, 1, a4, plane1, plane0, my1, my0, 1, 2, 16, mg.soff[2], 4, 2, 2)
+        // layer 3 (fnn_enc3):     16 <- 32
+        ST_BWD_LAYER(2, 1, a3, plane0, plane1, my0, my1, 1, 4, 16, mg.soff[1], 8, 4, 2)
+        // layer 2 (fnn_enc2):     32 <- 64
+        ST_BWD_LAYER(1, 2, a2, plane1, plane0, my1, my0, 2, 8, 32, mg.soff[0], 16, 8, 4)
+#undef ST_BWD_LAYER
         // ---- layer 1 (fnn_enc): 64 <- T.  Data gradient = dL/d(track), turned into dL/d(re, im).
-        wgrad_mma<4>(a1, plane0, 4, ks1, save, R0c, BF, ss, mg.soff_v, warp, gq, t);
-        bias_grad(dbias + 0 * 64, plane0, 64, warp, lane);
+        __syncthreads();
+        stage_h_async(plane1, save, R0c, BF, ss, mg.soff_v, 2 * ks1, threadIdx.x);      // the input tracks V
         {
             float c[2][NT1][4];
             layer_mma_T<NT1>(my0, 8, W + mg.off[0], mg.ld[0], c, gq, t);
-            // through the (own rows of the) other plane so the output-side math runs lane <-> row with one code copy
+            stage_h_wait();
+            __syncthreads();
+            wgrad_mma<4>(a1, plane0, plane1, 4, ks1, warp, gq, t);
+            bias_grad(dbias + 0 * 64, plane0, 64, warp, lane);
+            __syncthreads();
+            // dL/d(track) goes through the warp's own rows of plane0 so the output-side math runs lane <-> row
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int n = 0; n < NT1; ++n) {
-                    float* q = my1 + (16 * mt + gq) * RS + 8 * n + 2 * t;
+                    float* q = my0 + (16 * mt + gq) * RS + 8 * n + 2 * t;
                     *reinterpret_cast<float2*>(q) = make_float2(c[mt][n][0], c[mt][n][1]);
                     *reinterpret_cast<float2*>(q + 8 * RS) = make_float2(c[mt][n][2], c[mt][n][3]);
                 }
@@ -590,16 +566,15 @@ ae_bwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
             const long R = R0 + lane;
             if (R < BF) {
                 const int b = (int)(R / d.F), f = (int)(R - (long)b * d.F);
-                const float* rec = save + R * ss + mg.soff_v;
 #pragma unroll 1
                 for (int tt = 0; tt < d.T; ++tt) {
-                    float gv = my1[lane * RS + tt];
+                    float gv = my0[lane * RS + tt];
                     if (tt >= tail0) gv += tail_ws[((long)b * d.OT + (tt - tail0)) * d.F + f];
                     const long o = ((long)b * d.Tp + tt) * rowstride + f;
                     const float re = __ldg(spec + o), im = __ldg(spec + o + d.Fp);
                     if (AE == 0) {          // mag = sqrt(re^2+im^2); subgradient 0 at 0 (torch.norm backward)
                         if (g_mag) gv += __ldg(g_mag + ((long)b * d.T + tt) * d.F + f);
-                        const float m = __ldg(rec + tt);
+                        const float m = my1[lane * RS + tt];
                         const float sc = m > 0.f ? gv / m : 0.f;
                         g_spec[o] = sc * re;
                         g_spec[o + d.Fp] = sc * im;
