@@ -127,6 +127,9 @@ const char* st_profile_stage_name(int i);
 int st_profile(st_handle* h, int enable);
 int st_profile_read(st_handle* h, float* ms, long* calls);
 
+/* Diagnostic: cycle counters of the regions of the tensor-core autoencoder backward (16 values; reading resets). */
+int st_debug_ae_timing(st_handle* h, int on, long long* out_host);
+
 /* Test/diagnostic access to workspace buffers by name ("spec", "ri", "frames_out", "g_ri", "g_spec",
  * "wcat", "sfold").  Copies up to n floats to a HOST buffer, synchronising the device. */
 int st_debug_read(st_handle* h, const char* name, float* dst_host, long n);

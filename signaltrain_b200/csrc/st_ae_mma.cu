@@ -66,18 +66,30 @@ __device__ __forceinline__ void layer_mma(const float* __restrict__ act, int kst
             split_tf32(ap[4], ahi[mt][2], alo[mt][2]);
             split_tf32(ap[8 * RS + 4], ahi[mt][3], alo[mt][3]);
         }
+        // pass-major over groups of n-tiles: consecutive MMAs hit different accumulators (the three passes of one
+        // accumulator are 2*NG instructions apart), so the tensor pipe is not serialised on accumulator latency
+        constexpr int NG = NT < 4 ? NT : 4;
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            const float* wp = W + (8 * n + g) * ld + 8 * j + t;
-            uint32_t bh0, bl0, bh1, bl1;
-            split_tf32(wp[0], bh0, bl0);
-            split_tf32(wp[4], bh1, bl1);
+        for (int n0 = 0; n0 < NT; n0 += NG) {
+            uint32_t bh[NG][2], bl[NG][2];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], alo[mt], bh0, bh1);
+            for (int q = 0; q < NG; ++q) {
+                const float* wp = W + (8 * (n0 + q) + g) * ld + 8 * j + t;
+                split_tf32(wp[0], bh[q][0], bl[q][0]);
+                split_tf32(wp[4], bh[q][1], bl[q][1]);
+            }
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], ahi[mt], bl0, bl1);
+            for (int q = 0; q < NG; ++q)
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], ahi[mt], bh0, bh1);
+                for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n0 + q], alo[mt], bh[q][0], bh[q][1]);
+#pragma unroll
+            for (int q = 0; q < NG; ++q)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n0 + q], ahi[mt], bl[q][0], bl[q][1]);
+#pragma unroll
+            for (int q = 0; q < NG; ++q)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n0 + q], ahi[mt], bh[q][0], bh[q][1]);
         }
     }
 }
@@ -98,14 +110,18 @@ __device__ __forceinline__ void store_act(float* __restrict__ act, const float (
 }
 
 // Copy columns [0, width) of the warp's tile to the saved-activation record of each row (coalesced float4 rows).
+template <int WIDTH>
 __device__ __forceinline__ void save_tile(const float* __restrict__ act, float* __restrict__ save, long R0, long BF, int ss,
-                                          int soff, int width, int lane) {
-    const int w4 = width >> 2;
-    for (int idx = lane; idx < ROWS_PER_WARP * w4; idx += 32) {
-        const int r = idx / w4, c4 = idx - r * w4;
-        if (R0 + r < BF)
-            *reinterpret_cast<float4*>(save + (R0 + r) * ss + soff + 4 * c4) = *reinterpret_cast<const float4*>(act + r * RS + 4 * c4);
-    }
+                                          int soff, int lane) {
+    constexpr int W4 = WIDTH / 4;                 // float4 per row: 4, 8 or 16 -> 32 / W4 rows per warp instruction
+    constexpr int RPI = 32 / W4;
+    const int c4 = lane % W4, r0 = lane / W4;
+    float* dst = save + (R0 + r0) * ss + soff + 4 * c4;
+    const float* src = act + r0 * RS + 4 * c4;
+#pragma unroll
+    for (int i = 0; i < ROWS_PER_WARP / RPI; ++i)
+        if (R0 + r0 + i * RPI < BF)
+            *reinterpret_cast<float4*>(dst + (long)i * RPI * ss) = *reinterpret_cast<const float4*>(src + i * RPI * RS);
 }
 
 struct MmaGeom {
@@ -154,7 +170,7 @@ ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
     const long ntiles = (BF + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
     const int tail0 = d.T - d.OT;
     const int rowstride = 2 * d.Fp;
-    const int kcols = 8 * mg.ks[0];
+    const int kcols = mg.ks[0] <= 4 ? 32 : 64;      // track columns held in the tile / record (zero beyond T)
 
     for (long tile = (long)blockIdx.x * FWD_WARPS + warp; tile < ntiles; tile += (long)gridDim.x * FWD_WARPS) {
         const long R0 = tile * ROWS_PER_WARP;
@@ -167,7 +183,7 @@ ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
             const float* sp = spec + (long)b * d.Tp * rowstride + f;
             float* mo = (AE == 0 && mag_out) ? mag_out + (long)b * d.T * d.F + f : nullptr;
             __syncwarp();
-#pragma unroll 2
+#pragma unroll 8
             for (int tt = 0; tt < kcols; ++tt) {
                 float v = 0.f;
                 if (ok && tt < d.T) {
@@ -182,26 +198,26 @@ ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
                 act[lane * RS + tt] = v;
             }
             __syncwarp();
-            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff_v, kcols, lane);
+            if (save) { if (kcols == 32) save_tile<32>(act, save, R0, BF, mg.ss, mg.soff_v, lane); else save_tile<64>(act, save, R0, BF, mg.ss, mg.soff_v, lane); }
         }
         // ---- fnn_enc .. fnn_enc4
         {
             float c[2][8][4];
             layer_mma<8>(act, mg.ks[0], W + mg.off[0], mg.ld[0], bias + mg.boff[0], c, gq, t);
             store_act<8>(act, c, gq, t);
-            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[0], 64, lane);
+            if (save) save_tile<64>(act, save, R0, BF, mg.ss, mg.soff[0], lane);
         }
         {
             float c[2][4][4];
             layer_mma<4>(act, 8, W + mg.off[1], mg.ld[1], bias + mg.boff[1], c, gq, t);
             store_act<4>(act, c, gq, t);
-            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[1], 32, lane);
+            if (save) save_tile<32>(act, save, R0, BF, mg.ss, mg.soff[1], lane);
         }
         {
             float c[2][2][4];
             layer_mma<2>(act, 4, W + mg.off[2], mg.ld[2], bias + mg.boff[2], c, gq, t);
             store_act<2>(act, c, gq, t);
-            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[2], 16, lane);
+            if (save) save_tile<16>(act, save, R0, BF, mg.ss, mg.soff[2], lane);
         }
         {
             float c[2][2][4];
@@ -216,31 +232,31 @@ ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
 #pragma unroll
             for (int kk = 0; kk < 16; ++kk) act[lane * RS + 16 + kk] = (ok && kk < d.K) ? __ldg(kp + kk) : 0.f;
             __syncwarp();
-            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[3], 32, lane);     // h4 ++ knobs: fnn_addknobs' input
+            if (save) save_tile<32>(act, save, R0, BF, mg.ss, mg.soff[3], lane);     // h4 ++ knobs: fnn_addknobs' input
         }
         {
             float c[2][2][4];
             layer_mma<2>(act, 4, W + mg.off[4], mg.ld[4], bias + mg.boff[4], c, gq, t);
             store_act<2>(act, c, gq, t);
-            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[4], 16, lane);
+            if (save) save_tile<16>(act, save, R0, BF, mg.ss, mg.soff[4], lane);
         }
         {
             float c[2][2][4];
             layer_mma<2>(act, 2, W + mg.off[5], mg.ld[5], bias + mg.boff[5], c, gq, t);
             store_act<2>(act, c, gq, t);
-            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[5], 16, lane);
+            if (save) save_tile<16>(act, save, R0, BF, mg.ss, mg.soff[5], lane);
         }
         {
             float c[2][4][4];
             layer_mma<4>(act, 2, W + mg.off[6], mg.ld[6], bias + mg.boff[6], c, gq, t);
             store_act<4>(act, c, gq, t);
-            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[6], 32, lane);
+            if (save) save_tile<32>(act, save, R0, BF, mg.ss, mg.soff[6], lane);
         }
         {
             float c[2][8][4];
             layer_mma<8>(act, 4, W + mg.off[7], mg.ld[7], bias + mg.boff[7], c, gq, t);
             store_act<8>(act, c, gq, t);
-            if (save) save_tile(act, save, R0, BF, mg.ss, mg.soff[7], 64, lane);
+            if (save) save_tile<64>(act, save, R0, BF, mg.ss, mg.soff[7], lane);
         }
         // ---- fnn_dec; ELU'd outputs go through the tile so the output-side math runs lane <-> row (coalesced, and one
         //      copy of the transcendental code instead of one per accumulator register)
@@ -284,6 +300,8 @@ ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
 // ------------------------------------------------------------------------------------------------------------
 constexpr int BWD_WARPS = 8;
 constexpr int CTA_ROWS = BWD_WARPS * ROWS_PER_WARP;     // 256 rows per CTA tile
+constexpr int PS = 72;     // backward plane row stride: 8 (mod 32) -> the transposed (weight-gradient) fragment loads, which
+                           // dominate the backward's shared-memory traffic, are conflict-free
 
 __device__ __forceinline__ float elu_grad(float h) { return h > 0.f ? 1.f : h + 1.f; }   // dELU/dz through the output h
 
@@ -301,24 +319,34 @@ __device__ __forceinline__ void layer_mma_T(const float* __restrict__ gz, int ks
         uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-            const float* ap = gz + (16 * mt + g) * RS + 8 * j + t;
+            const float* ap = gz + (16 * mt + g) * PS + 8 * j + t;
             split_tf32(ap[0], ahi[mt][0], alo[mt][0]);
-            split_tf32(ap[8 * RS], ahi[mt][1], alo[mt][1]);
+            split_tf32(ap[8 * PS], ahi[mt][1], alo[mt][1]);
             split_tf32(ap[4], ahi[mt][2], alo[mt][2]);
-            split_tf32(ap[8 * RS + 4], ahi[mt][3], alo[mt][3]);
+            split_tf32(ap[8 * PS + 4], ahi[mt][3], alo[mt][3]);
         }
+        constexpr int NG = NT < 4 ? NT : 4;      // pass-major over groups of n-tiles (see layer_mma)
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            const float* wp = W + (8 * j + t) * ld + 8 * n + g;
-            uint32_t bh0, bl0, bh1, bl1;
-            split_tf32(wp[0], bh0, bl0);
-            split_tf32(wp[4 * ld], bh1, bl1);
+        for (int n0 = 0; n0 < NT; n0 += NG) {
+            uint32_t bh[NG][2], bl[NG][2];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], alo[mt], bh0, bh1);
+            for (int q = 0; q < NG; ++q) {
+                const float* wp = W + (8 * j + t) * ld + 8 * (n0 + q) + g;
+                split_tf32(wp[0], bh[q][0], bl[q][0]);
+                split_tf32(wp[4 * ld], bh[q][1], bl[q][1]);
+            }
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], ahi[mt], bl0, bl1);
+            for (int q = 0; q < NG; ++q)
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n], ahi[mt], bh0, bh1);
+                for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n0 + q], alo[mt], bh[q][0], bh[q][1]);
+#pragma unroll
+            for (int q = 0; q < NG; ++q)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n0 + q], ahi[mt], bl[q][0], bl[q][1]);
+#pragma unroll
+            for (int q = 0; q < NG; ++q)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n0 + q], ahi[mt], bh[q][0], bh[q][1]);
         }
     }
 }
@@ -331,7 +359,7 @@ __device__ __forceinline__ void store_gz(float* __restrict__ hp, const float (&c
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            float* p = hp + (16 * mt + g + 8 * h) * RS + 2 * t;
+            float* p = hp + (16 * mt + g + 8 * h) * PS + 2 * t;
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
                 const float2 hh = *reinterpret_cast<const float2*>(p + 8 * n);
@@ -344,12 +372,13 @@ __device__ __forceinline__ void store_gz(float* __restrict__ hp, const float (&c
 // Asynchronously stage columns [hbase, hbase + 4*w4) of the CTA tile's saved records into a plane (cp.async, 16 B per
 // request, rows past the end of the batch zero-filled).
 __device__ __forceinline__ void stage_h_async(float* __restrict__ plane, const float* __restrict__ save, long R0c, long BF, int ss,
-                                              int hbase, int w4, int tid) {
+                                              int hbase, int lg_w4 /* log2(float4 per row): 2, 3 or 4 */, int tid) {
+    const int w4 = 1 << lg_w4;
     for (int idx = tid; idx < CTA_ROWS * w4; idx += BWD_WARPS * 32) {
-        const int r = idx / w4, c4 = idx - r * w4;
+        const int r = idx >> lg_w4, c4 = idx & (w4 - 1);
         const bool ok = R0c + r < BF;
         const float* src = save + (ok ? (R0c + r) : 0) * ss + hbase + 4 * c4;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(plane + r * RS + 4 * c4);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(plane + r * PS + 4 * c4);
         const int bytes = ok ? 16 : 0;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
     }
@@ -359,9 +388,9 @@ __device__ __forceinline__ void stage_h_wait() { asm volatile("cp.async.wait_gro
 
 // Weight gradient of one layer, this warp's (mo, ni) output tiles, reduction over the CTA tile's 256 rows:
 //   dW[o][i] += sum_rows gz[row][o] * h[row][i]
-//   A = gz^T from the gz plane (m = o, k = row):  a0 (m g, k t) = G[(8ks+t)*RS + 16mo+g], a1 (m g+8, k t),
+//   A = gz^T from the gz plane (m = o, k = row):  a0 (m g, k t) = G[(8ks+t)*PS + 16mo+g], a1 (m g+8, k t),
 //                                                 a2 (m g, k t+4), a3 (m g+8, k t+4)
-//   B = h from the staged plane (k = row, n = i): b0 (k t, n g) = H[(8ks+t)*RS + 8ni+g], b1 (k t+4, n g)
+//   B = h from the staged plane (k = row, n = i): b0 (k t, n g) = H[(8ks+t)*PS + 8ni+g], b1 (k t+4, n g)
 // Pair p = warp + 8q -> (mo = p % MB, ni = p / MB); MB divides 8, so all of a warp's pairs share mo (one A fragment).
 template <int NPW>
 __device__ __forceinline__ void wgrad_mma(float (&acc)[NPW][4], const float* __restrict__ gzp, const float* __restrict__ hpl,
@@ -369,44 +398,62 @@ __device__ __forceinline__ void wgrad_mma(float (&acc)[NPW][4], const float* __r
     const int P = MB * NB;
     if (warp >= P) return;
     const int mo = warp % MB;
-    float tmp[2][NPW][4];
+    // KG k-steps in flight with their own accumulators, MMAs issued pass-major: KG*NPW independent accumulators between the
+    // three dependent passes of any one of them
+    constexpr int KG = NPW == 1 ? 4 : 2;
+    float tmp[KG][NPW][4];
 #pragma unroll
-    for (int par = 0; par < 2; ++par)
+    for (int k = 0; k < KG; ++k)
 #pragma unroll
-        for (int q = 0; q < NPW; ++q) tmp[par][q][0] = tmp[par][q][1] = tmp[par][q][2] = tmp[par][q][3] = 0.f;
-    const float* pa = gzp + t * RS + 16 * mo + g;
-    const float* pb = hpl + t * RS + g;
+        for (int q = 0; q < NPW; ++q) tmp[k][q][0] = tmp[k][q][1] = tmp[k][q][2] = tmp[k][q][3] = 0.f;
+    const float* pa = gzp + t * PS + 16 * mo + g;
+    const float* pb = hpl + t * PS + g;
+    int nib[NPW];
+    bool on[NPW];
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) {
+        on[q] = warp + 8 * q < P;
+        nib[q] = 8 * ((warp + 8 * q) / MB);
+    }
 #pragma unroll 1
-    for (int ks2 = 0; ks2 < CTA_ROWS / 16; ++ks2) {
+    for (int ks0 = 0; ks0 < CTA_ROWS / 8; ks0 += KG) {
+        uint32_t ahi[KG][4], alo[KG][4], bh[KG][NPW][2], bl[KG][NPW][2];
 #pragma unroll
-        for (int par = 0; par < 2; ++par) {
-            const int ks = 2 * ks2 + par;
-            uint32_t ahi[4], alo[4];
-            const float* ap = pa + 8 * ks * RS;
-            split_tf32(ap[0], ahi[0], alo[0]);
-            split_tf32(ap[8], ahi[1], alo[1]);
-            split_tf32(ap[4 * RS], ahi[2], alo[2]);
-            split_tf32(ap[4 * RS + 8], ahi[3], alo[3]);
-            const float* bp = pb + 8 * ks * RS;
+        for (int k = 0; k < KG; ++k) {
+            const float* ap = pa + 8 * (ks0 + k) * PS;
+            split_tf32(ap[0], ahi[k][0], alo[k][0]);
+            split_tf32(ap[8], ahi[k][1], alo[k][1]);
+            split_tf32(ap[4 * PS], ahi[k][2], alo[k][2]);
+            split_tf32(ap[4 * PS + 8], ahi[k][3], alo[k][3]);
+            const float* bp = pb + 8 * (ks0 + k) * PS;
 #pragma unroll
             for (int q = 0; q < NPW; ++q) {
-                const int pidx = warp + 8 * q;
-                if (pidx < P) {
-                    const int ni = pidx / MB;
-                    uint32_t bh0, bl0, bh1, bl1;
-                    split_tf32(bp[8 * ni], bh0, bl0);
-                    split_tf32(bp[4 * RS + 8 * ni], bh1, bl1);
-                    mma_tf32(tmp[par][q], alo, bh0, bh1);
-                    mma_tf32(tmp[par][q], ahi, bl0, bl1);
-                    mma_tf32(tmp[par][q], ahi, bh0, bh1);
-                }
+                split_tf32(on[q] ? bp[nib[q]] : 0.f, bh[k][q][0], bl[k][q][0]);
+                split_tf32(on[q] ? bp[4 * PS + nib[q]] : 0.f, bh[k][q][1], bl[k][q][1]);
             }
         }
+#pragma unroll
+        for (int k = 0; k < KG; ++k)
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) mma_tf32(tmp[k][q], alo[k], bh[k][q][0], bh[k][q][1]);
+#pragma unroll
+        for (int k = 0; k < KG; ++k)
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) mma_tf32(tmp[k][q], ahi[k], bl[k][q][0], bl[k][q][1]);
+#pragma unroll
+        for (int k = 0; k < KG; ++k)
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) mma_tf32(tmp[k][q], ahi[k], bh[k][q][0], bh[k][q][1]);
     }
 #pragma unroll
     for (int q = 0; q < NPW; ++q)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[q][e] += tmp[0][q][e] + tmp[1][q][e];
+        for (int e = 0; e < 4; ++e) {
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < KG; ++k) sum += tmp[k][q][e];
+            acc[q][e] += sum;
+        }
 }
 
 template <int NPW>
@@ -425,15 +472,26 @@ __device__ __forceinline__ void wgrad_flush(const float (&acc)[NPW][4], float* _
     }
 }
 
-// Bias gradient: column sums of the plane over the CTA tile's rows; output o is owned by warp o % 8.
-__device__ __forceinline__ void bias_grad(float* __restrict__ db, const float* __restrict__ plane, int outp, int warp, int lane) {
-    for (int o = warp; o < outp; o += BWD_WARPS) {
+// Bias gradient: column sums of the gz plane.  Each warp sums ITS 32 rows for all columns (lane <-> column: conflict-free)
+// into bpart[warp][col]; after the CTA barrier that follows, bias_combine adds the 8 partials in fixed order.
+__device__ __forceinline__ void bias_partial(float* __restrict__ bpart, const float* __restrict__ myplane, int outp, int warp,
+                                             int lane) {
+    for (int o = lane; o < outp; o += 32) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < ROWS_PER_WARP; r += 2) {
+            s0 += myplane[r * PS + o];
+            s1 += myplane[(r + 1) * PS + o];
+        }
+        bpart[warp * 64 + o] = s0 + s1;
+    }
+}
+__device__ __forceinline__ void bias_combine(float* __restrict__ db, const float* __restrict__ bpart, int outp, int tid) {
+    if (tid < outp) {
         float s = 0.f;
 #pragma unroll
-        for (int q = 0; q < CTA_ROWS / 32; ++q) s += plane[(lane + 32 * q) * RS + o];
-#pragma unroll
-        for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
-        if (lane == 0) db[o] += s;
+        for (int w = 0; w < BWD_WARPS; ++w) s += bpart[w * 64 + tid];
+        db[tid] += s;
     }
 }
 
@@ -444,13 +502,18 @@ ae_bwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
                   const float* __restrict__ save, const float* __restrict__ mag_hat, const float* __restrict__ phs_hat,
                   const float* __restrict__ g_ri, const float* __restrict__ g_mag_hat, const float* __restrict__ g_mag,
                   float* __restrict__ tail_ws, float* __restrict__ g_spec, float* __restrict__ g_spec_lo,
-                  float* __restrict__ partials) {
+                  float* __restrict__ partials, long long* __restrict__ timing) {
     extern __shared__ __align__(16) float smem[];
+    // optional region timing (st_debug_ae_timing): cycles of warp 0 per region, summed over CTAs
+    long long tclk = 0, treg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define ST_T0() if (timing) tclk = clock64();
+#define ST_T(i) if (timing) { const long long n_ = clock64(); treg[i] += n_ - tclk; tclk = n_; }
     float* W = smem;
     float* bias = W + mg.wfloats;                      // staged but unused here (keeps one staging routine)
     float* plane0 = bias + mg.bfloats;
-    float* plane1 = plane0 + CTA_ROWS * RS;
-    float* dbias = plane1 + CTA_ROWS * RS;             // [9][64]
+    float* plane1 = plane0 + CTA_ROWS * PS;
+    float* dbias = plane1 + CTA_ROWS * PS;             // [9][64]
+    float* bpart = dbias + ST_AE_LAYERS * 64;          // [8 warps][64] bias-gradient partials of the current layer
     stage_weights_mma(mg, g, p, W, bias, threadIdx.x, blockDim.x);
     for (int i = threadIdx.x; i < ST_AE_LAYERS * 64; i += blockDim.x) dbias[i] = 0.f;
     __syncthreads();
@@ -463,8 +526,8 @@ ae_bwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
     const int rowstride = 2 * d.Fp;
     const int ss = mg.ss;
     const int ks1 = mg.ks[0];
-    float* my0 = plane0 + warp * ROWS_PER_WARP * RS;
-    float* my1 = plane1 + warp * ROWS_PER_WARP * RS;
+    float* my0 = plane0 + warp * ROWS_PER_WARP * PS;
+    float* my1 = plane1 + warp * ROWS_PER_WARP * PS;
 
     // persistent weight-gradient accumulators: [pairs of this warp][C fragment]
     float a1[4][4], a2[2][4], a3[1][4], a4[1][4], a5[1][4], a6[1][4], a7[1][4], a8[2][4], a9[1][4];
@@ -478,16 +541,18 @@ ae_bwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
 
     for (long ct = blockIdx.x; ct < nct; ct += gridDim.x) {
         const long R0c = ct * CTA_ROWS, R0 = R0c + warp * ROWS_PER_WARP;
+        ST_T0()
         // ---- output side: gz9 into plane0 (own rows), skip/residual gradient to tail_ws.  lane <-> row.
         {
             const long R = R0 + lane;
             const bool ok = R < BF;
             const int b = ok ? (int)(R / d.F) : 0, f = ok ? (int)(R - (long)b * d.F) : 0;
             const float* rec = save + (ok ? R : 0) * ss;
-#pragma unroll 1
-            for (int j = 0; j < mg.outp[8]; ++j) {
+            for (int j = d.OT; j < mg.outp[8]; ++j) my0[lane * PS + j] = 0.f;
+#pragma unroll 3
+            for (int j = 0; j < d.OT; ++j) {
                 float gz = 0.f;
-                if (ok && j < d.OT) {
+                if (ok) {
                     const float e9 = __ldg(rec + mg.soff[8] + j);
                     const long oo = ((long)b * d.OT + j) * d.F + f;
                     const long orr = ((long)b * d.OTp + j) * rowstride + f;
@@ -505,7 +570,7 @@ ae_bwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
                         tail_ws[oo] = gp;
                     }
                 }
-                my0[lane * RS + j] = gz;
+                my0[lane * PS + j] = gz;
             }
         }
         // One layer step:  gz_l lives in `cur` (all 256 rows).  (1) start staging h_{l-1} into `nxt` (cp.async);
@@ -514,67 +579,82 @@ ae_bwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
         // warp's own rows of `nxt`; (7) CTA barrier.  `cur` and `nxt` then swap roles.
 #define ST_BWD_LAYER(L, NPW_, ACC, CUR, NXT, MYCUR, MYNXT, MB_, NB_, OUTP_, HBASE_, HW4_, NT_, KS_)                          \
         __syncthreads();                                                                                                    \
+        ST_T(0)                                                                                                             \
         stage_h_async(NXT, save, R0c, BF, ss, HBASE_, HW4_, threadIdx.x);                                                   \
         {                                                                                                                   \
             float c[2][NT_][4];                                                                                             \
+            ST_T(1)                                                                                                         \
             layer_mma_T<NT_>(MYCUR, KS_, W + mg.off[L], mg.ld[L], c, gq, t);                                                \
+            ST_T(2)                                                                                                         \
+            bias_partial(bpart, MYCUR, OUTP_, warp, lane);                                                                  \
+            ST_T(5)                                                                                                         \
             stage_h_wait();                                                                                                 \
             __syncthreads();                                                                                                \
+            ST_T(3)                                                                                                         \
             wgrad_mma<NPW_>(ACC, CUR, NXT, MB_, NB_, warp, gq, t);                                                          \
-            bias_grad(dbias + L * 64, CUR, OUTP_, warp, lane);                                                              \
+            bias_combine(dbias + L * 64, bpart, OUTP_, threadIdx.x);                                                        \
+            ST_T(4)                                                                                                         \
             __syncthreads();                                                                                                \
             store_gz<NT_>(MYNXT, c, gq, t);                                                                                 \
+            ST_T(6)                                                                                                         \
         }
         // layer 9 (fnn_dec):      OT(<=16) <- 64 ;  h8 is 64 wide
-        ST_BWD_LAYER(8, 1, a9, plane0, plane1, my0, my1, 1, 8, mg.outp[8], mg.soff[7], 16, 8, mg.outp[8] / 8)
+        ST_BWD_LAYER(8, 1, a9, plane0, plane1, my0, my1, 1, 8, mg.outp[8], mg.soff[7], 4, 8, mg.outp[8] / 8)
         // layer 8 (fnn_dec2):     64 <- 32
-        ST_BWD_LAYER(7, 2, a8, plane1, plane0, my1, my0, 4, 4, 64, mg.soff[6], 8, 4, 8)
+        ST_BWD_LAYER(7, 2, a8, plane1, plane0, my1, my0, 4, 4, 64, mg.soff[6], 3, 4, 8)
         // layer 7 (fnn_dec3):     32 <- 16
-        ST_BWD_LAYER(6, 1, a7, plane0, plane1, my0, my1, 2, 2, 32, mg.soff[5], 4, 2, 4)
+        ST_BWD_LAYER(6, 1, a7, plane0, plane1, my0, my1, 2, 2, 32, mg.soff[5], 2, 2, 4)
         // layer 6 (fnn_dec4):     16 <- 16
-        ST_BWD_LAYER(5, 1, a6, plane1, plane0, my1, my0, 1, 2, 16, mg.soff[4], 4, 2, 2)
+        ST_BWD_LAYER(5, 1, a6, plane1, plane0, my1, my0, 1, 2, 16, mg.soff[4], 2, 2, 2)
         // layer 5 (fnn_addknobs): 16 <- 16 + knobs (record slot of h4 is 32 wide: h4 ++ knobs); only h4 carries gradient
-        ST_BWD_LAYER(4, 1, a5, plane0, plane1, my0, my1, 1, 4, 16, mg.soff[3], 8, 2, 2)
+        ST_BWD_LAYER(4, 1, a5, plane0, plane1, my0, my1, 1, 4, 16, mg.soff[3], 3, 2, 2)
         // layer 4 (fnn_enc4):     16 <- 16
-        ST_BWD_LAYER(3, 1, a4, plane1, plane0, my1, my0, 1, 2, 16, mg.soff[2], 4, 2, 2)
+        ST_BWD_LAYER(3, 1, a4, plane1, plane0, my1, my0, 1, 2, 16, mg.soff[2], 2, 2, 2)
         // layer 3 (fnn_enc3):     16 <- 32
-        ST_BWD_LAYER(2, 1, a3, plane0, plane1, my0, my1, 1, 4, 16, mg.soff[1], 8, 4, 2)
+        ST_BWD_LAYER(2, 1, a3, plane0, plane1, my0, my1, 1, 4, 16, mg.soff[1], 3, 4, 2)
         // layer 2 (fnn_enc2):     32 <- 64
-        ST_BWD_LAYER(1, 2, a2, plane1, plane0, my1, my0, 2, 8, 32, mg.soff[0], 16, 8, 4)
+        ST_BWD_LAYER(1, 2, a2, plane1, plane0, my1, my0, 2, 8, 32, mg.soff[0], 4, 8, 4)
 #undef ST_BWD_LAYER
         // ---- layer 1 (fnn_enc): 64 <- T.  Data gradient = dL/d(track), turned into dL/d(re, im).
         __syncthreads();
-        stage_h_async(plane1, save, R0c, BF, ss, mg.soff_v, 2 * ks1, threadIdx.x);      // the input tracks V
+        ST_T(0)
+        stage_h_async(plane1, save, R0c, BF, ss, mg.soff_v, ks1 <= 4 ? 3 : 4, threadIdx.x);   // the input tracks V (32|64 wide)
         {
             float c[2][NT1][4];
+            ST_T(1)
             layer_mma_T<NT1>(my0, 8, W + mg.off[0], mg.ld[0], c, gq, t);
+            ST_T(2)
+            bias_partial(bpart, my0, 64, warp, lane);
+            ST_T(5)
             stage_h_wait();
             __syncthreads();
+            ST_T(3)
             wgrad_mma<4>(a1, plane0, plane1, 4, ks1, warp, gq, t);
-            bias_grad(dbias + 0 * 64, plane0, 64, warp, lane);
+            bias_combine(dbias + 0 * 64, bpart, 64, threadIdx.x);
+            ST_T(4)
             __syncthreads();
             // dL/d(track) goes through the warp's own rows of plane0 so the output-side math runs lane <-> row
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int n = 0; n < NT1; ++n) {
-                    float* q = my0 + (16 * mt + gq) * RS + 8 * n + 2 * t;
+                    float* q = my0 + (16 * mt + gq) * PS + 8 * n + 2 * t;
                     *reinterpret_cast<float2*>(q) = make_float2(c[mt][n][0], c[mt][n][1]);
-                    *reinterpret_cast<float2*>(q + 8 * RS) = make_float2(c[mt][n][2], c[mt][n][3]);
+                    *reinterpret_cast<float2*>(q + 8 * PS) = make_float2(c[mt][n][2], c[mt][n][3]);
                 }
             __syncwarp();
             const long R = R0 + lane;
             if (R < BF) {
                 const int b = (int)(R / d.F), f = (int)(R - (long)b * d.F);
-#pragma unroll 1
+#pragma unroll 5
                 for (int tt = 0; tt < d.T; ++tt) {
-                    float gv = my0[lane * RS + tt];
+                    float gv = my0[lane * PS + tt];
                     if (tt >= tail0) gv += tail_ws[((long)b * d.OT + (tt - tail0)) * d.F + f];
                     const long o = ((long)b * d.Tp + tt) * rowstride + f;
                     const float re = __ldg(spec + o), im = __ldg(spec + o + d.Fp);
                     if (AE == 0) {          // mag = sqrt(re^2+im^2); subgradient 0 at 0 (torch.norm backward)
                         if (g_mag) gv += __ldg(g_mag + ((long)b * d.T + tt) * d.F + f);
-                        const float m = my1[lane * RS + tt];
+                        const float m = my1[lane * PS + tt];
                         const float sc = m > 0.f ? gv / m : 0.f;
                         g_spec[o] = sc * re;
                         g_spec[o + d.Fp] = sc * im;
@@ -589,7 +669,12 @@ ae_bwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
             }
         }
         __syncthreads();
+        ST_T(7)
     }
+    if (timing && threadIdx.x == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(timing) + i, (unsigned long long)treg[i]);
+#undef ST_T0
+#undef ST_T
     // ---- flush this CTA's partial gradients (summed over CTAs in fixed order by ae_grad_reduce_kernel)
     float* dst = partials + ((long)blockIdx.x * 2 + AE) * g.flat_total;
     wgrad_flush<4>(a1, dst + g.flat_off[0], 4, ks1, 64, d.T, warp, gq, t);
@@ -626,7 +711,7 @@ MmaGeom build_mma_geom(const AeGeom& g, int nt9) {
     mg.wfloats = (off + 3) / 4 * 4;
     mg.bfloats = (boff + 3) / 4 * 4;
     mg.soff_v = 272 + 8 * nt9;
-    mg.ss = mg.soff_v + 8 * mg.ks[0];
+    mg.ss = mg.soff_v + (mg.ks[0] <= 4 ? 32 : 64);
     return mg;
 }
 
@@ -646,7 +731,7 @@ void launch_fwd_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const 
 
 }  // namespace
 
-int st_ae_mma_record_floats(const StDims& d) { return 272 + 8 * (d.OT <= 16 ? 2 : (d.OT <= 32 ? 4 : 8)) + (d.T + 7) / 8 * 8; }
+int st_ae_mma_record_floats(const StDims& d) { return 272 + 8 * (d.OT <= 16 ? 2 : (d.OT <= 32 ? 4 : 8)) + (d.T <= 32 ? 32 : 64); }
 
 // save_m / save_p: NULL (inference) or B*F records of st_ae_mma_record_floats() floats each (training).
 // Returns false when the geometry is outside what the tensor-core kernels cover (caller uses the SIMT kernel).
@@ -671,7 +756,7 @@ template <int NT1>
 void launch_bwd_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const AeParams& pm, const AeParams& pp, const float* spec,
                      int B, const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat, const float* g_ri,
                      const float* g_mag_hat, const float* g_mag, float* tail_ws, float* g_spec, float* g_spec_lo, float* partials,
-                     int grid, size_t smem, cudaStream_t s) {
+                     long long* timing, int grid, size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(ae_bwd_mma_kernel<NT1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -679,9 +764,9 @@ void launch_bwd_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const 
         configured = true;
     }
     ae_bwd_mma_kernel<NT1, 0><<<grid, BWD_WARPS * 32, smem, s>>>(d, g, mg, pm, spec, B, save_m, mag_hat, phs_hat, g_ri, g_mag_hat,
-                                                                 g_mag, tail_ws, g_spec, g_spec_lo, partials);
+                                                                 g_mag, tail_ws, g_spec, g_spec_lo, partials, timing);
     ae_bwd_mma_kernel<NT1, 1><<<grid, BWD_WARPS * 32, smem, s>>>(d, g, mg, pp, spec, B, save_p, mag_hat, phs_hat, g_ri, g_mag_hat,
-                                                                 g_mag, tail_ws, g_spec, g_spec_lo, partials);
+                                                                 g_mag, tail_ws, g_spec, g_spec_lo, partials, timing ? timing + 8 : nullptr);
 }
 }  // namespace
 
@@ -691,18 +776,18 @@ void launch_bwd_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const 
 int st_launch_ae_backward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, int B,
                               const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat,
                               const float* g_ri, const float* g_mag_hat, const float* g_mag, float* tail_ws, float* g_spec,
-                              float* g_spec_lo, float* partials, int sm_count, cudaStream_t s) {
+                              float* g_spec_lo, float* partials, long long* timing, int sm_count, cudaStream_t s) {
     if (d.T > 64 || d.OT > 16 || d.K > 16) return 0;
     const MmaGeom mg = build_mma_geom(g, 2);
-    const size_t smem = sizeof(float) * ((size_t)mg.wfloats + mg.bfloats + 2 * (size_t)CTA_ROWS * RS + ST_AE_LAYERS * 64);
+    const size_t smem = sizeof(float) * ((size_t)mg.wfloats + mg.bfloats + 2 * (size_t)CTA_ROWS * PS + ST_AE_LAYERS * 64 + BWD_WARPS * 64);
     if (smem > 227 * 1024) return 0;
     const long nct = ((long)B * d.F + CTA_ROWS - 1) / CTA_ROWS;
     const int grid = (int)std::min<long>(nct, sm_count);
     if (mg.ks[0] <= 4)
         launch_bwd_pair<4>(d, g, mg, pm, pp, spec, B, save_m, save_p, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, tail_ws, g_spec,
-                           g_spec_lo, partials, grid, smem, s);
+                           g_spec_lo, partials, timing, grid, smem, s);
     else
         launch_bwd_pair<8>(d, g, mg, pm, pp, spec, B, save_m, save_p, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, tail_ws, g_spec,
-                           g_spec_lo, partials, grid, smem, s);
+                           g_spec_lo, partials, timing, grid, smem, s);
     return grid;
 }

@@ -35,6 +35,7 @@ struct st_handle {
     bool training = true;         // st_set_training: save activations in st_forward for a following st_backward
     bool have_saves = false;      // the last forward wrote ae_save_*
     bool use_mma_bwd = true;
+    long long* ae_timing = nullptr;   // device: 16 region counters of the tensor-core AE backward (st_debug_ae_timing)
     float* small = nullptr;       // reduction scratch + scalar outputs
     unsigned* counters = nullptr;
     double* win = nullptr;        // [hamming | GLA] in double, for st_init_frontend
@@ -491,7 +492,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         int gr = 0;
         if (h->have_saves)
             gr = st_launch_ae_backward_mma(d, h->g, pm, pp, h->spec, B, h->ae_save_m, h->ae_save_p, h->mag_hat_ws, h->phs_hat_ws,
-                                           h->g_ri, g_mag_hat, g_mag, h->tail_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->sm_count, s);
+                                           h->g_ri, g_mag_hat, g_mag, h->tail_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_timing, h->sm_count, s);
         if (gr > 0)
             part_ctas = gr;
         else
@@ -709,4 +710,22 @@ extern "C" int st_debug_gemm(st_handle* h, int use_tc /*0 FFMA, 1 tcgen05, 2 tcg
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
     return r;
+}
+
+// Diagnostic: enable (on=1) region timing of the tensor-core autoencoder backward and read the 16 cycle counters
+// (8 regions x {magnitude, phase} launch; warp 0 of every CTA, summed).  Reading resets them.  out may be NULL.
+extern "C" int st_debug_ae_timing(st_handle* h, int on, long long* out_host) {
+    if (!h) return 1;
+    ST_CUDA_OK(cudaSetDevice(h->device));
+    ST_CUDA_OK(cudaDeviceSynchronize());
+    if (on && !h->ae_timing) {
+        ST_CUDA_OK(cudaMalloc(&h->ae_timing, 16 * sizeof(long long)));
+        ST_CUDA_OK(cudaMemset(h->ae_timing, 0, 16 * sizeof(long long)));
+    }
+    if (out_host && h->ae_timing) {
+        ST_CUDA_OK(cudaMemcpy(out_host, h->ae_timing, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+        ST_CUDA_OK(cudaMemset(h->ae_timing, 0, 16 * sizeof(long long)));
+    }
+    if (!on && h->ae_timing) { cudaFree(h->ae_timing); h->ae_timing = nullptr; }
+    return 0;
 }

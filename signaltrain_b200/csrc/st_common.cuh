@@ -143,7 +143,7 @@ bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& 
 int st_launch_ae_backward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, int B,
                               const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat,
                               const float* g_ri, const float* g_mag_hat, const float* g_mag, float* tail_ws, float* g_spec_hi,
-                              float* g_spec_lo, float* partials, int sm_count, cudaStream_t s);
+                              float* g_spec_lo, float* partials, long long* timing /*nullable: 16 counters*/, int sm_count, cudaStream_t s);
 
 // st_loss_opt.cu
 void st_launch_loss(const StDims& d, const float* y_hat, const float* y, const float* mag_hat, const float* sbf,
