@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import data as st_data
-from . import learningrate, loss_functions, misc, nn_proc, optim
+from . import learningrate, loss_functions, misc, nn_proc, optim, parallel
 
 
 class FusedTrainer:
@@ -32,12 +32,8 @@ class FusedTrainer:
         self.optimizer = optimizer if optimizer is not None else optim.Adam(model, lr=float(lr_sched[0]))
         _, self.m, self.v = self.optimizer._state_lists()
         # one flat gradient buffer (16-byte aligned slots) so a single collective covers all 40 tensors
-        offs, total = [], 0
-        for p in self.params:
-            offs.append(total)
-            total += (p.numel() + 3) // 4 * 4
-        self.flat_grads = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.grads = [self.flat_grads[o:o + p.numel()].view(p.shape) for o, p in zip(offs, self.params)]
+        fb = parallel.FlatBuffer([tuple(p.shape) for p in self.params], dev)
+        self.flat_grads, self.grads = fb.flat, fb.views
         for p, g in zip(model.ordered_parameters(), self.grads):
             p.grad = g
         self.lr_sched = np.asarray(lr_sched, dtype=np.float64)
@@ -46,10 +42,10 @@ class FusedTrainer:
         self.l1_lambda = l1_lambda
         self.sbf = None
         self.eng = None
-        import torch.distributed as dist
-        self.dist = dist if (distributed if distributed is not None else (dist.is_available() and dist.is_initialized())) else None
         self.pg = process_group
-        self.world = self.dist.get_world_size(self.pg) if self.dist else 1
+        self.world = parallel.world_size(self.pg) if distributed is not False else 1
+        if self.world > 1:
+            parallel.broadcast_parameters(self.params, 0, self.pg)
         self.loss_buf = torch.zeros((), device=dev, dtype=torch.float32)
 
     def _setup(self, x):
@@ -72,8 +68,8 @@ class FusedTrainer:
             y_hat, _, mag_hat, _ = eng.forward(x, knobs, self.params)
             loss, g_y, g_m = eng.loss(y_hat, y, mag_hat, self.sbf, self.l1_lambda / 10)
             eng.backward(g_y, None, g_m, self.params, self.grads)
-            self.dist.all_reduce(self.flat_grads, group=self.pg)
-            hp = eng.adam_hp(self.lr, step_no, grad_scale=1.0 / self.world, max_norm=1.0)
+            scale = parallel.allreduce_sum_(self.flat_grads, self.pg)       # NCCL over NVLink on the GPU box
+            hp = eng.adam_hp(self.lr, step_no, grad_scale=scale, max_norm=1.0)
             eng.adam_step(self.params, self.grads, self.m, self.v, hp)
             self.loss_buf = loss
         self.optimizer._step = step_no
