@@ -227,14 +227,15 @@ def run_native(args):
     h2d = B * (C + L + KNOBS) * 4
     # ---- per-stage device time (separate pass: the event pairs perturb the pipeline slightly) ---------------
     stages = {}
+    eng.profile(rank == 0)
     if rank == 0:
-        eng.profile(True)
         eng.profile_read()
-        for _ in range(max(3, min(K, 10))):
-            trainer.step(*batch_of(it, (xd, yd, kd)))
-            it += 1
+    for _ in range(max(3, min(K, 10))):          # every rank steps (the allreduce is collective); rank 0 records events
+        trainer.step(*batch_of(it, (xd, yd, kd)))
+        it += 1
+    if rank == 0:
         stages = {k: (ms / max(c, 1), c) for k, (ms, c) in eng.profile_read().items() if c}
-        eng.profile(False)
+    eng.profile(False)
     # ---- max over ranks ---------------------------------------------------------------------------------------
     t = torch.tensor([ms_total, e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
