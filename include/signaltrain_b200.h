@@ -69,6 +69,14 @@ int st_bins(const st_handle* h);                  /* F = ft/2+1            cls_f
  * Writes the four (N,N) front-end matrices into params[0..3]. */
 int st_init_frontend(st_handle* h, float* const* params, void* stream);
 
+/* Analysis.forward(wave_form) alone (cls_fe_dft.py:50-58): x (B,C) -> an_real, an_imag (B,T,F) with the (N,1,N)
+ * weights w_real / w_imag.  Synthesis.forward(real, imag) alone (cls_fe_dft.py:102-115): (B,OT,F) x2 -> wave (B,L).
+ * Forward only; they use the handle's workspace (a following st_backward needs a fresh st_forward). */
+int st_analysis(st_handle* h, const float* x, const float* w_real, const float* w_imag, int batch, float* an_real,
+                float* an_imag, void* stream);
+int st_synthesis(st_handle* h, const float* real, const float* imag, const float* w_real, const float* w_imag, int batch,
+                 float* wave, void* stream);
+
 /* st_model.forward(x, knobs, return_acts): nn_proc.py:392 -> AsymMPAEC.forward :305-340.
  *   x (B,C)  knobs (B,K)  ->  y_hat (B,L) [= 2*y_hat of :340]  mag (B,T,F)  mag_hat (B,OT,F)
  *   acts: NULL, or ST_NUM_ACTS device pointers receiving the reference's layer_acts (:311-335), each

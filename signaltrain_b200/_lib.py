@@ -33,6 +33,9 @@ _SIGNATURES = {
     "st_out_samples": (ctypes.c_int, [ctypes.c_void_p]),
     "st_bins": (ctypes.c_int, [ctypes.c_void_p]),
     "st_init_frontend": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "st_analysis": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_void_p]),
+    "st_synthesis": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, c_float_p,
+                                    ctypes.c_void_p]),
     "st_forward": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p, c_float_p, c_float_p,
                                   c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
     "st_loss": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_float, ctypes.c_int,

@@ -338,6 +338,54 @@ extern "C" int st_init_frontend(st_handle* h, float* const* params, void* stream
     return 0;
 }
 
+// Analysis.forward (cls_fe_dft.py:50-58) alone: x (B, C) -> an_real, an_imag (B, T, F).  `scale` = 1 here (the model
+// halves its input, nn_proc.py:307; a bare Analysis does not).
+static int analysis_only(st_handle* h, const float* x, const float* Wr, const float* Wi, int B, float* re, float* im, cudaStream_t s) {
+    const StDims& d = h->d;
+    if (ensure_workspace(h, B)) return 1;
+    st_launch_pad_split(x, h->xpad, h->xpad_lo, B, d.C, d.N, d.Sx, 1.0f, s);
+    st_launch_pack_analysis(d, Wr, Wi, h->wcat, h->wcat_lo, s);
+    const int MT = B * d.Tp, F2 = 2 * d.Fp;
+    int r = -1;
+    if (h->use_tc) {
+        TcOperand A{h->xpad, h->xpad_lo, MT, d.N, d.H}, W{h->wcat, h->wcat_lo, F2, d.N, d.N};
+        r = st_launch_gemm_tc(false, false, A, W, h->spec, F2, MT, F2, d.N, 1, 0, true, h->sm_count, s);
+    }
+    if (r < 0) {
+        GemmOperand A{h->xpad, h->xpad_lo, d.H}, W{h->wcat, h->wcat_lo, d.N};
+        st_launch_gemm(true, true, A, W, h->spec, F2, MT, F2, d.N, 1, 0, s);
+    }
+    st_launch_unpack_spec(d, h->spec, B, re, im, s);
+    h->launches += 4;
+    ST_LAUNCH_OK(h);
+    h->fwdB = 0;      // the workspace no longer holds a model forward
+    return 0;
+}
+
+// Synthesis.forward (cls_fe_dft.py:102-115) alone: real, imag (B, OT, F) -> wave (B, L).
+static int synthesis_only(st_handle* h, const float* re, const float* im, const float* Sr, const float* Si, int B, float* wave,
+                          cudaStream_t s) {
+    const StDims& d = h->d;
+    if (ensure_workspace(h, B)) return 1;
+    st_launch_pack_ri(d, re, im, B, h->ri, h->ri_lo, s);
+    st_launch_fold_synthesis(d, Sr, Si, h->sfold, h->sfold_lo, s);
+    const int MO = B * d.OTp, F2 = 2 * d.Fp;
+    int r = -1;
+    if (h->use_tc) {
+        TcOperand R{h->ri, h->ri_lo, MO, F2, F2}, S{h->sfold, h->sfold_lo, F2, d.N, d.N};
+        r = st_launch_gemm_tc(false, true, R, S, h->fo, d.N, MO, d.N, F2, 1, 0, true, h->sm_count, s);
+    }
+    if (r < 0) {
+        GemmOperand R{h->ri, h->ri_lo, F2}, S{h->sfold, h->sfold_lo, d.N};
+        st_launch_gemm(true, false, R, S, h->fo, d.N, MO, d.N, F2, 1, 0, s);
+    }
+    st_launch_overlap_add(d, h->fo, nullptr, B, wave, nullptr, nullptr, s);
+    h->launches += 4;
+    ST_LAUNCH_OK(h);
+    h->fwdB = 0;
+    return 0;
+}
+
 static int forward_impl(st_handle* h, const float* x, const float* knobs, int B, const float* const* params, float* y_hat,
                         float* mag, float* mag_hat_user, float* const* acts, cudaStream_t s) {
     const StDims& d = h->d;
@@ -728,4 +776,18 @@ extern "C" int st_debug_ae_timing(st_handle* h, int on, long long* out_host) {
     }
     if (!on && h->ae_timing) { cudaFree(h->ae_timing); h->ae_timing = nullptr; }
     return 0;
+}
+
+extern "C" int st_analysis(st_handle* h, const float* x, const float* w_real, const float* w_imag, int batch, float* an_real,
+                           float* an_imag, void* stream) {
+    if (!h) return 1;
+    if (!x || !w_real || !w_imag || !an_real || !an_imag) return st_fail_msg(h, "st_analysis: null argument");
+    return analysis_only(h, x, w_real, w_imag, batch, an_real, an_imag, (cudaStream_t)stream);
+}
+
+extern "C" int st_synthesis(st_handle* h, const float* real, const float* imag, const float* w_real, const float* w_imag, int batch,
+                            float* wave, void* stream) {
+    if (!h) return 1;
+    if (!real || !imag || !w_real || !w_imag || !wave) return st_fail_msg(h, "st_synthesis: null argument");
+    return synthesis_only(h, real, imag, w_real, w_imag, batch, wave, (cudaStream_t)stream);
 }

@@ -96,6 +96,8 @@ void st_launch_overlap_add(const StDims& d, const float* frames_out, const float
                            float* y_hat, float* x_fwdsyn, float* y_half, cudaStream_t s);
 void st_launch_finalize_dft_grads(const StDims& d, const float* part_a, const float* part_s, int splits_a,
                                   int splits_s, float* gWr, float* gWi, float* gSr, float* gSi, cudaStream_t s);
+void st_launch_unpack_spec(const StDims& d, const float* spec, int B, float* re, float* im, cudaStream_t s);
+void st_launch_pack_ri(const StDims& d, const float* re, const float* im, int B, float* ri_hi, float* ri_lo, cudaStream_t s);
 void st_launch_init_frontend(const StDims& d, float* Wr, float* Wi, float* Sr, float* Si, float* scratch, cudaStream_t s);
 
 // st_gemm_simt.cu  C[M,N] (+split partials) = op(A) * op(B)

@@ -101,6 +101,10 @@ __global__ void overlap_add_kernel(StDims d, const float* __restrict__ fo, const
             const float4 v = ld4(fo + ((long)b * d.OTp + t) * d.N + (j + d.N - t * d.H));
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
+        if (!x) {      // stand-alone Synthesis.forward (cls_fe_dft.py:102-115): no residual, no *2
+            st4(y_hat + (long)b * d.L + j, acc);
+            continue;
+        }
         float4 xr = ld4(x + (long)b * d.C + (d.C - d.L) + j);
         xr.x *= 0.5f; xr.y *= 0.5f; xr.z *= 0.5f; xr.w *= 0.5f;
         if (x_fwdsyn) st4(x_fwdsyn + (long)b * d.L + j, acc);
@@ -175,6 +179,32 @@ __global__ void init_frontend_kernel(StDims d, const double* __restrict__ win, f
     }
 }
 
+// spec[(b,t), (re|im)] (row stride 2Fp, Tp rows per window) -> re, im as contiguous (B, T, F)   [Analysis.forward output]
+__global__ void unpack_spec_kernel(StDims d, const float* __restrict__ spec, int B, float* __restrict__ re, float* __restrict__ im) {
+    const long total = (long)B * d.T * d.F;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int f = (int)(i % d.F);
+        const long bt = i / d.F;
+        const int t = (int)(bt % d.T), b = (int)(bt / d.T);
+        const long o = ((long)b * d.Tp + t) * (2 * d.Fp) + f;
+        re[i] = spec[o];
+        im[i] = spec[o + d.Fp];
+    }
+}
+// re, im (B, OT, F) -> ri[(b,t), (re|im)] as a tf32 (hi, lo) pair   [Synthesis.forward input]
+__global__ void pack_ri_kernel(StDims d, const float* __restrict__ re, const float* __restrict__ im, int B, float* __restrict__ ri,
+                               float* __restrict__ ri_lo) {
+    const long total = (long)B * d.OT * d.F;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int f = (int)(i % d.F);
+        const long bt = i / d.F;
+        const int t = (int)(bt % d.OT), b = (int)(bt / d.OT);
+        const long o = ((long)b * d.OTp + t) * (2 * d.Fp) + f;
+        st_split_tf32(re[i], ri[o], ri_lo[o]);
+        st_split_tf32(im[i], ri[o + d.Fp], ri_lo[o + d.Fp]);
+    }
+}
+
 inline int grid_for(long items, int threads) {
     long g = (items + threads - 1) / threads;
     const long cap = 148L * 16;
@@ -205,4 +235,11 @@ void st_launch_finalize_dft_grads(const StDims& d, const float* pa, const float*
 void st_launch_init_frontend(const StDims& d, float* Wr, float* Wi, float* Sr, float* Si, float* scratch, cudaStream_t s) {
     init_frontend_kernel<<<grid_for((long)d.N * d.N, 256), 256, 0, s>>>(d, reinterpret_cast<const double*>(scratch), Wr, Wi,
                                                                         Sr, Si);
+}
+
+void st_launch_unpack_spec(const StDims& d, const float* spec, int B, float* re, float* im, cudaStream_t s) {
+    unpack_spec_kernel<<<grid_for((long)B * d.T * d.F, 256), 256, 0, s>>>(d, spec, B, re, im);
+}
+void st_launch_pack_ri(const StDims& d, const float* re, const float* im, int B, float* ri, float* ri_lo, cudaStream_t s) {
+    pack_ri_kernel<<<grid_for((long)B * d.OT * d.F, 256), 256, 0, s>>>(d, re, im, B, ri, ri_lo);
 }

@@ -131,6 +131,29 @@ class Engine:
             _check(t, "front-end weight", (self.g.N, 1, self.g.N), self.device)
         self._ok(self.lib.st_init_frontend(self.h, tab, self._stream()), "st_init_frontend")
 
+    def analysis(self, x, w_real, w_imag):
+        g = self.g
+        B = x.shape[0]
+        _check(x, "wave_form", (B, g.C), self.device)
+        _check(w_real, "conv_analysis_real.weight", (g.N, 1, g.N), self.device)
+        _check(w_imag, "conv_analysis_imag.weight", (g.N, 1, g.N), self.device)
+        re = torch.empty((B, g.T, g.F), device=self.device, dtype=torch.float32)
+        im = torch.empty_like(re)
+        self._ok(self.lib.st_analysis(self.h, _ptr(x), _ptr(w_real), _ptr(w_imag), B, _ptr(re), _ptr(im), self._stream()), "st_analysis")
+        return re, im
+
+    def synthesis(self, real, imag, w_real, w_imag):
+        g = self.g
+        B = real.shape[0]
+        _check(real, "real", (B, g.OT, g.F), self.device)
+        _check(imag, "imag", (B, g.OT, g.F), self.device)
+        _check(w_real, "conv_synthesis_real.weight", (g.N, 1, g.N), self.device)
+        _check(w_imag, "conv_synthesis_imag.weight", (g.N, 1, g.N), self.device)
+        wave = torch.empty((B, g.L), device=self.device, dtype=torch.float32)
+        self._ok(self.lib.st_synthesis(self.h, _ptr(real), _ptr(imag), _ptr(w_real), _ptr(w_imag), B, _ptr(wave), self._stream()),
+                 "st_synthesis")
+        return wave
+
     def set_training(self, on):
         self._ok(self.lib.st_set_training(self.h, int(bool(on))), "st_set_training")
 

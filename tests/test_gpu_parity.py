@@ -285,3 +285,24 @@ def test_full_size_batch_properties():
     sr, si = gf[2][:, 0], gf[3][:, 0]
     assert torch.equal(sr[1:d.F - 1], torch.flip(sr[d.F:], [0]))
     assert torch.equal(si[1:d.F - 1], -torch.flip(si[d.F:], [0]))
+
+
+def test_standalone_analysis_synthesis_roundtrip():
+    """Analysis.forward / Synthesis.forward as stand-alone classes (cls_fe_dft.py:50-58, 102-115): oracle parity, and
+    the STFT pair at its Fourier/Griffin-Lim initialisation reconstructs the waveform (8e-7)."""
+    import signaltrain_b200 as st
+    d = O.model_dims(1, 4, 4)
+    rng = np.random.RandomState(2)
+    B = 5
+    x = (0.5 * np.sin(2 * np.pi * 440 * np.arange(d.C) / 44100.0) + 0.1 * rng.standard_normal((B, d.C))).astype(np.float32)
+    ana = st.cls_fe_dft.Analysis(d.N, d.H).cuda()
+    syn = st.cls_fe_dft.Synthesis(d.N, d.H).cuda()
+    re, im = ana.forward(torch.from_numpy(x).cuda())
+    Wr, Wi, Sr, Si = O.dft_init(d.N, d.H)
+    ref_re, ref_im, _ = O.analysis_forward(d, Wr.astype(np.float64), Wi.astype(np.float64), x.astype(np.float64))
+    np.testing.assert_allclose(re.cpu().numpy(), ref_re, atol=SPEC_TOL, rtol=SPEC_RTOL)
+    np.testing.assert_allclose(im.cpu().numpy(), ref_im, atol=SPEC_TOL, rtol=SPEC_RTOL)
+    wave = syn.forward(re, im)                              # all T frames -> (T-1)*H - N samples back
+    assert wave.shape == (B, (d.T - 1) * d.H - d.N)
+    n = wave.shape[1]
+    np.testing.assert_allclose(wave.cpu().numpy(), x[:, :n], atol=5e-6)
