@@ -35,6 +35,7 @@ struct st_handle {
     bool training = true;         // st_set_training: save activations in st_forward for a following st_backward
     bool have_saves = false;      // the last forward wrote ae_save_*
     bool use_mma_bwd = true;
+    bool use_tc_ae = true;        // tcgen05 autoencoder forward (ST_DISABLE_TCGEN05_AE=1 -> mma.sync kernel)
     long long* ae_timing = nullptr;   // device: 16 region counters of the tensor-core AE backward (st_debug_ae_timing)
     float* small = nullptr;       // reduction scratch + scalar outputs
     unsigned* counters = nullptr;
@@ -178,6 +179,7 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     d.Sx = d.Tp * H; d.Sg = d.OTp * H;
     if (const char* e = getenv("ST_DISABLE_TCGEN05")) h->use_tc = !(e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_MMA_BACKWARD")) h->use_mma_bwd = !(e[0] == '1');
+    if (const char* e = getenv("ST_DISABLE_TCGEN05_AE")) h->use_tc_ae = !(e[0] == '1');
     build_geom(d, h->g);
     if (st_ae_configure(h, d, h->g)) {
         snprintf(g_create_err, sizeof(g_create_err), "%s", h->err);
@@ -423,9 +425,14 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         // production path: tensor-core (mma.sync TF32x3) register-resident chain; the SIMT kernel serves return_acts
         const bool save = h->training && h->use_mma_bwd;
         h->have_saves = false;
-        if (acts || !st_launch_ae_forward_mma(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri,
-                                              h->ri_lo, save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr,
-                                              h->sm_count, s))
+        bool done = false;
+        if (!acts && h->use_tc_ae)      // tcgen05 / TMEM chain; falls through to the mma.sync kernel for other geometries
+            done = st_launch_ae_forward_tc(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
+                                           save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->sm_count, s);
+        if (!acts && !done)
+            done = st_launch_ae_forward_mma(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
+                                            save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->sm_count, s);
+        if (!done)
             st_launch_ae_forward(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo, acts,
                                  h->ae_grid, s);
         else
