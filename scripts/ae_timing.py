@@ -14,7 +14,7 @@ x, y, k = (torch.from_numpy(a).cuda() for a in data.make_pool(200, 8192, 2048, d
 for _ in range(3):
     tr.step(x, y, k)
 eng = tr.eng
-buf = (ctypes.c_longlong * 16)()
+buf = (ctypes.c_longlong * 24)()
 eng.lib.st_debug_ae_timing(eng.h, 1, None)
 n = 5
 for _ in range(n):
@@ -28,3 +28,11 @@ for ae in range(2):
     for i in range(8):
         print("   %-26s %9.0f cyc/CTA/step  %5.1f%%" % (names[i], buf[8 * ae + i] / ncta / n, 100.0 * buf[8 * ae + i] / max(tot, 1)))
 eng.lib.st_debug_ae_timing(eng.h, 0, None)
+
+fnames = ["input stage", "wait MMA (d_ready)", "hidden epilogue", "output epilogue"]
+print("tcgen05 forward, stream-0 thread 0, cycles/CTA/step:")
+for ae in range(2):
+    tot = sum(buf[16 + 4 * ae + i] for i in range(4))
+    print("AE", ae, "total", tot / ncta / n)
+    for i in range(4):
+        print("   %-22s %9.0f  %5.1f%%" % (fnames[i], buf[16 + 4 * ae + i] / ncta / n, 100.0 * buf[16 + 4 * ae + i] / max(tot, 1)))

@@ -77,13 +77,32 @@ __device__ __forceinline__ void write_a4(float* ahi, float* alo, int row, int co
     *reinterpret_cast<float4*>(alo + off) = l;
 }
 
+// Copy `ncols` (16, 32 or 64; from column col0) of the stream's tile, as hi + lo, to the rows' saved records: each lane
+// moves one 16-byte chunk, a warp instruction covers whole 64/128-byte row segments (coalesced), 128 threads cooperate.
+__device__ __forceinline__ void save_from_tile(const float* __restrict__ ahi, const float* __restrict__ alo, float* __restrict__ save,
+                                               long R0, long BF, int ss, int soff, int col0, int ncols, int tid128) {
+    const int cpr = ncols >> 2;                               // chunks per row: 4, 8 or 16
+    const int lg = cpr == 4 ? 2 : (cpr == 8 ? 3 : 4);
+    for (int idx = tid128; idx < TILE * cpr; idx += 128) {
+        const int r = idx >> lg, c = idx & (cpr - 1);
+        if (R0 + r >= BF) continue;
+        const int off = sw128_off(r, col0 + 4 * c, TILE);
+        const float4 h = *reinterpret_cast<const float4*>(ahi + off), l = *reinterpret_cast<const float4*>(alo + off);
+        *reinterpret_cast<float4*>(save + (R0 + r) * ss + soff + 4 * c) = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+    }
+}
+
 // AE = 0: magnitude autoencoder ('sf').  AE = 1: phase autoencoder + residual + polar->rect.
 template <int AE>
+// 9 warps are allocated as 12 (register file granule = 4 warps): 168 registers per thread is the ceiling
 __global__ void __launch_bounds__(THREADS, 1)
 ae_fwd_tc_kernel(StDims d, AeGeom g, TcAeGeom tg, AeParams p, const float* __restrict__ spec, const float* __restrict__ knobs,
                  int B, float* __restrict__ mag_out, float* __restrict__ mag_hat, float* __restrict__ phs_hat,
-                 float* __restrict__ ri, float* __restrict__ ri_lo, float* __restrict__ save) {
+                 float* __restrict__ ri, float* __restrict__ ri_lo, float* __restrict__ save, long long* __restrict__ timing) {
     extern __shared__ uint8_t smem_raw[];
+    long long tclk = 0, treg[4] = {0, 0, 0, 0};
+#define ST_T0() if (timing) tclk = clock64();
+#define ST_T(i) if (timing) { const long long n_ = clock64(); treg[i] += n_ - tclk; tclk = n_; }
     float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* whi = smem;
     float* wlo = whi + tg.wfloats;
@@ -166,41 +185,53 @@ ae_fwd_tc_kernel(StDims d, AeGeom g, TcAeGeom tg, AeParams p, const float* __res
             const bool ok = R < BF;
             const int b = ok ? (int)(R / d.F) : 0, f = ok ? (int)(R - (long)b * d.F) : 0;
             float* rec = save ? save + (ok ? R : 0) * tg.ss : nullptr;
-            // ---- input track -> K-block 0 of A (columns >= T are zero)
+            ST_T0()
+            // ---- input track -> K-block 0 of A (columns >= T are zero).  All loads are issued before any use.
             {
                 const float* sp = spec + (long)b * d.Tp * rowstride + f;
                 float* mo = (AE == 0 && mag_out && ok) ? mag_out + (long)b * d.T * d.F + f : nullptr;
-#pragma unroll 2
-                for (int c4 = 0; c4 < 32; c4 += 4) {
-                    float v[4];
+#pragma unroll 1
+                for (int c0 = 0; c0 < 32; c0 += 16) {          // two batches of 16 frames: 32 loads in flight per thread
+                    float re[16], im[16];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int tt = c4 + e;
-                        v[e] = 0.f;
-                        if (ok && tt < d.T) {
-                            const float re = __ldg(sp + (long)tt * rowstride), im = __ldg(sp + (long)tt * rowstride + d.Fp);
+                    for (int e = 0; e < 16; ++e) {
+                        const bool in = ok && c0 + e < d.T;
+                        re[e] = in ? __ldg(sp + (long)(c0 + e) * rowstride) : 0.f;
+                        im[e] = in ? __ldg(sp + (long)(c0 + e) * rowstride + d.Fp) : 0.f;
+                    }
+#pragma unroll
+                    for (int c4 = 0; c4 < 16; c4 += 4) {
+                        float v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int tt = c0 + c4 + e;
                             if (AE == 0) {
-                                v[e] = sqrtf(re * re + im * im);                             // nn_proc.py:309
-                                if (mo) mo[(long)tt * d.F] = v[e];
+                                v[e] = sqrtf(re[c4 + e] * re[c4 + e] + im[c4 + e] * im[c4 + e]);       // nn_proc.py:309
+                                if (mo && tt < d.T) mo[(long)tt * d.F] = v[e];
                             } else {
-                                v[e] = atan2f(im, re + 1e-7f);                               // nn_proc.py:310
+                                v[e] = (ok && tt < d.T) ? atan2f(im[c4 + e], re[c4 + e] + 1e-7f) : 0.f; // nn_proc.py:310
                             }
                         }
+                        write_a4(ahi, alo, row, c0 + c4, make_float4(v[0], v[1], v[2], v[3]));
                     }
-                    const float4 v4 = make_float4(v[0], v[1], v[2], v[3]);
-                    write_a4(ahi, alo, row, c4, v4);
-                    if (rec && ok) *reinterpret_cast<float4*>(rec + tg.soff_v + c4) = v4;
                 }
             }
             fence_async_smem();
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             if (threadIdx.x == 32 + 128 * s) mbar_arrive(&a_ready[s]);
+            if (save) {
+                save_from_tile(ahi, alo, save, tile * TILE, BF, tg.ss, tg.soff_v, 0, 32, threadIdx.x - 32 - 128 * s);
+                // the copy reads other threads' rows: nobody may start overwriting the tile before everyone is done
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            }
+            ST_T(0)
             // ---- layers
 #pragma unroll 1
             for (int l = 0; l < NL; ++l) {
                 mbar_wait(&d_ready[s], ph);
                 ph ^= 1;
                 tc_fence_after();
+                ST_T(1)
                 const int n = tg.n[l];
                 const float* bl = bias + tg.boff[l];
                 if (l < NL - 1) {
@@ -218,7 +249,6 @@ ae_fwd_tc_kernel(StDims d, AeGeom g, TcAeGeom tg, AeParams p, const float* __res
                             h.z = elu_f(__uint_as_float(rr[c4 + 2]) + bl[c0 + c4 + 2]);
                             h.w = elu_f(__uint_as_float(rr[c4 + 3]) + bl[c0 + c4 + 3]);
                             write_a4(ahi, alo, row, c0 + c4, h);
-                            if (rec && ok) *reinterpret_cast<float4*>(rec + tg.soff[l] + c0 + c4) = h;
                         }
                     }
                     if (l == 3) {
@@ -232,7 +262,6 @@ ae_fwd_tc_kernel(StDims d, AeGeom g, TcAeGeom tg, AeParams p, const float* __res
                             kv.z = (ok && c4 + 2 < d.K) ? __ldg(kp + c4 + 2) : 0.f;
                             kv.w = (ok && c4 + 3 < d.K) ? __ldg(kp + c4 + 3) : 0.f;
                             write_a4(ahi, alo, row, 16 + c4, kv);
-                            if (rec && ok) *reinterpret_cast<float4*>(rec + tg.soff[3] + 16 + c4) = kv;
                         }
                     } else if (n < 32 * tg.kb[l + 1]) {
                         // the next layer reads a full 32-column K-block: clear the columns this layer did not write
@@ -242,6 +271,12 @@ ae_fwd_tc_kernel(StDims d, AeGeom g, TcAeGeom tg, AeParams p, const float* __res
                     fence_async_smem();
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     if (threadIdx.x == 32 + 128 * s) mbar_arrive(&a_ready[s]);
+                    // the record copy reads the tile the MMAs are reading: it overlaps them for free
+                    if (save) {
+                        save_from_tile(ahi, alo, save, tile * TILE, BF, tg.ss, tg.soff[l], 0, l == 3 ? 32 : n, threadIdx.x - 32 - 128 * s);
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                    }
+                    ST_T(2)
                 } else {
                     // fnn_dec + output-side math (thread = row: coalesced along the bin axis)
                     uint32_t rr[16];
@@ -250,31 +285,43 @@ ae_fwd_tc_kernel(StDims d, AeGeom g, TcAeGeom tg, AeParams p, const float* __res
                     tc_fence_before();
                     if (ok) {
                         const float* sp = spec + ((long)b * d.Tp + tail0) * rowstride + f;
+                        float re[16], im[16], mh[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            if (j >= d.OT) break;
-                            const float ev = elu_f(__uint_as_float(rr[j]) + bl[j]);
-                            const float re = __ldg(sp + (long)j * rowstride), im = __ldg(sp + (long)j * rowstride + d.Fp);
-                            const long oo = ((long)b * d.OT + j) * d.F + f;
-                            if (rec) rec[tg.soff[8] + j] = ev;
-                            if (AE == 0) {
-                                mag_hat[oo] = ev * sqrtf(re * re + im * im);                 // 'sf', nn_proc.py:115
-                            } else {
-                                const float phv = ev + atan2f(im, re + 1e-7f);               // nn_proc.py:322
-                                const float m = mag_hat[oo];
-                                float sn, cs;
-                                sincosf(phv, &sn, &cs);
-                                phs_hat[oo] = phv;
-                                const long orr = ((long)b * d.OTp + j) * rowstride + f;
-                                st_split_tf32(m * cs, ri[orr], ri_lo[orr]);                 // nn_proc.py:325-326
-                                st_split_tf32(m * sn, ri[orr + d.Fp], ri_lo[orr + d.Fp]);
+                            const bool in = j < d.OT;
+                            re[j] = in ? __ldg(sp + (long)j * rowstride) : 0.f;
+                            im[j] = in ? __ldg(sp + (long)j * rowstride + d.Fp) : 0.f;
+                            mh[j] = (AE == 1 && in) ? mag_hat[((long)b * d.OT + j) * d.F + f] : 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (j < d.OT) {
+                                const float ev = elu_f(__uint_as_float(rr[j]) + bl[j]);
+                                const long oo = ((long)b * d.OT + j) * d.F + f;
+                                if (rec) rec[tg.soff[8] + j] = ev;
+                                if (AE == 0) {
+                                    mag_hat[oo] = ev * sqrtf(re[j] * re[j] + im[j] * im[j]);     // 'sf', nn_proc.py:115
+                                } else {
+                                    const float phv = ev + atan2f(im[j], re[j] + 1e-7f);         // nn_proc.py:322
+                                    float sn, cs;
+                                    sincosf(phv, &sn, &cs);
+                                    phs_hat[oo] = phv;
+                                    const long orr = ((long)b * d.OTp + j) * rowstride + f;
+                                    st_split_tf32(mh[j] * cs, ri[orr], ri_lo[orr]);             // nn_proc.py:325-326
+                                    st_split_tf32(mh[j] * sn, ri[orr + d.Fp], ri_lo[orr + d.Fp]);
+                                }
                             }
                         }
                     }
+                    ST_T(3)
                 }
             }
         }
+        if (timing && threadIdx.x == 32)
+            for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(timing) + i, (unsigned long long)treg[i]);
     }
+#undef ST_T0
+#undef ST_T
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -310,7 +357,7 @@ TcAeGeom build_tc_geom(const AeGeom& g) {
 // Same contract as st_launch_ae_forward_mma (same saved-record layout); covers T <= 32, OT <= 16, K <= 16.
 bool st_launch_ae_forward_tc(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
                              const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo,
-                             float* save_m, float* save_p, int sm_count, cudaStream_t s) {
+                             float* save_m, float* save_p, long long* timing, int sm_count, cudaStream_t s) {
     if (d.T > 32 || d.OT > 16 || d.K > 16) return false;
     const TcAeGeom tg = build_tc_geom(g);
     const size_t smem = 1024 + sizeof(float) * (2 * (size_t)tg.wfloats + NSTREAM * 2 * 2 * (size_t)KB_FLOATS + tg.bfloats) + 64;
@@ -323,7 +370,7 @@ bool st_launch_ae_forward_tc(const StDims& d, const AeGeom& g, const AeParams& p
     }
     const long ntiles = ((long)B * d.F + TILE - 1) / TILE;
     const int grid = (int)std::min<long>((ntiles + NSTREAM - 1) / NSTREAM, sm_count);
-    ae_fwd_tc_kernel<0><<<grid, THREADS, smem, s>>>(d, g, tg, pm, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m);
-    ae_fwd_tc_kernel<1><<<grid, THREADS, smem, s>>>(d, g, tg, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_p);
+    ae_fwd_tc_kernel<0><<<grid, THREADS, smem, s>>>(d, g, tg, pm, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m, timing);
+    ae_fwd_tc_kernel<1><<<grid, THREADS, smem, s>>>(d, g, tg, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_p, timing ? timing + 4 : nullptr);
     return true;
 }

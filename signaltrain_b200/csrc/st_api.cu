@@ -35,7 +35,8 @@ struct st_handle {
     bool training = true;         // st_set_training: save activations in st_forward for a following st_backward
     bool have_saves = false;      // the last forward wrote ae_save_*
     bool use_mma_bwd = true;
-    bool use_tc_ae = true;        // tcgen05 autoencoder forward (ST_DISABLE_TCGEN05_AE=1 -> mma.sync kernel)
+    bool use_tc_ae = false;       // tcgen05 autoencoder forward (ST_ENABLE_TCGEN05_AE=1): correct, but its CUDA-core epilogue
+                                  // makes it slower than the default chain
     long long* ae_timing = nullptr;   // device: 16 region counters of the tensor-core AE backward (st_debug_ae_timing)
     float* small = nullptr;       // reduction scratch + scalar outputs
     unsigned* counters = nullptr;
@@ -179,7 +180,7 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     d.Sx = d.Tp * H; d.Sg = d.OTp * H;
     if (const char* e = getenv("ST_DISABLE_TCGEN05")) h->use_tc = !(e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_MMA_BACKWARD")) h->use_mma_bwd = !(e[0] == '1');
-    if (const char* e = getenv("ST_DISABLE_TCGEN05_AE")) h->use_tc_ae = !(e[0] == '1');
+    if (const char* e = getenv("ST_ENABLE_TCGEN05_AE")) h->use_tc_ae = (e[0] == '1');
     build_geom(d, h->g);
     if (st_ae_configure(h, d, h->g)) {
         snprintf(g_create_err, sizeof(g_create_err), "%s", h->err);
@@ -428,7 +429,8 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         bool done = false;
         if (!acts && h->use_tc_ae)      // tcgen05 / TMEM chain; falls through to the mma.sync kernel for other geometries
             done = st_launch_ae_forward_tc(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
-                                           save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->sm_count, s);
+                                           save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->ae_timing ? h->ae_timing + 16 : nullptr,
+                                           h->sm_count, s);
         if (!acts && !done)
             done = st_launch_ae_forward_mma(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
                                             save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->sm_count, s);
@@ -768,18 +770,18 @@ extern "C" int st_debug_gemm(st_handle* h, int use_tc /*0 FFMA, 1 tcgen05, 2 tcg
 }
 
 // Diagnostic: enable (on=1) region timing of the tensor-core autoencoder backward and read the 16 cycle counters
-// (8 regions x {magnitude, phase} launch; warp 0 of every CTA, summed).  Reading resets them.  out may be NULL.
+// (backward: 8 regions x {magnitude, phase}; then tcgen05 forward: 4 regions x 2; 24 values).  Reading resets them.  out may be NULL.
 extern "C" int st_debug_ae_timing(st_handle* h, int on, long long* out_host) {
     if (!h) return 1;
     ST_CUDA_OK(cudaSetDevice(h->device));
     ST_CUDA_OK(cudaDeviceSynchronize());
     if (on && !h->ae_timing) {
-        ST_CUDA_OK(cudaMalloc(&h->ae_timing, 16 * sizeof(long long)));
-        ST_CUDA_OK(cudaMemset(h->ae_timing, 0, 16 * sizeof(long long)));
+        ST_CUDA_OK(cudaMalloc(&h->ae_timing, 24 * sizeof(long long)));
+        ST_CUDA_OK(cudaMemset(h->ae_timing, 0, 24 * sizeof(long long)));
     }
     if (out_host && h->ae_timing) {
-        ST_CUDA_OK(cudaMemcpy(out_host, h->ae_timing, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-        ST_CUDA_OK(cudaMemset(h->ae_timing, 0, 16 * sizeof(long long)));
+        ST_CUDA_OK(cudaMemcpy(out_host, h->ae_timing, 24 * sizeof(long long), cudaMemcpyDeviceToHost));
+        ST_CUDA_OK(cudaMemset(h->ae_timing, 0, 24 * sizeof(long long)));
     }
     if (!on && h->ae_timing) { cudaFree(h->ae_timing); h->ae_timing = nullptr; }
     return 0;
