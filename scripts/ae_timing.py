@@ -29,8 +29,8 @@ for ae in range(2):
         print("   %-26s %9.0f cyc/CTA/step  %5.1f%%" % (names[i], buf[8 * ae + i] / ncta / n, 100.0 * buf[8 * ae + i] / max(tot, 1)))
 eng.lib.st_debug_ae_timing(eng.h, 0, None)
 
-fnames = ["input stage", "wait MMA (d_ready)", "hidden epilogue", "output epilogue"]
-print("tcgen05 forward, stream-0 thread 0, cycles/CTA/step:")
+fnames = ["input stage", "layers (FFMA2 + reload)", "record copies", "output stage"]
+print("FFMA2 forward, warp 0, cycles/CTA/step:")
 for ae in range(2):
     tot = sum(buf[16 + 4 * ae + i] for i in range(4))
     print("AE", ae, "total", tot / ncta / n)

@@ -1,0 +1,379 @@
+// Autoencoders on the packed-FP32 pipe (FFMA2, fma.rn.f32x2) -- the production path.
+//
+// Why not the tensor cores: the nine Linear layers of AsymAutoEncoder (nn_proc.py:47-57, 79-121) are 9..64 wide and
+// the 1e-5 waveform parity needs fp32 products, i.e. 3xTF32 on the tensor pipe.  Measured on B200
+// (scripts/ubench/fma_ubench.cu): FFMA2 sustains 32 FMA/clk/SMSP in ONE issue slot per two cycles, the legacy
+// mma.sync TF32 path ~107/3 = 36 FMA-equivalents/clk/SMSP before fragment loads and hi/lo splitting, and the tcgen05
+// chain (st_ae_tc.cu) spends more CUDA-core work re-staging every layer's operand than the FFMA2 chain spends on the
+// layer itself.  The FFMA2 chain is exact fp32 (no split), has no operand shuffling, and is bounded by the FMA pipe.
+//
+// Forward mapping: a LANE owns TWO rows (row = one (batch, bin) pair); a warp owns a chunk of 64 consecutive rows and
+// walks the chain on its own (no block-wide barrier after the weights are staged):
+//   * the layer input a[row][k] sits in registers as k-pairs (float2);
+//   * weights W[o][k] are staged once per CTA in shared memory; one broadcast LDS.128 brings four k of one output and
+//     feeds 2 rows x 2 FFMA2 (shared-memory return bandwidth is 0.5 LDS.128/clk/SM, so >= 4 FFMA2 per LDS.128 keeps the
+//     FMA pipe the bound -- that is what the second row per lane is for);
+//   * the output loop is a real loop over groups of four outputs (compact code), so outputs go through a per-warp
+//     staging tile in shared memory and come back as the next layer's statically indexed registers; the same tile
+//     feeds the coalesced copy of the saved-activation record when training.
+// Chunks are dealt to warps round-robin across the whole grid (chunk c -> warp c / grid, CTA c % grid) so the last,
+// partial round spreads over all SMs.
+//
+// Reference semantics: AsymAutoEncoder.forward (nn_proc.py:77-126) for both autoencoders, plus the prologue
+// (mag / phase, :309-310) and epilogue (skip-filter :115, phase residual :322, polar->rect :325-326) of AsymMPAEC.forward.
+#include <algorithm>
+
+#include "st_common.cuh"
+
+namespace {
+
+constexpr int NL = ST_AE_LAYERS;
+constexpr int MAX_WARPS = 11;             // 11 x 64 staged rows + the weights fill the 227 KB of shared memory
+constexpr int MIN_WARPS = 8;
+constexpr int CHUNK = 64;                 // rows per warp chunk: lane <-> rows R0 + lane and R0 + 32 + lane
+constexpr int SS = 68;                    // staging-tile row stride (floats): 16-byte rows of consecutive lanes hit distinct banks
+
+struct F2Geom {
+    int woff[NL];     // float offset of W_l[o][INP_l] inside the weight block
+    int boff[NL];
+    int wfloats, bfloats;
+    int soff[NL];     // saved-record offsets (record shared with the mma.sync kernels: h1..h8, e9, v)
+    int soff_v, ss;
+};
+
+// ELU(alpha=1); exp through MUFU.EX2 with flush-to-zero (a flushed exp only moves a result that is -1 to 2^-126 anyway)
+__device__ __forceinline__ float elu_f(float z) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * 1.4426950408889634f));
+    return z > 0.f ? z : e - 1.f;
+}
+// acc += a * b on the packed-fp32 pipe.  volatile: keeps the source order, which interleaves eight independent
+// accumulator chains (left to itself the compiler walks one output at a time and the chain latency shows).
+__device__ __forceinline__ void fma2(float2& acc, const float2& a, float wx, float wy) {
+    unsigned long long& c = reinterpret_cast<unsigned long long&>(acc);
+    unsigned long long w;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(w) : "f"(wx), "f"(wy));
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(w));
+}
+
+// 4-byte asynchronous global -> shared copies: a rolled loop can put a whole row's loads in flight (no register per load,
+// no unrolled code), the math then runs from shared memory in a rolled loop as well -- the transcendental code
+// (atan2f, sincosf) exists once, which keeps the kernel inside the instruction cache.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Stage W_l[o][k] zero-padded to (OUTP, INP) plus biases.
+__device__ void stage_weights_f2(const F2Geom& fg, const AeGeom& g, const AeParams& p, const int* inp, const int* outp,
+                                 float* W, float* bias, int tid, int nthreads) {
+    for (int l = 0; l < NL; ++l) {
+        const int IN = g.in[l], OUT = g.out[l], IP = inp[l], OP = outp[l];
+        for (int idx = tid; idx < OP * IP; idx += nthreads) {
+            const int o = idx / IP, i = idx - o * IP;
+            W[fg.woff[l] + idx] = (o < OUT && i < IN) ? p.W[l][o * IN + i] : 0.f;
+        }
+        for (int o = tid; o < OP; o += nthreads) bias[fg.boff[l] + o] = (o < OUT) ? p.b[l][o] : 0.f;
+    }
+}
+
+// One Linear + ELU for the lane's two rows:  st[r][o] = ELU(b[o] + sum_k a[r][k] W[o][k]),  o in [0, OUTP).
+// Each accumulator is a (even-k, odd-k) pair of partial sums; eight independent FFMA2 chains per lane.
+template <int INP, int OUTP>
+__device__ __forceinline__ void layer_f2(const float* __restrict__ W, const float* __restrict__ bias, const float2 (&a)[2][32],
+                                         float* __restrict__ st0, float* __restrict__ st1) {
+#pragma unroll 1
+    for (int o = 0; o < OUTP; o += 4) {
+        float2 acc[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[0][j] = acc[1][j] = make_float2(0.f, 0.f);
+        const float* w = W + o * INP;
+#pragma unroll
+        for (int k = 0; k < INP; k += 4) {
+            float4 wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv[j] = *reinterpret_cast<const float4*>(w + j * INP + k);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) fma2(acc[r][j], a[r][k / 2], wv[j].x, wv[j].y);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) fma2(acc[r][j], a[r][k / 2 + 1], wv[j].z, wv[j].w);
+        }
+        const float4 bb = *reinterpret_cast<const float4*>(bias + o);
+        *reinterpret_cast<float4*>(st0 + o) = make_float4(elu_f(acc[0][0].x + acc[0][0].y + bb.x), elu_f(acc[0][1].x + acc[0][1].y + bb.y),
+                                                          elu_f(acc[0][2].x + acc[0][2].y + bb.z), elu_f(acc[0][3].x + acc[0][3].y + bb.w));
+        *reinterpret_cast<float4*>(st1 + o) = make_float4(elu_f(acc[1][0].x + acc[1][0].y + bb.x), elu_f(acc[1][1].x + acc[1][1].y + bb.y),
+                                                          elu_f(acc[1][2].x + acc[1][2].y + bb.z), elu_f(acc[1][3].x + acc[1][3].y + bb.w));
+    }
+}
+
+// The lane's own staged rows -> statically indexed registers (columns [0, WIDTH)).
+template <int WIDTH>
+__device__ __forceinline__ void reload_f2(float2 (&a)[2][32], const float* __restrict__ st0, const float* __restrict__ st1) {
+#pragma unroll
+    for (int c = 0; c < WIDTH / 4; ++c) {
+        const float4 v0 = *reinterpret_cast<const float4*>(st0 + 4 * c), v1 = *reinterpret_cast<const float4*>(st1 + 4 * c);
+        a[0][2 * c] = make_float2(v0.x, v0.y); a[0][2 * c + 1] = make_float2(v0.z, v0.w);
+        a[1][2 * c] = make_float2(v1.x, v1.y); a[1][2 * c + 1] = make_float2(v1.z, v1.w);
+    }
+}
+
+// Copy columns [0, WIDTH) of the warp's 64 staged rows to the rows' saved records: a warp instruction moves whole
+// 64..256-byte row segments (coalesced).  tile = [64 rows][SS].
+template <int WIDTH>
+__device__ __forceinline__ void save_f2(const float* __restrict__ tile, float* __restrict__ save, long R0, long BF, int ss, int soff,
+                                        int lane) {
+    constexpr int W4 = WIDTH / 4, RPI = 32 / W4;       // float4 per row; rows per warp instruction
+    const int c4 = lane % W4, r0 = lane / W4;
+#pragma unroll 4
+    for (int r = r0; r < CHUNK; r += RPI) {
+        if (R0 + r < BF)
+            *reinterpret_cast<float4*>(save + (R0 + r) * ss + soff + 4 * c4) = *reinterpret_cast<const float4*>(tile + r * SS + 4 * c4);
+    }
+}
+
+// AE = 0: magnitude autoencoder ('sf').  AE = 1: phase autoencoder + residual + polar->rect.
+// IN0 / IN4 / OUT8: T, 16 + K and OT rounded up to a multiple of four (compile time: the register tiles need it).
+template <int AE, int IN0, int IN4, int OUT8>
+__global__ void __launch_bounds__(MAX_WARPS * 32, 1)
+ae_fwd_f2_kernel(StDims d, AeGeom g, F2Geom fg, AeParams p, const float* __restrict__ spec, const float* __restrict__ knobs, int B,
+                 float* __restrict__ mag_out, float* __restrict__ mag_hat, float* __restrict__ phs_hat, float* __restrict__ ri,
+                 float* __restrict__ ri_lo, float* __restrict__ save, long long* __restrict__ timing) {
+    extern __shared__ __align__(16) float smem[];
+    // optional region timing (st_debug_ae_timing): cycles of warp 0 per region, summed over CTAs
+    long long tclk = 0, treg[4] = {0, 0, 0, 0};
+#define ST_T0() if (timing) tclk = clock64();
+#define ST_T(i) if (timing) { const long long n_ = clock64(); treg[i] += n_ - tclk; tclk = n_; }
+    float* W = smem;
+    float* bias = W + fg.wfloats;
+    float* tiles = bias + fg.bfloats;                       // [warps][64][SS]
+    {
+        const int inp[NL] = {IN0, 64, 32, 16, IN4, 16, 16, 32, 64}, outp[NL] = {64, 32, 16, 16, 16, 16, 32, 64, OUT8};
+        stage_weights_f2(fg, g, p, inp, outp, W, bias, threadIdx.x, blockDim.x);
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    float* tile = tiles + warp * CHUNK * SS;
+    float* st0 = tile + lane * SS;
+    float* st1 = tile + (32 + lane) * SS;
+    const long BF = (long)B * d.F;
+    const long nchunks = (BF + CHUNK - 1) / CHUNK;
+    const int tail0 = d.T - d.OT, rowstride = 2 * d.Fp;
+
+    for (long c = (long)warp * gridDim.x + blockIdx.x; c < nchunks; c += (long)nwarps * gridDim.x) {
+        const long R0 = c * CHUNK;
+        long R[2] = {R0 + lane, R0 + 32 + lane};
+        bool ok[2];
+        int b[2], f[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            ok[r] = R[r] < BF;
+            b[r] = ok[r] ? (int)(R[r] / d.F) : 0;
+            f[r] = ok[r] ? (int)(R[r] - (long)b[r] * d.F) : 0;
+        }
+        float2 a[2][32];
+        ST_T0()
+        // ---- input tracks (nn_proc.py:309-310): the row's T-frame magnitude / phase track.
+        // re -> own row cols [0, T), im -> cols [32, 32 + T); rows past the end read row 0 (valid memory) and are masked.
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+            const float* sp = spec + (long)b[r] * d.Tp * rowstride + f[r];
+            float* st = r == 0 ? st0 : st1;
+#pragma unroll 4
+            for (int t = 0; t < d.T; ++t) {
+                cp_async4(st + t, sp + (long)t * rowstride);
+                cp_async4(st + 32 + t, sp + (long)t * rowstride + d.Fp);
+            }
+        }
+        cp_async_wait_all();
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+            float* st = r == 0 ? st0 : st1;
+            float* mo = (AE == 0 && mag_out && ok[r]) ? mag_out + (long)b[r] * d.T * d.F + f[r] : nullptr;
+#pragma unroll 1
+            for (int t = 0; t < d.T; ++t) {
+                const float re = st[t], im = st[32 + t];
+                float v;
+                if (AE == 0) {
+                    v = ok[r] ? sqrtf(re * re + im * im) : 0.f;
+                    if (mo) mo[(long)t * d.F] = v;
+                } else {
+                    v = ok[r] ? atan2f(im, re + 1e-7f) : 0.f;
+                }
+                st[t] = v;
+            }
+            for (int t = d.T; t < 32; ++t) st[t] = 0.f;
+        }
+        reload_f2<IN0>(a, st0, st1);
+        ST_T(0)
+        if (save) {
+            __syncwarp();
+            save_f2<32>(tile, save, R0, BF, fg.ss, fg.soff_v, lane);
+            __syncwarp();
+        }
+        ST_T(2)
+        // ---- hidden layers.  After each: (sync) reload own rows as the next input, copy the record slot, (sync).
+#define ST_F2_LAYER(L, INP_, OUTP_, SAVEW_)                                              \
+        layer_f2<INP_, OUTP_>(W + fg.woff[L], bias + fg.boff[L], a, st0, st1);           \
+        reload_f2<OUTP_>(a, st0, st1);                                                   \
+        ST_T(1)                                                                          \
+        if (save) {                                                                      \
+            __syncwarp();                                                                \
+            save_f2<SAVEW_>(tile, save, R0, BF, fg.ss, fg.soff[L], lane);                \
+            __syncwarp();                                                                \
+        }                                                                                \
+        ST_T(2)
+        ST_F2_LAYER(0, IN0, 64, 64)
+        ST_F2_LAYER(1, 64, 32, 32)
+        ST_F2_LAYER(2, 32, 16, 16)
+        // layer 4 (fnn_enc4) and the knob concat (torch.cat, nn_proc.py:95-96): columns 16.. of fnn_addknobs' input
+        layer_f2<16, 16>(W + fg.woff[3], bias + fg.boff[3], a, st0, st1);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float* kp = knobs + (long)b[r] * d.K;
+            float* st = r == 0 ? st0 : st1;
+#pragma unroll
+            for (int c4 = 0; c4 < 16; c4 += 4) {
+                float4 kv;
+                kv.x = (ok[r] && c4 + 0 < d.K) ? __ldg(kp + c4 + 0) : 0.f;
+                kv.y = (ok[r] && c4 + 1 < d.K) ? __ldg(kp + c4 + 1) : 0.f;
+                kv.z = (ok[r] && c4 + 2 < d.K) ? __ldg(kp + c4 + 2) : 0.f;
+                kv.w = (ok[r] && c4 + 3 < d.K) ? __ldg(kp + c4 + 3) : 0.f;
+                *reinterpret_cast<float4*>(st + 16 + c4) = kv;
+            }
+        }
+        reload_f2<IN4>(a, st0, st1);
+        ST_T(1)
+        if (save) {
+            __syncwarp();
+            save_f2<32>(tile, save, R0, BF, fg.ss, fg.soff[3], lane);
+            __syncwarp();
+        }
+        ST_T(2)
+        ST_F2_LAYER(4, IN4, 16, 16)
+        ST_F2_LAYER(5, 16, 16, 16)
+        ST_F2_LAYER(6, 16, 32, 32)
+        ST_F2_LAYER(7, 32, 64, 64)
+#undef ST_F2_LAYER
+        // ---- fnn_dec + output-side math (lane <-> row: coalesced along the bin axis).  The tail frames of the spectrum
+        // (and mag_hat for the phase pass) are fetched into the free columns of the lane's rows while fnn_dec runs.
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+            const float* sp = spec + ((long)b[r] * d.Tp + tail0) * rowstride + f[r];
+            float* st = r == 0 ? st0 : st1;
+#pragma unroll 1
+            for (int j = 0; j < d.OT; ++j) {
+                cp_async4(st + 16 + j, sp + (long)j * rowstride);
+                cp_async4(st + 32 + j, sp + (long)j * rowstride + d.Fp);
+                if (AE == 1) cp_async4(st + 48 + j, mag_hat + ((long)b[r] * d.OT + j) * d.F + f[r]);
+            }
+        }
+        layer_f2<64, OUT8>(W + fg.woff[8], bias + fg.boff[8], a, st0, st1);
+        if (OUT8 < 16) {
+            *reinterpret_cast<float4*>(st0 + 12) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(st1 + 12) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        ST_T(1)
+        if (save) {
+            __syncwarp();
+            save_f2<16>(tile, save, R0, BF, fg.ss, fg.soff[8], lane);
+            __syncwarp();
+        }
+        ST_T(2)
+        cp_async_wait_all();                                 // the tail frames staged before fnn_dec
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+            if (!ok[r]) continue;
+            const float* st = r == 0 ? st0 : st1;
+#pragma unroll 1
+            for (int j = 0; j < d.OT; ++j) {
+                const float ev = st[j], re = st[16 + j], im = st[32 + j];
+                const long oo = ((long)b[r] * d.OT + j) * d.F + f[r];
+                if (AE == 0) {
+                    mag_hat[oo] = ev * sqrtf(re * re + im * im);                     // 'sf', nn_proc.py:115
+                } else {
+                    const float phv = ev + atan2f(im, re + 1e-7f);                   // nn_proc.py:322
+                    float sn, cs;
+                    sincosf(phv, &sn, &cs);
+                    phs_hat[oo] = phv;
+                    const float mh = st[48 + j];
+                    const long orr = ((long)b[r] * d.OTp + j) * rowstride + f[r];
+                    st_split_tf32(mh * cs, ri[orr], ri_lo[orr]);                     // nn_proc.py:325-326
+                    st_split_tf32(mh * sn, ri[orr + d.Fp], ri_lo[orr + d.Fp]);
+                }
+            }
+        }
+        ST_T(3)
+    }
+    if (timing && threadIdx.x == 0)
+        for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(timing) + i, (unsigned long long)treg[i]);
+#undef ST_T0
+#undef ST_T
+}
+
+F2Geom build_f2_geom(int in0, int in4, int out8) {
+    F2Geom fg;
+    const int inp[NL] = {in0, 64, 32, 16, in4, 16, 16, 32, 64}, outp[NL] = {64, 32, 16, 16, 16, 16, 32, 64, out8};
+    const int soff[NL] = {0, 64, 96, 112, 144, 160, 176, 208, 272};   // h1..h8 (h4 slot 32 wide: ++knobs), e9
+    int off = 0, boff = 0;
+    for (int l = 0; l < NL; ++l) {
+        fg.woff[l] = off;
+        off += inp[l] * outp[l];
+        fg.boff[l] = boff;
+        boff += outp[l];
+        fg.soff[l] = soff[l];
+    }
+    fg.wfloats = off;
+    fg.bfloats = (boff + 3) / 4 * 4;
+    fg.soff_v = 272 + 16;
+    fg.ss = fg.soff_v + 32;
+    return fg;
+}
+
+template <int IN0, int IN4, int OUT8>
+bool launch_fwd_f2(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, const float* knobs,
+                   int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo, float* save_m, float* save_p,
+                   long long* timing, int sm_count, cudaStream_t s) {
+    const F2Geom fg = build_f2_geom(IN0, IN4, OUT8);
+    // warps per CTA: the fewest rounds of chunks over the grid, then the fewest warps (more registers' worth of latency
+    // hiding is not needed: a warp with two accumulator chains already saturates the FMA pipe)
+    const long nchunks = ((long)B * d.F + CHUNK - 1) / CHUNK;
+    int warps = MIN_WARPS;
+    long best_rounds = -1;
+    for (int w = MIN_WARPS; w <= MAX_WARPS; ++w) {
+        const long per_round = (long)std::min<long>((nchunks + w - 1) / w, sm_count) * w;
+        const long rounds = (nchunks + per_round - 1) / per_round;
+        if (best_rounds < 0 || rounds < best_rounds) { best_rounds = rounds; warps = w; }
+    }
+    const size_t smem = sizeof(float) * ((size_t)fg.wfloats + fg.bfloats + (size_t)warps * CHUNK * SS);
+    if (smem > 227 * 1024) return false;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(ae_fwd_f2_kernel<0, IN0, IN4, OUT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+        if (cudaFuncSetAttribute(ae_fwd_f2_kernel<1, IN0, IN4, OUT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+        configured = true;
+    }
+    const int grid = (int)std::min<long>((nchunks + warps - 1) / warps, sm_count);
+    ae_fwd_f2_kernel<0, IN0, IN4, OUT8><<<grid, warps * 32, smem, s>>>(d, g, fg, pm, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m, timing);
+    ae_fwd_f2_kernel<1, IN0, IN4, OUT8><<<grid, warps * 32, smem, s>>>(d, g, fg, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_p,
+                                                                    timing ? timing + 4 : nullptr);
+    return true;
+}
+
+}  // namespace
+
+// Same contract and saved-record layout as st_launch_ae_forward_mma; covers T <= 32, OT <= 16, K <= 16.
+bool st_launch_ae_forward_f2(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
+                             const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo,
+                             float* save_m, float* save_p, long long* timing, int sm_count, cudaStream_t s) {
+    if (d.T > 32 || d.OT > 16 || d.K > 16) return false;
+    if (st_ae_mma_record_floats(d) != 320) return false;
+    // the reference's own geometry (comp_4c: T = 25, OT = 9, K = 4) gets the tight instantiation
+    if (d.T <= 28 && d.K <= 4 && d.OT <= 12)
+        return launch_fwd_f2<28, 20, 12>(d, g, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m, save_p, timing, sm_count, s);
+    return launch_fwd_f2<32, 32, 16>(d, g, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m, save_p, timing, sm_count, s);
+}

@@ -35,6 +35,7 @@ struct st_handle {
     bool training = true;         // st_set_training: save activations in st_forward for a following st_backward
     bool have_saves = false;      // the last forward wrote ae_save_*
     bool use_mma_bwd = true;
+    bool use_f2_fwd = true;       // FFMA2 (packed fp32) autoencoder forward (ST_DISABLE_FFMA2_AE=1 -> mma.sync kernels)
     bool use_tc_ae = false;       // tcgen05 autoencoder forward (ST_ENABLE_TCGEN05_AE=1): correct, but its CUDA-core epilogue
                                   // makes it slower than the default chain
     long long* ae_timing = nullptr;   // device: 16 region counters of the tensor-core AE backward (st_debug_ae_timing)
@@ -181,6 +182,7 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     if (const char* e = getenv("ST_DISABLE_TCGEN05")) h->use_tc = !(e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_MMA_BACKWARD")) h->use_mma_bwd = !(e[0] == '1');
     if (const char* e = getenv("ST_ENABLE_TCGEN05_AE")) h->use_tc_ae = (e[0] == '1');
+    if (const char* e = getenv("ST_DISABLE_FFMA2_AE")) h->use_f2_fwd = !(e[0] == '1');
     build_geom(d, h->g);
     if (st_ae_configure(h, d, h->g)) {
         snprintf(g_create_err, sizeof(g_create_err), "%s", h->err);
@@ -431,6 +433,10 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
             done = st_launch_ae_forward_tc(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
                                            save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->ae_timing ? h->ae_timing + 16 : nullptr,
                                            h->sm_count, s);
+        if (!acts && !done && h->use_f2_fwd)
+            done = st_launch_ae_forward_f2(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
+                                           save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr,
+                                           h->ae_timing ? h->ae_timing + 16 : nullptr, h->sm_count, s);
         if (!acts && !done)
             done = st_launch_ae_forward_mma(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
                                             save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->sm_count, s);

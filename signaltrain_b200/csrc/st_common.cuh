@@ -146,6 +146,10 @@ bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& 
 bool st_launch_ae_forward_tc(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
                              const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri_hi, float* ri_lo,
                              float* save_m, float* save_p, long long* timing /*nullable: 8 counters*/, int sm_count, cudaStream_t s);
+// st_ae_f2.cu: packed-fp32 (FFMA2) autoencoders, exact fp32 (production path; same record layout; T <= 32, OT <= 16)
+bool st_launch_ae_forward_f2(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
+                             const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri_hi, float* ri_lo,
+                             float* save_m, float* save_p, long long* timing /*nullable: 8 counters*/, int sm_count, cudaStream_t s);
 int st_launch_ae_backward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, int B,
                               const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat,
                               const float* g_ri, const float* g_mag_hat, const float* g_mag, float* tail_ws, float* g_spec_hi,
