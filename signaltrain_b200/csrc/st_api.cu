@@ -35,6 +35,7 @@ struct st_handle {
     bool training = true;         // st_set_training: save activations in st_forward for a following st_backward
     bool have_saves = false;      // the last forward wrote ae_save_*
     bool use_mma_bwd = true;
+    bool use_f2_bwd = true;       // FFMA2 warp-specialised autoencoder backward (ST_DISABLE_FFMA2_AE_BWD=1 -> mma.sync kernel)
     bool use_f2_fwd = true;       // FFMA2 (packed fp32) autoencoder forward (ST_DISABLE_FFMA2_AE=1 -> mma.sync kernels)
     bool use_tc_ae = false;       // tcgen05 autoencoder forward (ST_ENABLE_TCGEN05_AE=1): correct, but its CUDA-core epilogue
                                   // makes it slower than the default chain
@@ -183,6 +184,7 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     if (const char* e = getenv("ST_DISABLE_MMA_BACKWARD")) h->use_mma_bwd = !(e[0] == '1');
     if (const char* e = getenv("ST_ENABLE_TCGEN05_AE")) h->use_tc_ae = (e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_FFMA2_AE")) h->use_f2_fwd = !(e[0] == '1');
+    if (const char* e = getenv("ST_DISABLE_FFMA2_AE_BWD")) h->use_f2_bwd = !(e[0] == '1');
     build_geom(d, h->g);
     if (st_ae_configure(h, d, h->g)) {
         snprintf(g_create_err, sizeof(g_create_err), "%s", h->err);
@@ -553,7 +555,10 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         AeParams pm, pp;
         split_params(params, pm, pp);
         int gr = 0;
-        if (h->have_saves)
+        if (h->have_saves && h->use_f2_bwd && !h->ae_timing)
+            gr = st_launch_ae_backward_f2(d, h->g, pm, pp, h->spec, B, h->ae_save_m, h->ae_save_p, h->mag_hat_ws, h->phs_hat_ws,
+                                          h->g_ri, g_mag_hat, g_mag, h->g_spec, h->g_spec_lo, h->ae_part, h->sm_count, s);
+        if (gr == 0 && h->have_saves)
             gr = st_launch_ae_backward_mma(d, h->g, pm, pp, h->spec, B, h->ae_save_m, h->ae_save_p, h->mag_hat_ws, h->phs_hat_ws,
                                            h->g_ri, g_mag_hat, g_mag, h->tail_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_timing, h->sm_count, s);
         if (gr > 0)
