@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Region breakdown of the tensor-core AE backward (cycles of warp 0, summed over CTAs) at B=200."""
+"""Region breakdown of the autoencoder kernels (cycles of one producer / consumer warp per CTA, summed over CTAs) at B=200."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -20,13 +20,15 @@ n = 5
 for _ in range(n):
     tr.step(x, y, k)
 eng.lib.st_debug_ae_timing(eng.h, 1, buf)
-names = ["sync0(prev store/step0)", "stage issue", "bwd-data mma", "cp.async wait+sync", "wgrad", "bias_grad", "sync+store_gz", "L1 epilogue+sync"]
+names = ["producer: slot acquire (empty wait)", "producer: cp.async wait", "producer: output side", "producer: dgrad layers 9..2", "producer: layer 1 + input side", "-", "consumer u1a: waiting for full", "consumer u1a: wgrad work"]
+if os.environ.get("ST_DISABLE_FFMA2_AE_BWD") == "1":
+    names = ["sync0(prev store/step0)", "stage issue", "bwd-data mma", "cp.async wait+sync", "wgrad", "bias_grad", "sync+store_gz", "L1 epilogue+sync"]
 ncta = 148
 for ae in range(2):
     tot = sum(buf[8 * ae + i] for i in range(8))
     print("AE", ae, "total cycles/CTA/step", tot / ncta / n)
     for i in range(8):
-        print("   %-26s %9.0f cyc/CTA/step  %5.1f%%" % (names[i], buf[8 * ae + i] / ncta / n, 100.0 * buf[8 * ae + i] / max(tot, 1)))
+        print("   %-38s %9.0f cyc/CTA/step  %5.1f%%" % (names[i], buf[8 * ae + i] / ncta / n, 100.0 * buf[8 * ae + i] / max(tot, 1)))
 eng.lib.st_debug_ae_timing(eng.h, 0, None)
 
 fnames = ["input stage", "layers (FFMA2 + reload)", "record copies", "output stage"]

@@ -31,6 +31,7 @@ struct st_handle {
     float *yhat_ws = nullptr, *gy_ws = nullptr, *gmh_ws = nullptr;   // fused train step only
     float* knobs_ws = nullptr;    // copy of the forward's knobs (the SIMT backward recomputes the AE chain)
     float *ae_save_m = nullptr, *ae_save_p = nullptr;   // per-row activation records written by the tensor-core forward
+    float* gtrack_ws = nullptr;   // track gradients of the two autoencoders (FFMA2 backward -> ae_input_grad_kernel)
     float* tail_ws = nullptr;     // skip / residual gradient scratch of the tensor-core backward
     bool training = true;         // st_set_training: save activations in st_forward for a following st_backward
     bool have_saves = false;      // the last forward wrote ae_save_*
@@ -254,7 +255,7 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
 static void free_batch_buffers(st_handle* h) {
     float** bufs[] = {&h->xpad, &h->xpad_lo, &h->spec, &h->ri, &h->ri_lo, &h->fo, &h->mag_hat_ws, &h->phs_hat_ws, &h->gwave,
                       &h->gwave_lo, &h->g_ri, &h->g_spec, &h->g_spec_lo, &h->ae_part, &h->yhat_ws, &h->gy_ws, &h->gmh_ws,
-                      &h->knobs_ws, &h->ae_save_m, &h->ae_save_p, &h->tail_ws};
+                      &h->knobs_ws, &h->ae_save_m, &h->ae_save_p, &h->tail_ws, &h->gtrack_ws};
     for (float** b : bufs) {
         if (*b) cudaFree(*b);
         *b = nullptr;
@@ -312,6 +313,7 @@ static int ensure_workspace(st_handle* h, int B) {
         {&h->ae_save_m, (long)B * d.F * st_ae_mma_record_floats(d), false},
         {&h->ae_save_p, (long)B * d.F * st_ae_mma_record_floats(d), false},
         {&h->tail_ws, (long)B * d.OT * d.F, false},
+        {&h->gtrack_ws, 2L * B * d.T * d.F, false},
     };
     for (auto& r : req) {
         ST_CUDA_OK(cudaMalloc(r.p, r.n * sizeof(float)));
@@ -555,9 +557,9 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         AeParams pm, pp;
         split_params(params, pm, pp);
         int gr = 0;
-        if (h->have_saves && h->use_f2_bwd && !h->ae_timing)
+        if (h->have_saves && h->use_f2_bwd)
             gr = st_launch_ae_backward_f2(d, h->g, pm, pp, h->spec, B, h->ae_save_m, h->ae_save_p, h->mag_hat_ws, h->phs_hat_ws,
-                                          h->g_ri, g_mag_hat, g_mag, h->g_spec, h->g_spec_lo, h->ae_part, h->sm_count, s);
+                                          h->g_ri, g_mag_hat, g_mag, h->gtrack_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_timing, h->sm_count, s);
         if (gr == 0 && h->have_saves)
             gr = st_launch_ae_backward_mma(d, h->g, pm, pp, h->spec, B, h->ae_save_m, h->ae_save_p, h->mag_hat_ws, h->phs_hat_ws,
                                            h->g_ri, g_mag_hat, g_mag, h->tail_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_timing, h->sm_count, s);

@@ -159,8 +159,9 @@ int st_launch_ae_backward_mma(const StDims& d, const AeGeom& g, const AeParams& 
 // Returns the number of per-CTA partial-gradient vectors written (0: geometry not covered).
 int st_launch_ae_backward_f2(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, int B,
                              const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat,
-                             const float* g_ri, const float* g_mag_hat, const float* g_mag, float* g_spec, float* g_spec_lo,
-                             float* partials, int sm_count, cudaStream_t s);
+                             const float* g_ri, const float* g_mag_hat, const float* g_mag, float* g_track /*2*B*T*F*/, float* g_spec,
+                             float* g_spec_lo, float* partials, long long* timing /*nullable: 16 counters*/, int sm_count,
+                             cudaStream_t s);
 
 // st_loss_opt.cu
 void st_launch_loss(const StDims& d, const float* y_hat, const float* y, const float* mag_hat, const float* sbf,
