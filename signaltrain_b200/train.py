@@ -83,6 +83,64 @@ class FusedTrainer:
         for p in self.model.ordered_parameters():
             self.optimizer.state[p]["step"] = torch.tensor(float(self.optimizer._step))
 
+    def run_host_batches(self, batches, on_loss=None):
+        """Train on an iterable of pinned HOST batches (x, y, knobs) -- what `for x, y, knobs in dataloader` feeds the
+        reference's train_loop (train.py:104-106) with pin_memory=True.  The host->device copy of batch i+1 runs on a
+        copy stream while step i computes (two device buffers), and every step's loss is read back to the host one step
+        late (the reference reads it every 10th batch, train.py:125-129), so the host never waits for the step it has just
+        launched.  Returns the list of per-step losses (python floats); on_loss(i, value) is called as they arrive."""
+        dev = self.device
+        if getattr(self, "_feed", None) is None:             # created once: stream, events, pinned loss slots, device buffers
+            self._feed = {"stream": torch.cuda.Stream(device=dev), "bufs": [None, None],
+                          "ready": [torch.cuda.Event(), torch.cuda.Event()], "free": [torch.cuda.Event(), torch.cuda.Event()],
+                          "loss_host": [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)],
+                          "loss_ev": [torch.cuda.Event(), torch.cuda.Event()]}
+        fd = self._feed
+        copy_stream, bufs, ready, free = fd["stream"], fd["bufs"], fd["ready"], fd["free"]
+        loss_host, loss_ev = fd["loss_host"], fd["loss_ev"]
+        main = torch.cuda.current_stream(dev)
+        losses = []
+
+        def upload(slot, batch):
+            with torch.cuda.stream(copy_stream):
+                if bufs[slot] is None or any(b.shape != t.shape for b, t in zip(bufs[slot], batch)):
+                    bufs[slot] = tuple(torch.empty(t.shape, dtype=torch.float32, device=dev) for t in batch)
+                    copy_stream.wait_stream(main)
+                else:
+                    copy_stream.wait_event(free[slot])          # the step that read this buffer has finished
+                for dst, src in zip(bufs[slot], batch):
+                    dst.copy_(src, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def collect(i):
+            loss_ev[i % 2].synchronize()
+            v = float(loss_host[i % 2])
+            losses.append(v)
+            if on_loss is not None:
+                on_loss(i, v)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return losses
+        upload(0, nxt)
+        i = 0
+        while nxt is not None:
+            cur = i % 2
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(1 - cur, nxt)
+            main.wait_event(ready[cur])
+            loss = self.step(*bufs[cur])
+            free[cur].record(main)
+            loss_host[cur].copy_(loss, non_blocking=True)
+            loss_ev[cur].record(main)
+            if i > 0:
+                collect(i - 1)
+            i += 1
+        collect(i - 1)
+        return losses
+
 
 def eval_status_save(model, effect, epoch, epochs, lr, mom, device, dataloader_val, logfilename, first_time,
                      beta, vl_avg, out_checkpointname, parallel, optimizer, data_point, smoothed_loss, y_size, sr,

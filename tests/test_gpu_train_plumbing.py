@@ -47,3 +47,30 @@ def test_validation_forward_does_not_need_grad():
     y2, _, _ = model.forward(x, k)
     assert torch.equal(y1, y2) and y1.shape == (3, model.out_chunk_size)
     assert not y1.requires_grad and y2.requires_grad
+
+
+def test_host_batch_pipeline_matches_step_by_step():
+    """run_host_batches (H2D of batch i+1 overlapped with step i, loss read one step late) is the same arithmetic as
+    calling step() on device copies of the same batches: bit-identical losses and parameters."""
+    import signaltrain_b200 as st
+    from signaltrain_b200.train import FusedTrainer
+    lr, _ = st.learningrate.get_1cycle_schedule(1e-4, 200000, 1000, 200)
+    pool = st.data.make_pool(5 * 6, 8192, 2048, st.data.Compressor_4c(), 44100, seed=3)
+    host = [tuple(torch.from_numpy(a[i * 6:(i + 1) * 6]).pin_memory() for a in pool) for i in range(5)]
+    results = []
+    for mode in range(2):
+        torch.manual_seed(218)
+        model = st.nn_proc.st_model(1, 4, 4).cuda()
+        tr = FusedTrainer(model, lr)
+        if mode == 0:
+            losses = [float(tr.step(*(t.cuda() for t in b)).item()) for b in host]
+        else:
+            seen = []
+            losses = tr.run_host_batches(host, on_loss=lambda i, v: seen.append((i, v)))
+            assert [i for i, _ in seen] == list(range(5)) and [v for _, v in seen] == losses
+        torch.cuda.synchronize()
+        results.append((losses, [p.detach().clone() for p in model.parameters()]))
+    assert results[0][0] == results[1][0]
+    for a, b in zip(results[0][1], results[1][1]):
+        assert torch.equal(a, b)
+    assert tr.run_host_batches([]) == []
