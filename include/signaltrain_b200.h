@@ -77,6 +77,18 @@ int st_analysis(st_handle* h, const float* x, const float* w_real, const float* 
 int st_synthesis(st_handle* h, const float* real, const float* imag, const float* w_real, const float* w_imag, int batch,
                  float* wave, void* stream);
 
+/* DCT / MDCT front-end variant, signaltrain/cls_fe_dct_bases.py (the reference ships it but wires it to nothing):
+ *   Analysis.forward (:128-135): Conv1d(1 -> ft_size, kernel w_size, stride hop, padding ft_size, bias) then transpose:
+ *     x (B, chunk) -> out (B, frames, ft_size), frames = (chunk + 2 ft_size - w_size) / hop + 1;  w (ft_size, 1, w_size), bias (ft_size)
+ *   Synthesis.forward (:173-179): ConvTranspose1d(ft_size -> 1, kernel w_size, stride hop) trimmed by ft_size on both sides:
+ *     x_ft (B, frames, ft_size) -> wave (B, (frames - 1) hop + w_size - 2 ft_size);  w (ft_size, 1, w_size)
+ *   (tied_transform :36-54 is st_dct_synthesis with the analysis weights.)  Forward only; geometry is per call, the handle
+ *   supplies the device, the GEMM engine and a grow-only workspace. */
+int st_dct_analysis(st_handle* h, const float* x, const float* w, const float* bias, int batch, int chunk, int ft_size,
+                    int w_size, int hop, float* out, void* stream);
+int st_dct_synthesis(st_handle* h, const float* x_ft, const float* w, int batch, int frames, int ft_size, int w_size,
+                     int hop, float* wave, void* stream);
+
 /* st_model.forward(x, knobs, return_acts): nn_proc.py:392 -> AsymMPAEC.forward :305-340.
  *   x (B,C)  knobs (B,K)  ->  y_hat (B,L) [= 2*y_hat of :340]  mag (B,T,F)  mag_hat (B,OT,F)
  *   acts: NULL, or ST_NUM_ACTS device pointers receiving the reference's layer_acts (:311-335), each

@@ -219,6 +219,45 @@ def forward(d: Dims, P, x, knobs, dtype=np.float64, keep=True):
 # --------------------------------------------------------------------------------------------
 # loss                                                         loss_functions.py:9-10,22-43
 # --------------------------------------------------------------------------------------------
+# ---- DCT / MDCT front-end variant (signaltrain/cls_fe_dct_bases.py; shipped by the reference, wired to nothing) ----------
+def dct_core_modulation(freq_subbands, window_size):
+    """cls_fe_dct_bases.py:57-97 ('scott' method :85-90): w[n] cos(pi/M (k+1/2)(n+1/2+M/2)) sqrt(2/M), w = scipy.signal.cosine
+    (= sin(pi (n + 1/2) / window_size)), cast to float32."""
+    n = np.arange(window_size)
+    w = np.sin(np.pi * (n + 0.5) / window_size)
+    kvec = np.arange(0, freq_subbands) + 0.5
+    nvec = n + 0.5 + freq_subbands / 2
+    return (w * np.cos(np.pi / freq_subbands * kvec[np.newaxis].T * nvec) * np.sqrt(2. / freq_subbands)).astype(np.float32)
+
+
+def dct_analysis_forward(x, W, bias, hop, dtype=np.float64):
+    """Analysis.forward, cls_fe_dct_bases.py:128-135: Conv1d(1 -> sz, kernel wsz, stride hop, padding sz, bias) (:116-117),
+    transposed to (B, frames, sz).  W (sz, wsz), bias (sz)."""
+    W = np.asarray(W, dtype).reshape(W.shape[0], -1)
+    sz, wsz = W.shape
+    x = np.asarray(x, dtype)
+    B, C = x.shape
+    xp = np.zeros((B, C + 2 * sz), dtype)
+    xp[:, sz:sz + C] = x
+    nf = (C + 2 * sz - wsz) // hop + 1
+    frames = np.stack([xp[:, t * hop:t * hop + wsz] for t in range(nf)], axis=1)          # (B, nf, wsz)
+    return frames @ W.T + np.asarray(bias, dtype)
+
+
+def dct_synthesis_forward(x_ft, W, hop, dtype=np.float64):
+    """Synthesis.forward, cls_fe_dct_bases.py:173-179: ConvTranspose1d(sz -> 1, kernel wsz, stride hop) (:156-157), sz samples
+    trimmed on both sides.  Returns (B, 1, C) like the reference.  tied_transform (:36-54) is this with the analysis weights."""
+    W = np.asarray(W, dtype).reshape(W.shape[0], -1)
+    sz, wsz = W.shape
+    x_ft = np.asarray(x_ft, dtype)
+    B, nf, _ = x_ft.shape
+    out = np.zeros((B, (nf - 1) * hop + wsz), dtype)
+    fo = x_ft @ W                                                                         # (B, nf, wsz)
+    for t in range(nf):
+        out[:, t * hop:t * hop + wsz] += fo[:, t]
+    return out[:, None, sz:out.shape[1] - sz]
+
+
 def scale_by_freq(F, dtype=np.float32):
     """train.py:115-117: exp(7/F * arange(F)) (computed in float32 by the reference)."""
     return np.exp(np.float32(7.0 / F) * np.arange(F, dtype=np.float32)).astype(dtype)

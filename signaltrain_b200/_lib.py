@@ -36,6 +36,10 @@ _SIGNATURES = {
     "st_analysis": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_void_p]),
     "st_synthesis": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, c_float_p,
                                     ctypes.c_void_p]),
+    "st_dct_analysis": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "st_dct_synthesis": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "st_forward": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p, c_float_p, c_float_p,
                                   c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
     "st_loss": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_float, ctypes.c_int,

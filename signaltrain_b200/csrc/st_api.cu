@@ -31,6 +31,8 @@ struct st_handle {
     float *yhat_ws = nullptr, *gy_ws = nullptr, *gmh_ws = nullptr;   // fused train step only
     float* knobs_ws = nullptr;    // copy of the forward's knobs (the SIMT backward recomputes the AE chain)
     float *ae_save_m = nullptr, *ae_save_p = nullptr;   // per-row activation records written by the tensor-core forward
+    float* dct_ws = nullptr;      // workspace of the DCT / MDCT front-end variant (st_dct_analysis / st_dct_synthesis)
+    long dct_ws_floats = 0;
     float* gtrack_ws = nullptr;   // track gradients of the two autoencoders (FFMA2 backward -> ae_input_grad_kernel)
     float* tail_ws = nullptr;     // skip / residual gradient scratch of the tensor-core backward
     bool training = true;         // st_set_training: save activations in st_forward for a following st_backward
@@ -267,6 +269,7 @@ extern "C" void st_destroy(st_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     free_batch_buffers(h);
+    if (h->dct_ws) cudaFree(h->dct_ws);
     if (h->small) cudaFree(h->small);
     if (h->counters) cudaFree(h->counters);
     if (h->wcat) cudaFree(h->wcat);
@@ -797,6 +800,83 @@ extern "C" int st_debug_ae_timing(st_handle* h, int on, long long* out_host) {
         ST_CUDA_OK(cudaMemset(h->ae_timing, 0, 24 * sizeof(long long)));
     }
     if (!on && h->ae_timing) { cudaFree(h->ae_timing); h->ae_timing = nullptr; }
+    return 0;
+}
+
+// ---- DCT / MDCT front-end variant (cls_fe_dct_bases.py): same contraction + overlap-add machinery, other sizes ------
+static int dct_workspace(st_handle* h, long floats) {
+    ST_CUDA_OK(cudaSetDevice(h->device));
+    if (floats <= h->dct_ws_floats) return 0;
+    ST_CUDA_OK(cudaDeviceSynchronize());
+    if (h->dct_ws) cudaFree(h->dct_ws);
+    h->dct_ws = nullptr;
+    h->dct_ws_floats = 0;
+    ST_CUDA_OK(cudaMalloc(&h->dct_ws, floats * sizeof(float)));
+    h->dct_ws_floats = floats;
+    return 0;
+}
+static long up4(long n) { return (n + 3) / 4 * 4; }
+
+extern "C" int st_dct_analysis(st_handle* h, const float* x, const float* w, const float* bias, int batch, int chunk, int ft_size,
+                               int w_size, int hop, float* out, void* stream) {
+    if (!h) return 1;
+    if (!x || !w || !bias || !out) return st_fail_msg(h, "st_dct_analysis: null argument");
+    if (batch <= 0 || chunk <= 0 || ft_size <= 0 || w_size <= 0 || hop <= 0 || (chunk & 3) || (ft_size & 3) || (w_size & 31) || (hop & 3))
+        return st_fail_msg(h, "st_dct_analysis: sizes must be positive, chunk / ft_size / hop multiples of 4, w_size of 32");
+    if (chunk + 2 * ft_size < w_size) return st_fail_msg(h, "st_dct_analysis: chunk %d too short for a %d-tap window", chunk, w_size);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = batch, C = chunk, sz = ft_size, wsz = w_size;
+    const int nf = (C + 2 * sz - wsz) / hop + 1;                 // Conv1d output length (padding = sz, cls_fe_dct_bases.py:116)
+    const int Tp = (C + 2 * sz + hop - 1) / hop;                 // uniform-stride rows per window (>= nf; extras are dummies)
+    const long Sx = (long)Tp * hop, MT = (long)B * Tp;
+    const long n_x = up4(B * Sx + wsz), n_w = (long)sz * wsz, n_tmp = MT * sz;
+    if (dct_workspace(h, 2 * n_x + 2 * n_w + n_tmp)) return 1;
+    float *xh = h->dct_ws, *xl = xh + n_x, *wh = xl + n_x, *wl = wh + n_w, *tmp = wl + n_w;
+    ST_CUDA_OK(cudaMemsetAsync(xh, 0, 2 * n_x * sizeof(float), s));
+    st_launch_pad_split(x, xh, xl, B, C, sz, (int)Sx, 1.0f, s);
+    st_launch_pad_split(w, wh, wl, sz, wsz, 0, wsz, 1.0f, s);
+    int r = -1;
+    if (h->use_tc) {
+        TcOperand A{xh, xl, MT, wsz, hop}, W{wh, wl, sz, wsz, wsz};
+        r = st_launch_gemm_tc(false, false, A, W, tmp, sz, (int)MT, sz, wsz, 1, 0, true, h->sm_count, s);
+    }
+    if (r < 0) {
+        GemmOperand A{xh, xl, hop}, W{wh, wl, wsz};
+        st_launch_gemm(true, true, A, W, tmp, sz, (int)MT, sz, wsz, 1, 0, s);
+    }
+    st_launch_dct_bias_unpack(tmp, bias, B, nf, Tp, sz, out, s);
+    h->launches += 4;
+    ST_LAUNCH_OK(h);
+    return 0;
+}
+
+extern "C" int st_dct_synthesis(st_handle* h, const float* x_ft, const float* w, int batch, int frames, int ft_size, int w_size,
+                                int hop, float* wave, void* stream) {
+    if (!h) return 1;
+    if (!x_ft || !w || !wave) return st_fail_msg(h, "st_dct_synthesis: null argument");
+    if (batch <= 0 || frames <= 0 || ft_size <= 0 || w_size <= 0 || hop <= 0 || (ft_size & 31) || (w_size & 3) || (hop & 3))
+        return st_fail_msg(h, "st_dct_synthesis: sizes must be positive, ft_size a multiple of 32, w_size / hop of 4");
+    const int B = batch, nf = frames, sz = ft_size, wsz = w_size;
+    const int C = (nf - 1) * hop + wsz - 2 * sz;                 // ConvTranspose1d length minus the trim (cls_fe_dct_bases.py:174-176)
+    if (C <= 0) return st_fail_msg(h, "st_dct_synthesis: %d frames are too few for ft_size=%d", nf, sz);
+    cudaStream_t s = (cudaStream_t)stream;
+    const long M = (long)B * nf, n_a = M * sz, n_w = (long)sz * wsz, n_fo = M * wsz;
+    if (dct_workspace(h, 2 * n_a + 2 * n_w + n_fo)) return 1;
+    float *ah = h->dct_ws, *al = ah + n_a, *wh = al + n_a, *wl = wh + n_w, *fo = wl + n_w;
+    st_launch_pad_split(x_ft, ah, al, (int)M, sz, 0, sz, 1.0f, s);
+    st_launch_pad_split(w, wh, wl, sz, wsz, 0, wsz, 1.0f, s);
+    int r = -1;
+    if (h->use_tc) {
+        TcOperand A{ah, al, M, sz, sz}, S{wh, wl, sz, wsz, wsz};
+        r = st_launch_gemm_tc(false, true, A, S, fo, wsz, (int)M, wsz, sz, 1, 0, true, h->sm_count, s);
+    }
+    if (r < 0) {
+        GemmOperand A{ah, al, sz}, S{wh, wl, wsz};
+        st_launch_gemm(true, false, A, S, fo, wsz, (int)M, wsz, sz, 1, 0, s);
+    }
+    st_launch_dct_overlap_add(fo, B, nf, sz, wsz, hop, C, wave, s);
+    h->launches += 4;
+    ST_LAUNCH_OK(h);
     return 0;
 }
 

@@ -237,6 +237,42 @@ void st_launch_init_frontend(const StDims& d, float* Wr, float* Wi, float* Sr, f
                                                                         Sr, Si);
 }
 
+// ---- DCT / MDCT front-end variant (cls_fe_dct_bases.py) -------------------------------------------------------------
+// Analysis epilogue: out[b, t, k] = tmp[(b Tp + t), k] + bias[k], t < nf  (Conv1d bias, cls_fe_dct_bases.py:116-117, then
+// the transpose of :134)
+__global__ void dct_bias_unpack_kernel(const float* __restrict__ tmp, const float* __restrict__ bias, int B, int nf, int Tp, int sz,
+                                       float* __restrict__ out) {
+    const long total = (long)B * nf * (sz >> 2);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int k4 = (int)(i % (sz >> 2)) << 2;
+        const long bt = i / (sz >> 2);
+        const int t = (int)(bt % nf), b = (int)(bt / nf);
+        float4 v = ld4(tmp + ((long)b * Tp + t) * sz + k4);
+        const float4 bb = ld4(bias + k4);
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        st4(out + bt * sz + k4, v);
+    }
+}
+// Synthesis overlap-add + trim: ConvTranspose1d(stride hop) output position p = m + sz receives frame t's tap p - t hop
+// (cls_fe_dct_bases.py:156-157, trimmed by sz on both sides :174-176).  wave (B, C).
+__global__ void dct_overlap_add_kernel(const float* __restrict__ fo, int B, int nf, int sz, int wsz, int hop, int C, float* __restrict__ wave) {
+    const long total = (long)B * C;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int m = (int)(i % C), b = (int)(i / C);
+        const int p = m + sz;
+        const int t_hi = min(p / hop, nf - 1), t_lo = max(0, (p - wsz) / hop + ((p - wsz) >= 0 ? 1 : 0));
+        float acc = 0.f;
+        for (int t = t_lo; t <= t_hi; ++t) acc += fo[((long)b * nf + t) * wsz + (p - t * hop)];
+        wave[i] = acc;
+    }
+}
+void st_launch_dct_bias_unpack(const float* tmp, const float* bias, int B, int nf, int Tp, int sz, float* out, cudaStream_t s) {
+    dct_bias_unpack_kernel<<<grid_for((long)B * nf * (sz >> 2), 256), 256, 0, s>>>(tmp, bias, B, nf, Tp, sz, out);
+}
+void st_launch_dct_overlap_add(const float* fo, int B, int nf, int sz, int wsz, int hop, int C, float* wave, cudaStream_t s) {
+    dct_overlap_add_kernel<<<grid_for((long)B * C, 256), 256, 0, s>>>(fo, B, nf, sz, wsz, hop, C, wave);
+}
+
 void st_launch_unpack_spec(const StDims& d, const float* spec, int B, float* re, float* im, cudaStream_t s) {
     unpack_spec_kernel<<<grid_for((long)B * d.T * d.F, 256), 256, 0, s>>>(d, spec, B, re, im);
 }

@@ -154,6 +154,29 @@ class Engine:
                  "st_synthesis")
         return wave
 
+    def dct_analysis(self, x, weight, bias, ft_size, w_size, hop):
+        """cls_fe_dct_bases.Analysis.forward: x (B, C) -> (B, frames, ft_size)."""
+        B, C = x.shape
+        _check(x, "wave_form", (B, C), self.device)
+        _check(weight, "conv_analysis.weight", (ft_size, 1, w_size), self.device)
+        _check(bias, "conv_analysis.bias", (ft_size,), self.device)
+        nf = (C + 2 * ft_size - w_size) // hop + 1
+        out = torch.empty((B, nf, ft_size), device=self.device, dtype=torch.float32)
+        self._ok(self.lib.st_dct_analysis(self.h, _ptr(x), _ptr(weight), _ptr(bias), B, C, ft_size, w_size, hop, _ptr(out),
+                                          self._stream()), "st_dct_analysis")
+        return out
+
+    def dct_synthesis(self, x_ft, weight, ft_size, w_size, hop):
+        """cls_fe_dct_bases.Synthesis.forward: x_ft (B, frames, ft_size) -> (B, 1, (frames - 1) hop + w_size - 2 ft_size)."""
+        B, nf, _ = x_ft.shape
+        _check(x_ft, "x_ft", (B, nf, ft_size), self.device)
+        _check(weight, "conv_synthesis.weight", (ft_size, 1, w_size), self.device)
+        C = (nf - 1) * hop + w_size - 2 * ft_size
+        wave = torch.empty((B, 1, max(C, 1)), device=self.device, dtype=torch.float32)
+        self._ok(self.lib.st_dct_synthesis(self.h, _ptr(x_ft), _ptr(weight), B, nf, ft_size, w_size, hop, _ptr(wave), self._stream()),
+                 "st_dct_synthesis")
+        return wave
+
     def set_training(self, on):
         self._ok(self.lib.st_set_training(self.h, int(bool(on))), "st_set_training")
 

@@ -168,7 +168,42 @@ class TwoKnobComp(st.audio.Compressor_4c):
             self.knob_ranges = saved
 
 
+def make_dct_case(name, ft_size, w_size, hop, chunk, B, seed=218):
+    """cls_fe_dct_bases.Analysis / Synthesis / tied_transform.  The reference imports this module nowhere and its
+    Analysis.forward begins with an unconditional numpy -> .cuda() (:130), so the golden applies the REST of that forward --
+    the reference's own conv_analysis layer, viewed and transposed exactly as :131-134 do -- to a CPU tensor; Synthesis.forward
+    and tied_transform run unmodified.  Weights: the reference's own initialize() (bias = Conv1d's default random init under the
+    seed) plus a deterministic perturbation, so the transforms are general matrices rather than the analytic cosine basis."""
+    import importlib
+    dct = importlib.import_module("signaltrain.cls_fe_dct_bases")
+    torch.manual_seed(seed)
+    ana = dct.Analysis(ft_size=ft_size, w_size=w_size, hop_size=hop)
+    syn = dct.Synthesis(ft_size=ft_size, w_size=w_size, hop_size=hop)
+    out = {"ft_size": ft_size, "w_size": w_size, "hop": hop, "chunk": chunk}
+    out["core_rows"] = np.array([0, 1, 7, ft_size // 2, ft_size - 1])
+    out["core_modulation_rows"] = dct.core_modulation(ft_size, w_size)[out["core_rows"]]
+    out["bias"] = ana.conv_analysis.bias.detach().numpy().copy()
+    with torch.no_grad():
+        ana.conv_analysis.weight.add_(torch.from_numpy(perturbation(tuple(ana.conv_analysis.weight.shape), 777, 1e-3)))
+        syn.conv_synthesis.weight.add_(torch.from_numpy(perturbation(tuple(syn.conv_synthesis.weight.shape), 778, 1e-3)))
+    rng = np.random.RandomState(seed)
+    t = np.arange(chunk) / 44100.0
+    x = (0.5 * np.sin(2 * np.pi * rng.uniform(60, 4000, (B, 1)) * t) + 0.1 * rng.standard_normal((B, chunk))).astype(np.float32)
+    out["x"] = x
+    out["pert_seeds"] = np.array([777, 778])
+    with torch.no_grad():
+        wave = torch.from_numpy(x)
+        x_ft = torch.transpose(ana.conv_analysis(wave.view(B, 1, chunk)), 2, 1)          # cls_fe_dct_bases.py:131-134
+        out["x_ft"] = x_ft.numpy().copy()
+        out["wave"] = syn.forward(x_ft).numpy().copy()                                    # :173-179, unmodified
+        out["tied"] = dct.tied_transform(ana, x_ft, hop).numpy().copy()                   # :36-54, unmodified
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
+
+
 def main():
+    make_dct_case("dct_ft256_w512_h256_c4096_b3", 256, 512, 256, 4096, 3)
+    make_dct_case("dct_ft1024_w2048_h1024_c8192_b2", 1024, 2048, 1024, 8192, 2)
     make_case("comp4c_c8192_k4_b3", 1, 4, st.audio.Compressor_4c(), B=3)
     make_case("comp2k_c16384_k2_b2", 2, 4, TwoKnobComp(), B=2)
     make_case("denoise_c8192_k1_b2", 1, 4, st.audio.Denoise(), B=2)
