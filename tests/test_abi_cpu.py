@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -64,3 +66,10 @@ def test_model_surface_matches_reference_contract():
         assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(s)) for k, s in O.param_order(d)]
         assert m.mpaec.dft_analysis.conv_analysis_real.weight.shape == (1024, 1, 1024)
         assert hasattr(m, "clip_grad_norm_") and hasattr(m.mpaec, "clip_grad_norm_")
+
+
+def test_sliding_window_mirror():
+    """audio.py:23-49, the reference's own docstring example."""
+    from signaltrain_b200.predict_long import sliding_window
+    np.testing.assert_array_equal(sliding_window(np.arange(10), 5, overlap=2), [[0, 1, 2, 3, 4], [3, 4, 5, 6, 7], [6, 7, 8, 9, 0]])
+    assert sliding_window(np.arange(8), 4, overlap=0).shape == (2, 4)

@@ -74,3 +74,42 @@ def test_host_batch_pipeline_matches_step_by_step():
     for a, b in zip(results[0][1], results[1][1]):
         assert torch.equal(a, b)
     assert tr.run_host_batches([]) == []
+
+
+def test_predict_long_matches_oracle_windows():
+    """utils/predict_long.py:30-79: a long signal through overlapping windows, forward only; output bookkeeping as the reference."""
+    import signaltrain_b200 as st
+    from oracle import st_oracle as O
+    from signaltrain_b200.predict_long import predict_long, sliding_window
+    torch.manual_seed(218)
+    model = st.nn_proc.st_model(1, 4, 4).cuda()
+    d = O.model_dims(1, 4, 4)
+    n = 8192 + 5 * 2048 + 777                                     # not a whole number of hops: exercises the zero padding
+    rng = np.random.RandomState(5)
+    sig = (0.4 * np.sin(2 * np.pi * 440 * np.arange(n) / 44100) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    knobs = np.array([0.1, -0.3, 0.25, 0.4], dtype=np.float32)
+    y = predict_long(sig, knobs, model, model.in_chunk_size, model.out_chunk_size, device="cuda:0", batch_size=4)
+    assert y.dtype == np.float64
+    win = sliding_window(sig, 8192, overlap=8192 - 2048)
+    P = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    fw = O.forward(d, P, np.ascontiguousarray(win), np.tile(knobs, (win.shape[0], 1)), dtype=np.float64)
+    ref = fw["y_hat"].reshape(-1)
+    unique = 8192 + (win.shape[0] - 1) * 2048
+    ref = ref[:-(unique - n)] if unique > n else ref
+    assert y.shape == ref.shape
+    assert np.abs(y - ref).max() < 1e-5
+    assert model.training                                          # restored
+
+
+def test_lrfind_runs_the_train_step_through_the_module_api():
+    """utils/lr_finder.py:18-55: geometric lr sweep, three batches per value; the loss moves and stays finite."""
+    import signaltrain_b200 as st
+    from signaltrain_b200.lr_finder import lrfind
+    torch.manual_seed(218)
+    model = st.nn_proc.st_model(1, 4, 4).cuda()
+    opt = st.optim.Adam(model, lr=1e-6)
+    pool = st.data.make_pool(4 * 9, 8192, 2048, st.data.Compressor_4c(), 44100, seed=11)
+    batches = [tuple(torch.from_numpy(a[i * 4:(i + 1) * 4]) for a in pool) for i in range(9)]
+    lrs, losses = lrfind(model, batches, opt, st.loss_functions.calc_loss, start=1e-6, stop=1e-3, num_lrs=3)
+    assert len(lrs) == len(losses) == 9 and lrs[0] == lrs[2] and lrs[3] > lrs[2] and np.isclose(lrs[-1], 1e-3)
+    assert np.isfinite(losses).all() and len(set(losses)) > 1
