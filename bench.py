@@ -39,6 +39,26 @@ def measured_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback (B200_PROFILING.md)")
 
 
+def ncu_dram_traffic(stage):
+    """dram__bytes_read + dram__bytes_write of the stage's kernels from the committed `ncu --set full` summary (bytes per
+    stage = sum over its launches), or (None, why)."""
+    path = os.path.join(ROOT, "profiles", "r01_v6_ae_f2_ncu_full_summary.csv")
+    want = {"ae_backward": "ae_bwd_f2_kernel", "ae_forward": "ae_fwd_f2_kernel"}.get(stage)
+    if want is None or not os.path.exists(path):
+        return None, "no ncu --set full capture of this kernel committed"
+    import csv
+    rows = list(csv.reader(open(path)))
+    cols = [i for i, n in enumerate(rows[0]) if n.startswith(want)]
+    tot = 0.0
+    for r in rows[1:]:
+        if r[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += sum(float(r[i]) for i in cols) * 1e6
+    n = len(cols)
+    if stage == "ae_forward":          # the capture holds one of the stage's two launches
+        tot, n = 2 * tot / max(n, 1), 2
+    return tot, f"profiles/r01_v6_ae_f2_ncu_full_summary.csv ({n} launches of {want}, B=200)"
+
+
 def stage_work(d, B):
     """Algorithmic FLOPs / bytes per launch of each stage, SURVEY.md section 8(d) (fp32 words)."""
     BTF, BOF, W = B * d.T * d.F, B * d.OT * d.F, 2 * d.F * d.N
@@ -253,11 +273,21 @@ def run_native(args):
         achieved, peak, unit = w["flops"] / dur_s / 1e12, peaks["bf16_sustained"], "TFLOP/s"
     else:
         achieved, peak, unit = w["bytes"] / dur_s / 1e9, peaks["hbm"], "GB/s"
+    traffic, traffic_src = ncu_dram_traffic(top)
     roofline = {"kernel": top, "bound": w["bound"], "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                "traffic": None, "peak_source": peaks["src"], "kernel_ms": stages[top][0],
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["src"], "kernel_ms": stages[top][0],
                 "share_of_step": stages[top][0] / step_sum if step_sum else None,
                 "algorithmic_bytes": w["bytes"], "algorithmic_flops": w["flops"],
                 "stages_ms": {k: round(v[0], 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])}}
+    if top in ("ae_backward", "ae_forward"):
+        # the autoencoder chains run on the packed-fp32 FMA pipe by design (exact fp32): besides the
+        # HBM figure the contract asks for, state how far they are from the CUDA-core peak (no recompute: 2/3 of the flops)
+        useful = w["flops"] * (2.0 / 3.0 if top == "ae_backward" else 1.0)
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        roofline["fp32_fma"] = {"achieved_tflops": useful / dur_s / 1e12, "peak_tflops": fp32_peak,
+                                "frac": useful / dur_s / 1e12 / fp32_peak,
+                                "note": "148 SMs x 128 FMA lanes x 2 x 1.965 GHz; ncu: FMA pipe 32 %, shared-memory data pipe 59 % "
+                                        "(profiles/r01_v6_ae_f2_ncu_full_summary.csv)"}
     # CPU baseline: the oracle port on this box's host cores, bounded sample
     cores = os.cpu_count() or 1
     cpu_fps, cpu_ms = (None, None)
