@@ -89,6 +89,17 @@ int st_dct_analysis(st_handle* h, const float* x, const float* w, const float* b
 int st_dct_synthesis(st_handle* h, const float* x_ft, const float* w, int batch, int frames, int ft_size, int w_size,
                      int hop, float* wave, void* stream);
 
+/* Data step in front of the train step (the reference does it on CPU workers).
+ *   st_compressor_4c: audio.compressor_4controls (audio.py:380-426) as Compressor_4c.go_wc applies it (:497-498), batched:
+ *     x (batch, n) float32, knobs_wc (batch, 4) float64 world coordinates [threshold dB, ratio, attack s, release s]
+ *     -> y (batch, n) float32 (the reference's float64 result after the caller's .float(), train.py:120).
+ *   st_crop_windows: AudioFileDataSet.get_single_chunk's crop (datasets.py:236-241) and do_augment's polarity flip (:21-30)
+ *     from a device-resident corpus: window b is corpus_x[offsets[b] : +chunk] and the last y_size samples of the same
+ *     span of corpus_y, both times signs[b] (NULL: no flip).  offsets is a HOST array (the host RNG picks them). */
+int st_compressor_4c(st_handle* h, const float* x, const double* knobs_wc, int batch, int n, double sr, float* y, void* stream);
+int st_crop_windows(st_handle* h, const float* corpus_x, const float* corpus_y, long corpus_len, const long* offsets_host,
+                    const float* signs, int batch, int chunk, int y_size, float* x, float* y, void* stream);
+
 /* st_model.forward(x, knobs, return_acts): nn_proc.py:392 -> AsymMPAEC.forward :305-340.
  *   x (B,C)  knobs (B,K)  ->  y_hat (B,L) [= 2*y_hat of :340]  mag (B,T,F)  mag_hat (B,OT,F)
  *   acts: NULL, or ST_NUM_ACTS device pointers receiving the reference's layer_acts (:311-335), each

@@ -219,6 +219,37 @@ def forward(d: Dims, P, x, knobs, dtype=np.float64, keep=True):
 # --------------------------------------------------------------------------------------------
 # loss                                                         loss_functions.py:9-10,22-43
 # --------------------------------------------------------------------------------------------
+# ---- data step in front of the path: the comp_4c target generator and the window cropper ------------
+def compressor_4controls(x, thresh=-24.0, ratio=2.0, attackTime=0.01, releaseTime=0.01, sr=44100.0):
+    """audio.py:380-426, batched over the leading axis, with the dtypes the reference's numba-compiled function produces for a
+    float32 x: level detection in float64 (x_uni + 1e-8 promotes, :401-402), the static gain change and its smoothed copy
+    stored in float32 arrays (:396, :409) but updated with float64 arithmetic (:414-418), 10^(lin_A/20) * x in float64
+    (:420-422).  x (B, n) float32; scalars or (B,) arrays for the knobs.  Returns float64 (B, n)."""
+    x = np.asarray(x, np.float32)
+    B, N = x.shape
+    col = lambda v: np.broadcast_to(np.asarray(v, np.float64), (B,)).reshape(B, 1)
+    thresh, ratio = col(thresh), col(ratio)
+    aA = np.exp(-np.log(9) / (sr * col(attackTime)))[:, 0]
+    aR = np.exp(-np.log(9) / (sr * col(releaseTime)))[:, 0]
+    xd = x.astype(np.float64)
+    x_dB = np.maximum(20 * np.log10(np.abs(xd) + 1e-8), -96)
+    g = np.where(x_dB > thresh, thresh + (x_dB - thresh) / ratio - x_dB, 0.0).astype(np.float32)
+    lin = np.zeros((B, N), np.float32)
+    for n in range(1, N):
+        prev, gn = lin[:, n - 1], g[:, n]
+        a = np.where(gn < prev, aA, aR)
+        lin[:, n] = ((1 - a) * gn.astype(np.float64) + a * prev.astype(np.float64)).astype(np.float32)
+    return np.power(10.0, lin.astype(np.float64) / 20) * xd
+
+
+def crop_windows(corpus_x, corpus_y, offsets, signs, chunk, y_size):
+    """datasets.py:236-241 (random chunk of a preloaded pair, last y_size samples of the target) and :21-30 (do_augment's
+    polarity flip), for given start offsets and signs."""
+    x = np.stack([corpus_x[o:o + chunk] for o in offsets]) * np.asarray(signs)[:, None]
+    y = np.stack([corpus_y[o + chunk - y_size:o + chunk] for o in offsets]) * np.asarray(signs)[:, None]
+    return x.astype(np.float32), y.astype(np.float32)
+
+
 # ---- DCT / MDCT front-end variant (signaltrain/cls_fe_dct_bases.py; shipped by the reference, wired to nothing) ----------
 def dct_core_modulation(freq_subbands, window_size):
     """cls_fe_dct_bases.py:57-97 ('scott' method :85-90): w[n] cos(pi/M (k+1/2)(n+1/2+M/2)) sqrt(2/M), w = scipy.signal.cosine

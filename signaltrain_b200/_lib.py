@@ -40,6 +40,10 @@ _SIGNATURES = {
                                        ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "st_dct_synthesis": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "st_compressor_4c": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_float_p,
+                                        ctypes.c_void_p]),
+    "st_crop_windows": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_long, ctypes.c_void_p, c_float_p, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, c_float_p, c_float_p, ctypes.c_void_p]),
     "st_forward": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p, c_float_p, c_float_p,
                                   c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
     "st_loss": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_float, ctypes.c_int,

@@ -880,6 +880,39 @@ extern "C" int st_dct_synthesis(st_handle* h, const float* x_ft, const float* w,
     return 0;
 }
 
+// ---- data step in front of the path -------------------------------------------------------
+extern "C" int st_compressor_4c(st_handle* h, const float* x, const double* knobs_wc, int batch, int n, double sr, float* y, void* stream) {
+    if (!h) return 1;
+    if (!x || !knobs_wc || !y) return st_fail_msg(h, "st_compressor_4c: null argument");
+    if (batch <= 0 || n <= 0 || !(sr > 0)) return st_fail_msg(h, "st_compressor_4c: batch, n and sr must be positive");
+    if (dct_workspace(h, (long)batch * n)) return 1;
+    st_launch_compressor_4c(x, knobs_wc, batch, n, sr, h->dct_ws, y, (cudaStream_t)stream);
+    h->launches += 3;
+    ST_LAUNCH_OK(h);
+    return 0;
+}
+
+extern "C" int st_crop_windows(st_handle* h, const float* corpus_x, const float* corpus_y, long corpus_len, const long* offsets_host,
+                               const float* signs, int batch, int chunk, int y_size, float* x, float* y, void* stream) {
+    if (!h) return 1;
+    if (!corpus_x || !corpus_y || !offsets_host || !x || !y) return st_fail_msg(h, "st_crop_windows: null argument");
+    if (batch <= 0 || chunk <= 0 || y_size <= 0 || y_size > chunk) return st_fail_msg(h, "st_crop_windows: need 0 < y_size <= chunk");
+    for (int b = 0; b < batch; ++b)
+        if (offsets_host[b] < 0 || offsets_host[b] + chunk > corpus_len)
+            return st_fail_msg(h, "st_crop_windows: window %d (offset %ld, chunk %d) leaves the corpus of %ld samples", b, offsets_host[b],
+                               chunk, corpus_len);
+    ST_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const long need = ((long)batch * sizeof(long) + sizeof(float) - 1) / sizeof(float);
+    if (dct_workspace(h, need)) return 1;
+    long* off_dev = reinterpret_cast<long*>(h->dct_ws);
+    ST_CUDA_OK(cudaMemcpyAsync(off_dev, offsets_host, (size_t)batch * sizeof(long), cudaMemcpyHostToDevice, s));
+    st_launch_crop_windows(corpus_x, corpus_y, off_dev, signs, batch, chunk, y_size, x, y, s);
+    h->launches += 1;
+    ST_LAUNCH_OK(h);
+    return 0;
+}
+
 extern "C" int st_analysis(st_handle* h, const float* x, const float* w_real, const float* w_imag, int batch, float* an_real,
                            float* an_imag, void* stream) {
     if (!h) return 1;

@@ -165,6 +165,11 @@ int st_launch_ae_backward_f2(const StDims& d, const AeGeom& g, const AeParams& p
                              float* g_spec_lo, float* partials, long long* timing /*nullable: 16 counters*/, int sm_count,
                              cudaStream_t s);
 
+// st_data.cu
+void st_launch_compressor_4c(const float* x, const double* knobs_wc, int B, int n, double sr, float* scratch, float* y, cudaStream_t s);
+void st_launch_crop_windows(const float* cx, const float* cy, const long* off, const float* sign, int B, int C, int L, float* ox,
+                            float* oy, cudaStream_t s);
+
 // st_loss_opt.cu
 void st_launch_loss(const StDims& d, const float* y_hat, const float* y, const float* mag_hat, const float* sbf,
                     float l1_coef, int B, float* loss, float* g_y_hat, float* g_mag_hat, float* scratch,

@@ -201,7 +201,25 @@ def make_dct_case(name, ft_size, w_size, hop, chunk, B, seed=218):
     print(name, {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
 
 
+def make_compressor_case(name, B=4, n=4096, seed=218):
+    """audio.compressor_4controls (audio.py:380-426, numba-compiled) on float32 windows, one knob setting per window."""
+    rng = np.random.RandomState(seed)
+    t = np.arange(n) / 44100.0
+    x = (rng.uniform(0.2, 0.9, (B, 1)) * np.sin(2 * np.pi * rng.uniform(80, 3000, (B, 1)) * t) * np.exp(-rng.uniform(0, 8, (B, 1)) * t)
+         + 0.03 * rng.standard_normal((B, n))).astype(np.float32)
+    x[1, 100:400] = 0.0                                          # silence: the -96 dB floor and the 1e-8 offset
+    eff = st.audio.Compressor_4c()
+    knobs_nn = rng.beta(0.8, 0.8, size=(B, 4)) - 0.5
+    kr = eff.knob_ranges
+    knobs_wc = kr[:, 0] + (knobs_nn + 0.5) * (kr[:, 1] - kr[:, 0])
+    y = np.stack([st.audio.compressor_4controls(x[b].copy(), thresh=knobs_wc[b, 0], ratio=knobs_wc[b, 1], attackTime=knobs_wc[b, 2],
+                                                releaseTime=knobs_wc[b, 3], sr=44100.0) for b in range(B)])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x, knobs_wc=knobs_wc, y=y)
+    print(name, x.shape, y.dtype, float(np.abs(y).max()))
+
+
 def main():
+    make_compressor_case("compressor4c_n4096_b4")
     make_dct_case("dct_ft256_w512_h256_c4096_b3", 256, 512, 256, 4096, 3)
     make_dct_case("dct_ft1024_w2048_h1024_c8192_b2", 1024, 2048, 1024, 8192, 2)
     make_case("comp4c_c8192_k4_b3", 1, 4, st.audio.Compressor_4c(), B=3)
