@@ -306,3 +306,37 @@ def test_standalone_analysis_synthesis_roundtrip():
     assert wave.shape == (B, (d.T - 1) * d.H - d.N)
     n = wave.shape[1]
     np.testing.assert_allclose(wave.cpu().numpy(), x[:, :n], atol=5e-6)
+
+
+def test_autoencoder_backward_implementations_agree(monkeypatch):
+    """The warp-specialised FFMA2 backward (production), the mma.sync backward and the recomputing SIMT backward are three
+    independent implementations of the same gradients: they must agree on a ragged batch (37 windows: the last 32-row
+    chunk of every kernel is partial) and on a large one (512, BASELINE configs[2] shape)."""
+    d = O.model_dims(1, 4, 4)
+    P = O.init_params(d, seed=3)
+    rng = np.random.RandomState(9)
+    for B in (37, 512):
+        t = np.arange(d.C) / 44100.0
+        x = (0.4 * np.sin(2 * np.pi * rng.uniform(50, 4000, (B, 1)) * t) + 0.05 * rng.standard_normal((B, d.C))).astype(np.float32)
+        knobs = (rng.beta(0.8, 0.8, (B, d.K)) - 0.5).astype(np.float32)
+        y = np.tanh(1.3 * x[:, -d.L:]).astype(np.float32)
+        results = []
+        for env in ({}, {"ST_DISABLE_FFMA2_AE_BWD": "1"}, {"ST_DISABLE_FFMA2_AE_BWD": "1", "ST_DISABLE_MMA_BACKWARD": "1"}):
+            for k in ("ST_DISABLE_FFMA2_AE_BWD", "ST_DISABLE_MMA_BACKWARD"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            eng = _engine(d)                                  # the switches are read when the handle is created
+            params = _dev_params(P, d)
+            yh, _, mh, _ = eng.forward(_t(x), _t(knobs), params)
+            _, gy, gm = eng.loss(yh, _t(y), mh, _t(O.scale_by_freq(d.F)), 2e-6)
+            gs = [torch.zeros_like(p) for p in params]
+            eng.backward(gy, None, gm, params, gs)
+            torch.cuda.synchronize()
+            results.append([g.clone() for g in gs])
+            if B == 512 and len(results) == 2:
+                break                                         # the SIMT kernel at B=512 adds nothing the mma one does not
+        ref = results[0]
+        for other in results[1:]:
+            for i, (a, b) in enumerate(zip(ref, other)):
+                assert (a - b).abs().max().item() <= 3e-4 * max(a.abs().max().item(), 1e-12), (B, i)
