@@ -31,6 +31,10 @@ struct st_handle {
     float *yhat_ws = nullptr, *gy_ws = nullptr, *gmh_ws = nullptr;   // fused train step only
     float* knobs_ws = nullptr;    // copy of the forward's knobs (the SIMT backward recomputes the AE chain)
     float *ae_save_m = nullptr, *ae_save_p = nullptr;   // per-row activation records written by the tensor-core forward
+    // side stream: independent small kernels run beside the main stream's work (fork / join with events; off while profiling
+    // stages, whose event pairs live on the main stream)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float* dct_ws = nullptr;      // workspace of the DCT / MDCT front-end variant (st_dct_analysis / st_dct_synthesis)
     long dct_ws_floats = 0;
     float* gtrack_ws = nullptr;   // track gradients of the two autoencoders (FFMA2 backward -> ae_input_grad_kernel)
@@ -183,6 +187,12 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     d.Cp = C + 2 * N; d.Lp = L + 2 * N;
     d.Tp = (d.Cp + H - 1) / H; d.OTp = (d.Lp + H - 1) / H;
     d.Sx = d.Tp * H; d.Sg = d.OTp * H;
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        h->side = nullptr;                       // no overlap: everything stays on the caller's stream
+    }
     if (const char* e = getenv("ST_DISABLE_TCGEN05")) h->use_tc = !(e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_MMA_BACKWARD")) h->use_mma_bwd = !(e[0] == '1');
     if (const char* e = getenv("ST_ENABLE_TCGEN05_AE")) h->use_tc_ae = (e[0] == '1');
@@ -270,6 +280,9 @@ extern "C" void st_destroy(st_handle* h) {
     cudaSetDevice(h->device);
     free_batch_buffers(h);
     if (h->dct_ws) cudaFree(h->dct_ws);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side) cudaStreamDestroy(h->side);
     if (h->small) cudaFree(h->small);
     if (h->counters) cudaFree(h->counters);
     if (h->wcat) cudaFree(h->wcat);
@@ -402,17 +415,26 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
                         float* mag, float* mag_hat_user, float* const* acts, cudaStream_t s) {
     const StDims& d = h->d;
     if (ensure_workspace(h, B)) return 1;
+    // packing the weights does not depend on the batch: it runs on the side stream, beside the input padding
+    const bool beside = h->side && !h->prof_on;
+    {
+        cudaStream_t sp = beside ? h->side : s;
+        StageScope sc(h, SG_PACK_W, 2, s);
+        if (beside) {
+            ST_CUDA_OK(cudaEventRecord(h->ev_fork, s));          // behind whatever wrote the weights (the previous step's Adam)
+            ST_CUDA_OK(cudaStreamWaitEvent(sp, h->ev_fork, 0));
+        }
+        st_launch_pack_analysis(d, params[0], params[1], h->wcat, h->wcat_lo, sp);
+        st_launch_fold_synthesis(d, params[2], params[3], h->sfold, h->sfold_lo, sp);
+        if (beside) ST_CUDA_OK(cudaEventRecord(h->ev_join, sp));
+    }
     {
         StageScope sc(h, SG_PAD_X, 1 + (d.K > 0), s);
         // x/2 with the conv padding, as (hi, lo), window stride Sx = Tp*H (frame (b,t) = row b*Tp+t of a stride-H view)
         st_launch_pad_split(x, h->xpad, h->xpad_lo, B, d.C, d.N, d.Sx, 0.5f, s);
         if (d.K > 0) ST_CUDA_OK(cudaMemcpyAsync(h->knobs_ws, knobs, (long)B * d.K * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
-    {
-        StageScope sc(h, SG_PACK_W, 2, s);
-        st_launch_pack_analysis(d, params[0], params[1], h->wcat, h->wcat_lo, s);
-        st_launch_fold_synthesis(d, params[2], params[3], h->sfold, h->sfold_lo, s);
-    }
+    if (beside) ST_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
     ST_LAUNCH_OK(h);
     const int MT = B * d.Tp, MO = B * d.OTp, F2 = 2 * d.Fp;
     {   // analysis: spec[(b,t), (re|im) k] = sum_n frame[(b,t), n] * wcat[k, n]
@@ -573,14 +595,22 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
                                   g_mag, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_grid, s);
     }
     ST_LAUNCH_OK(h);
+    // the per-CTA autoencoder partials are summed on the side stream, beside the analysis weight-gradient GEMM
+    const bool beside = h->side && !h->prof_on;
     {
+        cudaStream_t sr = beside ? h->side : s;
         StageScope sc(h, SG_AE_REDUCE, 1, s);
         AeGrads gm, gp;
         for (int l = 0; l < ST_AE_LAYERS; ++l) {
             gm.W[l] = grads[4 + 2 * l];  gm.b[l] = grads[5 + 2 * l];
             gp.W[l] = grads[22 + 2 * l]; gp.b[l] = grads[23 + 2 * l];
         }
-        st_launch_ae_grad_reduce(h->g, h->ae_part, part_ctas, gm, gp, s);
+        if (beside) {
+            ST_CUDA_OK(cudaEventRecord(h->ev_fork, s));
+            ST_CUDA_OK(cudaStreamWaitEvent(sr, h->ev_fork, 0));
+        }
+        st_launch_ae_grad_reduce(h->g, h->ae_part, part_ctas, gm, gp, sr);
+        if (beside) ST_CUDA_OK(cudaEventRecord(h->ev_join, sr));
     }
     ST_LAUNCH_OK(h);
     {   // analysis weight gradient: G[(re|im) k, n] = sum_(b,t) g_spec[(b,t), k] * frame[(b,t), n]
@@ -600,6 +630,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         StageScope sc(h, SG_FINALIZE, 1, s);
         st_launch_finalize_dft_grads(d, h->part_a, h->part_s, sa, ss, grads[0], grads[1], grads[2], grads[3], s);
     }
+    if (beside) ST_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));        // all 40 gradients are complete on the caller's stream
     ST_LAUNCH_OK(h);
     return 0;
 }
