@@ -299,12 +299,29 @@ int st_tc_pick_bn(int n) {
     return 0;
 }
 
+// N-tile width for a given problem: among the multiples of 16 (32 for MN-major B) in [64, 256] that divide N, the one with
+// the fewest rounds x width over the SMs (a persistent CTA per SM walks ceil(work / SMs) tiles whose duration scales with
+// the width); ties go to the wider tile (fewer operand re-reads).  The synthesis GEMM (18 M-tiles x N = 1024) thus gets
+// 144 tiles of 128 instead of 72 of 256, which left half the SMs idle.
+static int pick_bn_for(int n, int tiles_m, int splits, bool b_mn, int sm_count) {
+    int best = 0;
+    long best_cost = 0;
+    for (int bn = 256; bn >= 64; bn -= 16) {
+        if (n % bn || (b_mn && (bn % 32))) continue;
+        const long work = (long)tiles_m * (n / bn) * splits;
+        const long cost = (work + sm_count - 1) / sm_count * bn;
+        if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+    }
+    return best;
+}
+
 // A: K-major -> A.rows = M, A.cols = K;  MN-major -> A.rows = K, A.cols = M.   Same for B with N.
 // Returns the number of split-K planes written, or -1 if this shape cannot take the tensor-core path.
 int st_launch_gemm_tc(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand& B, float* C, long ldc, int M, int N, int K,
                       int splits, long split_stride, bool promote, int sm_count, cudaStream_t s) {
-    const int BN = st_tc_pick_bn(N);
-    if (BN == 0 || (b_mn && (BN % 32))) return -1;
+    if (splits < 1) splits = 1;
+    const int BN = pick_bn_for(N, (M + BM - 1) / BM, splits, b_mn, sm_count > 0 ? sm_count : 148);
+    if (BN == 0) return -1;
     if ((A.ld & 3) || (B.ld & 3) || (ldc & 3) || (N & 3)) return -1;
     if (!a_mn && (K % BKF)) return -1;           // K-major operands are not zero-filled along K by a row bound
     if (!b_mn && (K % BKF)) return -1;
