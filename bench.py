@@ -42,7 +42,7 @@ def measured_peaks():
 def ncu_dram_traffic(stage):
     """dram__bytes_read + dram__bytes_write of the stage's kernels from the committed `ncu --set full` summary (bytes per
     stage = sum over its launches), or (None, why)."""
-    path = os.path.join(ROOT, "profiles", "r01_v6_ae_f2_ncu_full_summary.csv")
+    path = os.path.join(ROOT, "profiles", "r01_v7_ae_f2_ncu_full_summary.csv")
     want = {"ae_backward": "ae_bwd_f2_kernel", "ae_forward": "ae_fwd_f2_kernel"}.get(stage)
     if want is None or not os.path.exists(path):
         return None, "no ncu --set full capture of this kernel committed"
@@ -56,7 +56,7 @@ def ncu_dram_traffic(stage):
     n = len(cols)
     if stage == "ae_forward":          # the capture holds one of the stage's two launches
         tot, n = 2 * tot / max(n, 1), 2
-    return tot, f"profiles/r01_v6_ae_f2_ncu_full_summary.csv ({n} launches of {want}, B=200)"
+    return tot, f"profiles/r01_v7_ae_f2_ncu_full_summary.csv ({n} launches of {want}, B=200)"
 
 
 def stage_work(d, B):
@@ -286,8 +286,8 @@ def run_native(args):
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
         roofline["fp32_fma"] = {"achieved_tflops": useful / dur_s / 1e12, "peak_tflops": fp32_peak,
                                 "frac": useful / dur_s / 1e12 / fp32_peak,
-                                "note": "148 SMs x 128 FMA lanes x 2 x 1.965 GHz; ncu: FMA pipe 32 %, shared-memory data pipe 59 % "
-                                        "(profiles/r01_v6_ae_f2_ncu_full_summary.csv)"}
+                                "note": "148 SMs x 128 FMA lanes x 2 x 1.965 GHz; ncu (both kernels on all SMs): FMA pipe 32 %, shared-memory data "
+                                        "pipe 59 % (profiles/r01_v6_ae_f2_ncu_full_summary.csv)"}
     # CPU baseline: the oracle port on this box's host cores, bounded sample
     cores = os.cpu_count() or 1
     cpu_fps, cpu_ms = (None, None)
