@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "st_common.cuh"
 #include "st_tc_prims.cuh"
@@ -52,6 +53,30 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, bool mn_major) {
     return d;
 }
 
+// ---- 2-CTA cluster variant: the pair works on two M-tiles of the same N-tile, each CTA fetches HALF of the B tile and
+// multicasts it into both CTAs' shared memory (half the L2 reads for B; the GEMMs are operand-bandwidth bound because every
+// k-block moves hi and lo planes of both operands).  The MMA stays cta_group::1; only the B loads, the stage-release barrier
+// (both CTAs' MMAs must have retired before either overwrites a stage) and cluster syncs at both ends differ.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 struct TcParams {
     float* C;
     long ldc;
@@ -63,7 +88,7 @@ struct TcParams {
     int stages;
 };
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool MC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
@@ -80,7 +105,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], MC ? 2 : 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -91,19 +116,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (MC) cluster_sync_all();                // the peer's barriers are initialised before anything arrives on them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_work = p.tiles_m * p.tiles_n * p.splits;
+    // work items: (M-tile, N-tile, split); in cluster mode the pair shares an item of (M-tile PAIR, N-tile, split) and CTA
+    // `rank` takes M-tile 2 * pair + rank (a pair's second tile may lie past M: loads zero-fill, stores are guarded)
+    const uint32_t rank = MC ? cluster_ctarank() : 0u;
+    const int tiles_mw = MC ? (p.tiles_m + 1) / 2 : p.tiles_m;
+    const int total_work = tiles_mw * p.tiles_n * p.splits;
+    const int w_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int w_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+#define ST_TILE_M0(TT) (((MC ? 2 * ((TT) / p.tiles_n) + (int)rank : (TT) / p.tiles_n)) * BM)
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            for (int w = w_first; w < total_work; w += w_step) {
                 const int split = w % p.splits, tt = w / p.splits;
-                const int m0 = (tt / p.tiles_n) * BM, n0 = (tt % p.tiles_n) * p.BN;
+                const int m0 = ST_TILE_M0(tt), n0 = (tt % p.tiles_n) * p.BN;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -124,7 +157,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                             tma_load_2d(sA_lo + g * 4096, &tmAl, &full[stage], m0 + 32 * g, k0);
                         }
                     }
-                    if (!B_MN) {
+                    if (MC) {                 // my half of the B tile, into both CTAs (the peer sends the other half)
+                        if (!B_MN) {
+                            const int hr = p.BN >> 1;                       // rows per half (a multiple of the 8-row swizzle atom)
+                            tma_load_2d_mc(sB_hi + rank * hr * 128, &tmBh, &full[stage], k0, n0 + (int)rank * hr, 0x3);
+                            tma_load_2d_mc(sB_lo + rank * hr * 128, &tmBl, &full[stage], k0, n0 + (int)rank * hr, 0x3);
+                        } else {
+                            for (int g = (int)rank; g < p.BN / 32; g += 2) {
+                                tma_load_2d_mc(sB_hi + g * 4096, &tmBh, &full[stage], n0 + 32 * g, k0, 0x3);
+                                tma_load_2d_mc(sB_lo + g * 4096, &tmBl, &full[stage], n0 + 32 * g, k0, 0x3);
+                            }
+                        }
+                    } else if (!B_MN) {
                         tma_load_2d(sB_hi, &tmBh, &full[stage], k0, n0);
                         tma_load_2d(sB_lo, &tmBl, &full[stage], k0, n0);
                     } else {
@@ -148,7 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase[2] = {0, 0};
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            for (int w = w_first; w < total_work; w += w_step) {
                 const int split = w % p.splits;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -174,7 +218,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                             umma_tf32(tmem_d, ah, bh, idesc, 1u);
                             accumulate = 1u;
                         }
-                        umma_commit(&empty[stage]);                        // smem stage reusable once these MMAs retire
+                        if (MC) umma_commit_mc(&empty[stage], 0x3);        // ... in BOTH CTAs: each also writes the other's stage
+                        else umma_commit(&empty[stage]);                   // smem stage reusable once these MMAs retire
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(&tfull[acc]);                              // partial accumulator complete -> epilogue
@@ -191,9 +236,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int ncols = p.BN >> 1;                   // multiple of 8, <= 128
         int acc = 0;
         uint32_t acc_phase[2] = {0, 0};
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        for (int w = w_first; w < total_work; w += w_step) {
             const int split = w % p.splits, tt = w / p.splits;
-            const int m0 = (tt / p.tiles_n) * BM, n0 = (tt % p.tiles_n) * p.BN + half * ncols;
+            const int m0 = ST_TILE_M0(tt), n0 = (tt % p.tiles_n) * p.BN + half * ncols;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
             float sum[128];
@@ -235,8 +280,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             }
         }
     }
+#undef ST_TILE_M0
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (MC) cluster_sync_all();                // nobody leaves while the peer may still write its shared memory or barriers
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -277,17 +324,32 @@ bool make_map(CUtensorMap* tm, const float* base, long rows, long cols, long ld,
     return r == CUDA_SUCCESS;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool MC>
 cudaError_t launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcParams& p,
                    int grid, size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    gemm_tc_kernel<A_MN, B_MN><<<grid, NTHREADS, smem, s>>>(ah, al, bh, bl, p);
-    return cudaGetLastError();
+    if (!MC) {
+        gemm_tc_kernel<A_MN, B_MN, MC><<<grid, NTHREADS, smem, s>>>(ah, al, bh, bl, p);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A_MN, B_MN, MC>, ah, al, bh, bl, p);
 }
 
 }  // namespace
@@ -339,17 +401,33 @@ int st_launch_gemm_tc(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand&
     p.stages = (int)std::min<size_t>(4, (227 * 1024 - 2048) / stage_bytes);
     if (p.stages < 2) return -1;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+    // cluster (B-multicast) mode, opt-in (ST_GEMM_MULTICAST=1): measured no gain on the K-major GEMMs and a 25-35 % loss on the
+    // MN-major ones (the analysis GEMM takes 81 us with or without it): halving the L2 reads of B does not help because the
+    // bytes landing in each SM's shared memory are unchanged -- the limit is per-SM operand ingress / TMA latency with two
+    // 78 KB stages, which only cta_group::2 tiles (half of B per CTA) would lower.  Needs an even slab count for MN-major B.
+    static int mc_env = -1;
+    if (mc_env < 0) { const char* e = getenv("ST_GEMM_MULTICAST"); mc_env = (e && e[0] == '1') ? 1 : 0; }
+    const bool mc = mc_env == 1 && sm_count >= 2 && p.tiles_m >= 2 && (b_mn ? ((BN / 32) % 2 == 0) : ((BN / 2) % 8 == 0));
     CUtensorMap ah, al, bh, bl;
-    const int abox = a_mn ? 32 : BM, bbox = b_mn ? 32 : BN;
+    const int abox = a_mn ? 32 : BM, bbox = b_mn ? 32 : (mc ? BN / 2 : BN);
     if (!make_map(&ah, A.hi, A.rows, A.cols, A.ld, abox, a_mn) || !make_map(&al, A.lo, A.rows, A.cols, A.ld, abox, a_mn) ||
         !make_map(&bh, B.hi, B.rows, B.cols, B.ld, bbox, b_mn) || !make_map(&bl, B.lo, B.rows, B.cols, B.ld, bbox, b_mn))
         return -1;
-    const int work = p.tiles_m * p.tiles_n * p.splits;
-    const int grid = std::min(work, sm_count);
     cudaError_t e;
-    if (!a_mn && !b_mn) e = launch<false, false>(ah, al, bh, bl, p, grid, smem, s);
-    else if (!a_mn && b_mn) e = launch<false, true>(ah, al, bh, bl, p, grid, smem, s);
-    else if (a_mn && !b_mn) e = launch<true, false>(ah, al, bh, bl, p, grid, smem, s);
-    else e = launch<true, true>(ah, al, bh, bl, p, grid, smem, s);
+    if (mc) {
+        const int pairs = (p.tiles_m + 1) / 2 * p.tiles_n * p.splits;
+        const int grid = 2 * std::min(pairs, sm_count / 2);
+        if (!a_mn && !b_mn) e = launch<false, false, true>(ah, al, bh, bl, p, grid, smem, s);
+        else if (!a_mn && b_mn) e = launch<false, true, true>(ah, al, bh, bl, p, grid, smem, s);
+        else if (a_mn && !b_mn) e = launch<true, false, true>(ah, al, bh, bl, p, grid, smem, s);
+        else e = launch<true, true, true>(ah, al, bh, bl, p, grid, smem, s);
+    } else {
+        const int work = p.tiles_m * p.tiles_n * p.splits;
+        const int grid = std::min(work, sm_count);
+        if (!a_mn && !b_mn) e = launch<false, false, false>(ah, al, bh, bl, p, grid, smem, s);
+        else if (!a_mn && b_mn) e = launch<false, true, false>(ah, al, bh, bl, p, grid, smem, s);
+        else if (a_mn && !b_mn) e = launch<true, false, false>(ah, al, bh, bl, p, grid, smem, s);
+        else e = launch<true, true, false>(ah, al, bh, bl, p, grid, smem, s);
+    }
     return e == cudaSuccess ? p.splits : -1;
 }
