@@ -132,6 +132,14 @@ int st_mae(st_handle* h, const float* a, const float* b, long n, float* out, voi
 int st_backward(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat,
                 int batch, const float* const* params, float* const* grads, void* stream);
 
+/* The same backward in two calls, for data-parallel callers: after st_backward_begin the synthesis gradients (grads[2],
+ * grads[3]) are final, so their allreduce can run while st_backward_finish computes the autoencoder and analysis gradients.
+ * begin + finish == st_backward, bit for bit. */
+int st_backward_begin(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat,
+                      int batch, const float* const* params, float* const* grads, void* stream);
+int st_backward_finish(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat,
+                       int batch, const float* const* params, float* const* grads, void* stream);
+
 /* model.clip_grad_norm_() (nn_proc.py:299-302, torch clip_grad_norm_ max_norm=1 norm_type=1 over the
  * four DFT tensors): scales grads[0..3] in place, writes the total L1 norm to total_norm[0] (device). */
 int st_clip_grad_norm(st_handle* h, float* const* grads, float max_norm, float* total_norm, void* stream);

@@ -51,6 +51,10 @@ _SIGNATURES = {
     "st_mae": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_long, c_float_p, ctypes.c_void_p]),
     "st_backward": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p,
                                    ctypes.c_void_p, ctypes.c_void_p]),
+    "st_backward_begin": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p,
+                                   ctypes.c_void_p, ctypes.c_void_p]),
+    "st_backward_finish": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p,
+                                   ctypes.c_void_p, ctypes.c_void_p]),
     "st_clip_grad_norm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, c_float_p, ctypes.c_void_p]),
     "st_adam_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.POINTER(StAdam), ctypes.c_void_p]),

@@ -19,6 +19,7 @@ struct st_handle {
     int sm_count = 148;
     int maxB = 0;
     int fwdB = 0;                 // batch of the last st_forward (st_backward must match)
+    int bwd_ss = -1;              // split-K planes of the synthesis weight gradient written by st_backward_begin
     int ae_grid = 0;
     // workspace (device)
     // GEMM operands are kept as exact tf32 (hi, lo) pairs: *_lo is the residual of the buffer of the same name
@@ -533,12 +534,18 @@ extern "C" int st_mae(st_handle* h, const float* a, const float* b, long n, floa
     return 0;
 }
 
+// phase: 0 = the whole backward; 1 = "begin": up to and including the FINAL synthesis gradients (grads[2], grads[3]), so a
+// data-parallel caller can start their allreduce; 2 = "finish": the autoencoders and the analysis gradients.
 static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat, int B,
-                         const float* const* params, float* const* grads, cudaStream_t s) {
+                         const float* const* params, float* const* grads, cudaStream_t s, int phase = 0) {
     const StDims& d = h->d;
     if (B != h->fwdB || B > h->maxB)
         return st_fail_msg(h, "st_backward: batch %d does not match the preceding st_forward (%d)", B, h->fwdB);
     ST_CUDA_OK(cudaSetDevice(h->device));
+    const int MT = B * d.Tp, MO = B * d.OTp, F2 = 2 * d.Fp;
+    const long plane = (long)F2 * d.N;
+    int ss = -1, sa = -1;
+    if (phase != 2) {
     // adjoint of (*2, trim [N:-N]): zero-padded 2*g
     {
         StageScope sc(h, SG_PAD_G, 1, s);
@@ -546,8 +553,6 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         st_launch_pad_split(g_y_hat, h->gwave, h->gwave_lo, B, d.L, d.N, d.Sg, 2.0f, s);
     }
     ST_LAUNCH_OK(h);
-    const int MT = B * d.Tp, MO = B * d.OTp, F2 = 2 * d.Fp;
-    const long plane = (long)F2 * d.N;
     {   // synthesis data gradient: g_ri[(b,t), k] = sum_n gframe[(b,t), n] * sfold[k, n]   (gframe = adjoint of overlap-add)
         StageScope sc(h, SG_GEMM_SYNTH_DGRAD, 1, s);
         int r = -1;
@@ -561,7 +566,6 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         }
     }
     ST_LAUNCH_OK(h);
-    int ss = -1, sa = -1;
     {   // synthesis weight gradient (folded): G[k, n] = sum_(b,t) ri[(b,t), k] * gframe[(b,t), n]
         StageScope sc(h, SG_GEMM_SYNTH_WGRAD, 1, s);
         if (h->use_tc) {
@@ -575,6 +579,15 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         }
     }
     ST_LAUNCH_OK(h);
+    h->bwd_ss = ss;
+    if (phase == 1) {       // the synthesis pair is complete after its split-K planes are summed and un-folded
+        StageScope sc(h, SG_FINALIZE, 1, s);
+        st_launch_finalize_dft_grads(d, h->part_a, h->part_s, 0, ss, grads[0], grads[1], grads[2], grads[3], 2, s);
+        ST_LAUNCH_OK(h);
+        return 0;
+    }
+    }   // phase != 2
+    if (phase == 2) ss = h->bwd_ss;
     int part_ctas = h->ae_grid;
     {   // both autoencoders: back-propagate, dL/d(re|im) -> g_spec, per-CTA weight-gradient partials.  Tensor-core path
         // from the saved activations when the forward wrote them; otherwise the SIMT kernel recomputes the chain.
@@ -628,7 +641,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
     ST_LAUNCH_OK(h);
     {
         StageScope sc(h, SG_FINALIZE, 1, s);
-        st_launch_finalize_dft_grads(d, h->part_a, h->part_s, sa, ss, grads[0], grads[1], grads[2], grads[3], s);
+        st_launch_finalize_dft_grads(d, h->part_a, h->part_s, sa, ss, grads[0], grads[1], grads[2], grads[3], phase == 2 ? 1 : 3, s);
     }
     if (beside) ST_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));        // all 40 gradients are complete on the caller's stream
     ST_LAUNCH_OK(h);
@@ -642,6 +655,27 @@ extern "C" int st_backward(st_handle* h, const float* g_y_hat, const float* g_ma
     if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_backward(params)")) return 1;
     if (check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_backward(grads)")) return 1;
     return backward_impl(h, g_y_hat, g_mag, g_mag_hat, batch, params, grads, (cudaStream_t)stream);
+}
+
+extern "C" int st_backward_begin(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat, int batch,
+                                 const float* const* params, float* const* grads, void* stream) {
+    if (!h) return 1;
+    if (!g_y_hat) return st_fail_msg(h, "st_backward_begin: null g_y_hat");
+    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_backward_begin(params)")) return 1;
+    if (check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_backward_begin(grads)")) return 1;
+    h->bwd_ss = -1;
+    return backward_impl(h, g_y_hat, g_mag, g_mag_hat, batch, params, grads, (cudaStream_t)stream, 1);
+}
+
+extern "C" int st_backward_finish(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat, int batch,
+                                  const float* const* params, float* const* grads, void* stream) {
+    if (!h) return 1;
+    if (h->bwd_ss < 0) return st_fail_msg(h, "st_backward_finish: no st_backward_begin before it");
+    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_backward_finish(params)")) return 1;
+    if (check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_backward_finish(grads)")) return 1;
+    const int rc = backward_impl(h, g_y_hat, g_mag, g_mag_hat, batch, params, grads, (cudaStream_t)stream, 2);
+    h->bwd_ss = -1;
+    return rc;
 }
 
 extern "C" int st_clip_grad_norm(st_handle* h, float* const* grads, float max_norm, float* total_norm, void* stream) {

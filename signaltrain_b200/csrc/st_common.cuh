@@ -95,7 +95,8 @@ void st_launch_fold_synthesis(const StDims& d, const float* Sr, const float* Si,
 void st_launch_overlap_add(const StDims& d, const float* frames_out, const float* x, int B,
                            float* y_hat, float* x_fwdsyn, float* y_half, cudaStream_t s);
 void st_launch_finalize_dft_grads(const StDims& d, const float* part_a, const float* part_s, int splits_a,
-                                  int splits_s, float* gWr, float* gWi, float* gSr, float* gSi, cudaStream_t s);
+                                  int splits_s, float* gWr, float* gWi, float* gSr, float* gSi, int which /*1: analysis, 2: synthesis*/,
+                                  cudaStream_t s);
 void st_launch_unpack_spec(const StDims& d, const float* spec, int B, float* re, float* im, cudaStream_t s);
 void st_launch_dct_bias_unpack(const float* tmp, const float* bias, int B, int nf, int Tp, int sz, float* out, cudaStream_t s);
 void st_launch_dct_overlap_add(const float* fo, int B, int nf, int sz, int wsz, int hop, int C, float* wave, cudaStream_t s);

@@ -119,9 +119,11 @@ __global__ void overlap_add_kernel(StDims d, const float* __restrict__ fo, const
 // (N,1,N) gradient tensors:
 //   analysis: rows >= F receive no gradient (sliced off at cls_fe_dft.py:55-56) -> written as zero
 //   synthesis: un-fold: dS[k] = G[k] (k<=F-1), dSr[N-k] = G_r[k], dSi[N-k] = -G_i[k] (1<=k<=F-2)
+// which: bit 0 = the analysis pair, bit 1 = the synthesis pair (data parallel finalizes the synthesis gradients early so
+// their allreduce overlaps the rest of the backward)
 __global__ void finalize_dft_grads_kernel(StDims d, const float* __restrict__ pa, const float* __restrict__ ps,
                                           int sa, int ss, float* __restrict__ gWr, float* __restrict__ gWi,
-                                          float* __restrict__ gSr, float* __restrict__ gSi) {
+                                          float* __restrict__ gSr, float* __restrict__ gSi, int which) {
     const int n4 = d.N >> 2;
     const long plane = 2L * d.Fp * d.N;
     const long total = (long)d.N * n4;           // one thread per (row k in [0,N), 4 columns)
@@ -130,25 +132,30 @@ __global__ void finalize_dft_grads_kernel(StDims d, const float* __restrict__ pa
         const int c = (int)(i - (long)k * n4) << 2;
         const long o = (long)k * d.N + c;
         if (k >= d.F) {   // dead analysis rows; synthesis rows >= F are written by their mirror partner below
-            st4(gWr + o, make_float4(0.f, 0.f, 0.f, 0.f));
-            st4(gWi + o, make_float4(0.f, 0.f, 0.f, 0.f));
+            if (which & 1) {
+                st4(gWr + o, make_float4(0.f, 0.f, 0.f, 0.f));
+                st4(gWi + o, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
             continue;
         }
         float4 ar = make_float4(0.f, 0.f, 0.f, 0.f), ai = ar, sr = ar, si = ar;
-        for (int s = 0; s < sa; ++s) {
+        for (int s = 0; s < ((which & 1) ? sa : 0); ++s) {
             const float4 a = ld4(pa + s * plane + (long)k * d.N + c);
             const float4 b = ld4(pa + s * plane + (long)(d.Fp + k) * d.N + c);
             ar.x += a.x; ar.y += a.y; ar.z += a.z; ar.w += a.w;
             ai.x += b.x; ai.y += b.y; ai.z += b.z; ai.w += b.w;
         }
-        for (int s = 0; s < ss; ++s) {
+        for (int s = 0; s < ((which & 2) ? ss : 0); ++s) {
             const float4 a = ld4(ps + s * plane + (long)k * d.N + c);
             const float4 b = ld4(ps + s * plane + (long)(d.Fp + k) * d.N + c);
             sr.x += a.x; sr.y += a.y; sr.z += a.z; sr.w += a.w;
             si.x += b.x; si.y += b.y; si.z += b.z; si.w += b.w;
         }
-        st4(gWr + o, ar);
-        st4(gWi + o, ai);
+        if (which & 1) {
+            st4(gWr + o, ar);
+            st4(gWi + o, ai);
+        }
+        if (!(which & 2)) continue;
         st4(gSr + o, sr);
         st4(gSi + o, si);
         if (k >= 1 && k <= d.F - 2) {
@@ -229,8 +236,8 @@ void st_launch_overlap_add(const StDims& d, const float* fo, const float* x, int
     overlap_add_kernel<<<grid_for((long)B * (d.L >> 2), 256), 256, 0, s>>>(d, fo, x, B, y_hat, x_fwdsyn, y_half);
 }
 void st_launch_finalize_dft_grads(const StDims& d, const float* pa, const float* ps, int sa, int ss, float* gWr,
-                                  float* gWi, float* gSr, float* gSi, cudaStream_t s) {
-    finalize_dft_grads_kernel<<<grid_for((long)d.N * (d.N >> 2), 256), 256, 0, s>>>(d, pa, ps, sa, ss, gWr, gWi, gSr, gSi);
+                                  float* gWi, float* gSr, float* gSi, int which, cudaStream_t s) {
+    finalize_dft_grads_kernel<<<grid_for((long)d.N * (d.N >> 2), 256), 256, 0, s>>>(d, pa, ps, sa, ss, gWr, gWi, gSr, gSi, which);
 }
 void st_launch_init_frontend(const StDims& d, float* Wr, float* Wi, float* Sr, float* Si, float* scratch, cudaStream_t s) {
     init_frontend_kernel<<<grid_for((long)d.N * d.N, 256), 256, 0, s>>>(d, reinterpret_cast<const double*>(scratch), Wr, Wi,

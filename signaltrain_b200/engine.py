@@ -220,7 +220,8 @@ class Engine:
         self._ok(self.lib.st_mae(self.h, _ptr(a), _ptr(b), a.numel(), _ptr(out), self._stream()), "st_mae")
         return out
 
-    def backward(self, g_y_hat, g_mag, g_mag_hat, params, grads):
+    def backward(self, g_y_hat, g_mag, g_mag_hat, params, grads, part=None):
+        """part: None = whole backward; "begin" = until the synthesis gradients (grads[2], grads[3]) are final; "finish" = rest."""
         B = g_y_hat.shape[0]
         g = self.g
         _check(g_y_hat, "g_y_hat", (B, g.L), self.device)
@@ -228,8 +229,9 @@ class Engine:
             _check(g_mag, "g_mag", (B, g.T, g.F), self.device)
         if g_mag_hat is not None:
             _check(g_mag_hat, "g_mag_hat", (B, g.OT, g.F), self.device)
-        self._ok(self.lib.st_backward(self.h, _ptr(g_y_hat), _ptr(g_mag), _ptr(g_mag_hat), B, self.table(params, "params"),
-                                      self.table(grads, "grads"), self._stream()), "st_backward")
+        fn = {None: self.lib.st_backward, "begin": self.lib.st_backward_begin, "finish": self.lib.st_backward_finish}[part]
+        self._ok(fn(self.h, _ptr(g_y_hat), _ptr(g_mag), _ptr(g_mag_hat), B, self.table(params, "params"),
+                    self.table(grads, "grads"), self._stream()), "st_backward" + ("_" + part if part else ""))
 
     def clip_grad_norm(self, grads4, max_norm=1.0):
         for t in grads4:

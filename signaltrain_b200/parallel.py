@@ -41,6 +41,45 @@ def allreduce_sum_(flat, group=None):
     return 1.0 / w
 
 
+class GradReducer:
+    """Sum-allreduce of the flat gradient buffer in the pieces that actually carry information, overlapped with the backward.
+
+    Layout of the flat buffer (state_dict order): analysis real | analysis imag | synthesis real | synthesis imag | the two
+    autoencoders.  Rows >= F of the analysis tensors never receive gradient (cls_fe_dft.py:55-56 slices those bins off), so
+    only their first F rows travel: 12.6 MB instead of 16.8 MB at N = 1024.  The synthesis pair is final after the first
+    half of the backward (`Engine.backward(part="begin")`), so `start_synthesis()` launches its allreduce (8.4 MB) while the
+    autoencoder and analysis gradients are still being computed; `finish()` reduces the rest (4.3 MB on the critical path)
+    and waits for everything.  Works with any backend (NCCL on the GPU box, gloo on CPU in the tests)."""
+
+    def __init__(self, fb: FlatBuffer, shapes, live_rows, group=None):
+        self.flat, self.group = fb.flat, group
+        n = [1] * len(shapes)
+        for i, sh in enumerate(shapes):
+            for d in sh:
+                n[i] *= int(d)
+        row = n[0] // int(shapes[0][0])
+        o = fb.offsets
+        self.analysis = [self.flat[o[0]:o[0] + live_rows * row], self.flat[o[1]:o[1] + live_rows * row]]
+        self.synthesis = self.flat[o[2]:o[3] + n[3]]
+        self.rest = self.flat[o[4]:]
+        self.pending = []
+
+    def start_synthesis(self):
+        if world_size(self.group) > 1:
+            self.pending.append(dist.all_reduce(self.synthesis, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Returns the factor the consumer must scale by (1/world)."""
+        w = world_size(self.group)
+        if w > 1:
+            for t in self.analysis + [self.rest]:
+                self.pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            for work in self.pending:
+                work.wait()
+            self.pending = []
+        return 1.0 / w
+
+
 def shard_range(n_items, rank, world):
     """Contiguous shard [lo, hi) of n_items windows for `rank` (earlier ranks take the remainder)."""
     base, rem = divmod(n_items, world)

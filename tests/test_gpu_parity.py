@@ -340,3 +340,39 @@ def test_autoencoder_backward_implementations_agree(monkeypatch):
         for other in results[1:]:
             for i, (a, b) in enumerate(zip(ref, other)):
                 assert (a - b).abs().max().item() <= 3e-4 * max(a.abs().max().item(), 1e-12), (B, i)
+
+
+def test_backward_in_two_calls_is_bit_identical():
+    """st_backward_begin + st_backward_finish (the data-parallel split: the synthesis gradients are final after `begin`)
+    produce exactly the gradients of st_backward; after `begin` the synthesis pair already holds its final values."""
+    d = O.model_dims(1, 4, 4)
+    eng = _engine(d)
+    P = O.init_params(d, seed=4)
+    rng = np.random.RandomState(2)
+    B = 9
+    x = (0.3 * rng.standard_normal((B, d.C))).astype(np.float32)
+    knobs = (rng.beta(0.8, 0.8, (B, d.K)) - 0.5).astype(np.float32)
+    y = np.tanh(x[:, -d.L:]).astype(np.float32)
+    params = _dev_params(P, d)
+    sbf = _t(O.scale_by_freq(d.F))
+
+    def run(split):
+        yh, _, mh, _ = eng.forward(_t(x), _t(knobs), params)
+        _, gy, gm = eng.loss(yh, _t(y), mh, sbf, 2e-6)
+        gs = [torch.full_like(p, float("nan")) for p in params]
+        if not split:
+            eng.backward(gy, None, gm, params, gs)
+            return gs, None
+        eng.backward(gy, None, gm, params, gs, part="begin")
+        torch.cuda.synchronize()
+        early = [gs[2].clone(), gs[3].clone()]
+        eng.backward(gy, None, gm, params, gs, part="finish")
+        return gs, early
+    whole, _ = run(False)
+    parts, early = run(True)
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(whole, parts)):
+        assert torch.equal(a, b), i
+    assert torch.equal(early[0], whole[2]) and torch.equal(early[1], whole[3])
+    with pytest.raises(RuntimeError):
+        eng.backward(_t(y), None, None, params, parts, part="finish")          # no begin before it

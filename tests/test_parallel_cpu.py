@@ -37,7 +37,14 @@ def _worker(rank, world, port, q):
     fb = parallel.FlatBuffer(shapes, "cpu")
     for v, (name, _) in zip(fb.views, O.param_order(d)):
         v.copy_(torch.from_numpy(np.ascontiguousarray(grads[name], dtype=np.float32)))
+    # the production exchange: synthesis pair first (overlappable), then live analysis rows + autoencoders; dead rows stay home
+    fb2 = parallel.FlatBuffer(shapes, "cpu")
+    fb2.flat.copy_(fb.flat)
+    red = parallel.GradReducer(fb2, shapes, d.F)
+    red.start_synthesis()
+    scale2 = red.finish()
     scale = parallel.allreduce_sum_(fb.flat)
+    assert scale2 == scale and torch.equal(fb.flat, fb2.flat), "sliced allreduce differs from the whole-buffer allreduce"
     avg = {name: v.numpy().astype(np.float64) * scale for v, (name, _) in zip(fb.views, O.param_order(d))}
     total = O.clip_grad_norm_(avg)
     Pn = O.adam_step({n: a.astype(np.float64) for n, a in P.items()}, avg, {}, 1e-4 / 15)
