@@ -131,7 +131,7 @@ __device__ __forceinline__ void save_f2(const float* __restrict__ tile, float* _
 #pragma unroll 4
     for (int r = r0; r < CHUNK; r += RPI) {
         if (R0 + r < BF)
-            *reinterpret_cast<float4*>(save + (R0 + r) * ss + soff + 4 * c4) = *reinterpret_cast<const float4*>(tile + r * SS + 4 * c4);
+            __stcs(reinterpret_cast<float4*>(save + (R0 + r) * ss + soff + 4 * c4), *reinterpret_cast<const float4*>(tile + r * SS + 4 * c4));   // streaming: 263 MB of records per step must not evict the GEMM operands from L2
     }
 }
 
