@@ -194,19 +194,25 @@ ae_fwd_f2_kernel(StDims d, AeGeom g, F2Geom fg, AeParams p, const float* __restr
         for (int r = 0; r < 2; ++r) {
             float* st = r == 0 ? st0 : st1;
             float* mo = (AE == 0 && mag_out && ok[r]) ? mag_out + (long)b[r] * d.T * d.F + f[r] : nullptr;
+            // four frames per step through 16-byte accesses: the row stride (68 floats) makes those conflict-free, while
+            // scalar accesses of 32 lanes to their own rows hit each bank four times
 #pragma unroll 1
-            for (int t = 0; t < d.T; ++t) {
-                const float re = st[t], im = st[32 + t];
-                float v;
-                if (AE == 0) {
-                    v = ok[r] ? sqrtf(re * re + im * im) : 0.f;
-                    if (mo) mo[(long)t * d.F] = v;
-                } else {
-                    v = ok[r] ? atan2f(im, re + 1e-7f) : 0.f;
+            for (int t = 0; t < 32; t += 4) {
+                const float4 re4 = *reinterpret_cast<const float4*>(st + t), im4 = *reinterpret_cast<const float4*>(st + 32 + t);
+                const float re[4] = {re4.x, re4.y, re4.z, re4.w}, im[4] = {im4.x, im4.y, im4.z, im4.w};
+                float v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool on = ok[r] && t + q < d.T;
+                    if (AE == 0) {
+                        v[q] = on ? sqrtf(re[q] * re[q] + im[q] * im[q]) : 0.f;
+                        if (mo && t + q < d.T) mo[(long)(t + q) * d.F] = v[q];
+                    } else {
+                        v[q] = on ? atan2f(im[q], re[q] + 1e-7f) : 0.f;
+                    }
                 }
-                st[t] = v;
+                *reinterpret_cast<float4*>(st + t) = make_float4(v[0], v[1], v[2], v[3]);
             }
-            for (int t = d.T; t < 32; ++t) st[t] = 0.f;
         }
         reload_f2<IN0>(a, st0, st1);
         ST_T(0)
