@@ -29,6 +29,22 @@ sys.path.insert(0, ROOT)
 CHUNK_SCALE, SHRINK, KNOBS, SR = 1, 4, 4, 44100
 METRIC = "audio frames/sec per train step (comp_4c)"
 
+# BASELINE.json configs by index.  1 is the bench line (the config the metric is quoted on); 2-4 are the other GPU configs,
+# runnable here as extra, clearly labelled lines (--workload N) at N=1 or under torchrun: per-GPU batch as named, synthetic
+# windows of the named effect.  "tf32" = the reduced-precision mode (st_set_precision), this repo's answer to the bf16 configs.
+WORKLOADS = {
+    1: dict(scale=1, knobs=4, batch=200, precision="fp32", effect="Compressor_4c", dtype="f32",
+            name="comp_4c synthetic, chunk=8192, batch=200 per GPU, fp32 (BASELINE configs[1])"),
+    2: dict(scale=1, knobs=4, batch=512, precision="tf32", effect="Compressor_4c", dtype="tf32",
+            name="comp_4c synthetic windows (stand-in for the gen_dataset.py files), chunk=8192, batch=512 per GPU, reduced precision: "
+                 "single-pass TF32 products, fp32 storage/accumulate/optimiser (BASELINE configs[2], quoted as bf16)"),
+    3: dict(scale=2, knobs=2, batch=256, precision="fp32", effect="Compressor_2knob", dtype="f32",
+            name="LA2A-style 2-knob compressor, synthetic, chunk=16384, batch=256 per GPU, fp32 (BASELINE configs[3])"),
+    4: dict(scale=1, knobs=1, batch=256, precision="tf32", effect="Denoise", dtype="tf32",
+            name="denoise, chunk=8192, batch=256 per GPU, reduced precision: single-pass TF32 products, fp32 "
+                 "storage/accumulate/optimiser (BASELINE configs[4], quoted as bf16)"),
+}
+
 
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -120,16 +136,17 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_step_rate(B, steps, warmup, threads):
+def cpu_reference_step_rate(B, steps, warmup, threads, wl=None):
     """The reference's algorithm (oracle port, float32) on the host cores: frames/s and ms/step."""
+    wl = wl or WORKLOADS[1]
     from oracle import st_oracle as O
     from signaltrain_b200 import data
     try:
         from threadpoolctl import threadpool_limits
     except Exception:
         threadpool_limits = None
-    d = O.model_dims(CHUNK_SCALE, SHRINK, KNOBS)
-    x, y, k = data.make_pool(B, d.C, d.L, data.Compressor_4c(), SR, seed=218)
+    d = O.model_dims(wl["scale"], SHRINK, wl["knobs"])
+    x, y, k = data.make_pool(B, d.C, d.L, getattr(data, wl["effect"])(), SR, seed=218)
     lr_sched, _ = O.get_1cycle_schedule(1e-4, 200000, 1000, 200)
     tr = O.Trainer(d, O.init_params(d, seed=218), lr_sched, dtype=np.float32)
     ctx = threadpool_limits(limits=threads) if threadpool_limits else None
@@ -149,13 +166,14 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    B = args.batch
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl["batch"]
     steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    fps, ms = cpu_reference_step_rate(B, steps, warm, threads)
+    fps, ms = cpu_reference_step_rate(B, steps, warm, threads, wl)
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"comp_4c synthetic, chunk=8192, batch={B}, fp32 (BASELINE configs[1])", "where": "host CPU"},
+            "config": {"workload": wl["name"].replace(f"batch={wl['batch']} per GPU", f"batch={B}"), "where": "host CPU (float32)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": f"{steps} full train steps of B={B} windows (oracle/st_oracle.py Trainer, float32, "
                                        f"numpy/BLAS on {threads} threads)"},
@@ -179,12 +197,15 @@ def run_native(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, K, Wm = args.batch, args.steps, max(3, args.warmup)
+    wl = WORKLOADS[args.workload]
+    CHUNK_SCALE, KNOBS = wl["scale"], wl["knobs"]
+    B, K, Wm = args.batch or wl["batch"], args.steps, max(3, args.warmup)
 
     torch.manual_seed(218)
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):      # stdout carries exactly one JSON line
         model = st.nn_proc.st_model(scale_factor=CHUNK_SCALE, shrink_factor=SHRINK, num_knobs=KNOBS, sr=SR).to(dev)
+    model.set_precision(wl["precision"])
     C, L = model.in_chunk_size, model.out_chunk_size
     lr_sched, _ = st.learningrate.get_1cycle_schedule(lr_max=1e-4, n_data_points=200000, epochs=1000, batch_size=200)
     trainer = FusedTrainer(model, lr_sched)
@@ -192,7 +213,7 @@ def run_native(args):
     # window pool larger than L2 (126 MB): P windows * (C + L + K) * 4 B
     nbatch = max(4, -(-int(168e6) // (B * (C + L + KNOBS) * 4)))
     P = nbatch * B
-    xh, yh, kh = data.make_pool(P, C, L, data.Compressor_4c(), SR, seed=218 + rank)
+    xh, yh, kh = data.make_pool(P, C, L, getattr(data, wl["effect"])(), SR, seed=218 + rank)
     xp, yp, kp = (torch.from_numpy(a).pin_memory() for a in (xh, yh, kh))
     xd, yd, kd = xp.to(dev), yp.to(dev), kp.to(dev)
 
@@ -273,13 +294,13 @@ def run_native(args):
         achieved, peak, unit = w["flops"] / dur_s / 1e12, peaks["bf16_sustained"], "TFLOP/s"
     else:
         achieved, peak, unit = w["bytes"] / dur_s / 1e9, peaks["hbm"], "GB/s"
-    traffic, traffic_src = ncu_dram_traffic(top)
+    traffic, traffic_src = ncu_dram_traffic(top) if args.workload == 1 and B == 200 else (None, "no ncu --set full capture at this workload")
     roofline = {"kernel": top, "bound": w["bound"], "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["src"], "kernel_ms": stages[top][0],
                 "share_of_step": stages[top][0] / step_sum if step_sum else None,
                 "algorithmic_bytes": w["bytes"], "algorithmic_flops": w["flops"],
                 "stages_ms": {k: round(v[0], 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])}}
-    if top in ("ae_backward", "ae_forward"):
+    if top in ("ae_backward", "ae_forward") and wl["precision"] == "fp32" and CHUNK_SCALE == 1:
         # the autoencoder chains run on the packed-fp32 FMA pipe by design (exact fp32): besides the
         # HBM figure the contract asks for, state how far they are from the CUDA-core peak (no recompute: 2/3 of the flops)
         useful = w["flops"] * (2.0 / 3.0 if top == "ae_backward" else 1.0)
@@ -292,12 +313,13 @@ def run_native(args):
     cores = os.cpu_count() or 1
     cpu_fps, cpu_ms = (None, None)
     if world == 1 and not args.no_cpu_baseline:
-        cpu_fps, cpu_ms = cpu_reference_step_rate(B, 3, 1, cores)
+        cpu_fps, cpu_ms = cpu_reference_step_rate(B, 3, 1, cores, wl)
     frames = world * B * C
     line = {"metric": METRIC, "value": frames * K / (ms_total * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"comp_4c synthetic, chunk={C}, batch={B} per GPU, fp32, {world}xB200 (BASELINE configs[1])",
+            "dtype": wl["dtype"], "data": "synthetic",
+            "config": {"workload": wl["name"].replace(f"batch={wl['batch']} per GPU", f"batch={B} per GPU") + f", {world}xB200",
+                       "precision": eng.precision,
                        "global_batch": world * B, "windows_per_s": world * B * K / (ms_total * 1e-3),
                        "stft_frames_per_s": world * B * d.T * K / (ms_total * 1e-3),
                        "l2": f"pool: each step reads a different batch of a {P}-window ({P * (C + L + KNOBS) * 4 / 1e6:.0f} MB) pool",
@@ -319,7 +341,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=200)
+    ap.add_argument("--batch", type=int, default=0, help="windows per GPU per step (default: the workload's)")
+    ap.add_argument("--workload", type=int, default=1, choices=sorted(WORKLOADS),
+                    help="index into BASELINE.json configs (1 = the bench line; 2-4 = the other GPU configs, extra lines)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

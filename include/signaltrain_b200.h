@@ -114,6 +114,19 @@ int st_forward(st_handle* h, const float* x, const float* knobs, int batch,
  * (it recomputes the chain with the slower SIMT kernels). */
 int st_set_training(st_handle* h, int on);
 
+/* Arithmetic of the contractions (the reference's `apex_opt` argument of train.train(), train.py:167-170,232-236, is its
+ * only precision knob: "O0" fp32 ... "O2" mixed).  Storage, accumulation, loss, atan2 and the optimiser are fp32 in both modes.
+ *   ST_PRECISION_FP32 (default): fp32-faithful products -- 3xTF32 tensor-core GEMMs on exact (hi, lo) operand pairs, exact
+ *     fp32 FMA chains in the autoencoders; waveforms within 1e-5 of the reference.
+ *   ST_PRECISION_TF32: every product of the five DFT contractions and of the autoencoder layers is ONE tensor-core TF32
+ *     multiply (operands rounded to 10 mantissa bits, fp32 accumulate) -- the mixed-precision class of BASELINE configs 3 and 5
+ *     (apex O1/O2 in the reference); waveforms within ~2e-3 of the fp32 path (tests/test_gpu_precision.py states the bound).
+ * Takes effect at the next st_forward; a backward must follow a forward of the same mode. */
+#define ST_PRECISION_FP32 0
+#define ST_PRECISION_TF32 1
+int st_set_precision(st_handle* h, int mode);
+int st_get_precision(const st_handle* h);
+
 /* loss_functions.calc_loss(y_hat, y, mag_hat, scale_by_freq=..., l1_lambda): loss_functions.py:26-43,
  * branches :34 (scale_by_freq NULL: l1_coef*mean|mag_hat|) and :36 (l1_coef*mean|mag_hat*s|; the caller
  * passes l1_coef = l1_lambda/10 as the reference does).  scale_by_freq is F floats (the reference
@@ -172,7 +185,8 @@ int st_debug_ae_timing(st_handle* h, int on, long long* out_host);
 /* Test/diagnostic access to workspace buffers by name ("spec", "ri", "frames_out", "g_ri", "g_spec",
  * "wcat", "sfold").  Copies up to n floats to a HOST buffer, synchronising the device. */
 int st_debug_read(st_handle* h, const char* name, float* dst_host, long n);
-/* Test hook: C[M,N] = A*B on (hi, lo) tf32-pair operands through the tcgen05 (use_tc=1) or FFMA (use_tc=0) kernel.
+/* Test hook: C[M,N] = A*B on (hi, lo) tf32-pair operands through the tcgen05 (use_tc=1; 2 = promoted accumulation;
+ * 3 = single-pass TF32 on the hi planes only) or FFMA (use_tc=0) kernel.
  * a_mn/b_mn: 0 = K-major [row][k], 1 = MN-major [k][row]; rows may overlap (ld < row length).  Split-K planes are
  * written M*ldc apart; returns their number or -1 if the shape is not covered. */
 int st_debug_gemm(st_handle* h, int use_tc, int a_mn, int b_mn, const float* a_hi, const float* a_lo, long a_ld,

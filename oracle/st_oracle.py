@@ -131,6 +131,46 @@ def init_params(d: Dims, seed=218):
 # --------------------------------------------------------------------------------------------
 # forward                                                                   nn_proc.py:305-340
 # --------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------
+# reduced-precision emulation (checker for st_set_precision(ST_PRECISION_TF32))
+# --------------------------------------------------------------------------------------------
+_OPERAND_ROUNDING = None
+
+
+class operand_rounding:
+    """Context manager: inside it every contraction of the path (the five DFT contractions and the autoencoder layers,
+    forward and backward) sees its two operands rounded to TF32 (10 explicit mantissa bits, round-to-nearest ties away,
+    as `cvt.rna.tf32.f32`), products and sums exact in the working dtype.  The reference's counterpart is apex mixed
+    precision (train.py:133-136); there is no reference run of it here (apex absent), so this is a model of the CUDA
+    path's arithmetic used to bound its error, not a pin."""
+
+    def __init__(self, mode="tf32"):
+        assert mode in (None, "tf32")
+        self.mode = mode
+
+    def __enter__(self):
+        global _OPERAND_ROUNDING
+        self.prev, _OPERAND_ROUNDING = _OPERAND_ROUNDING, self.mode
+        return self
+
+    def __exit__(self, *exc):
+        global _OPERAND_ROUNDING
+        _OPERAND_ROUNDING = self.prev
+        return False
+
+
+def round_tf32(a):
+    """fp32 -> tf32 (rna): add half an ulp of the 13 dropped bits to the magnitude, clear them."""
+    a32 = np.ascontiguousarray(a, dtype=np.float32)
+    bits = a32.view(np.uint32)
+    out = ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    return out.astype(np.asarray(a).dtype if np.asarray(a).dtype in (np.float32, np.float64) else np.float32)
+
+
+def _q(a):
+    return a if _OPERAND_ROUNDING is None else round_tf32(a)
+
+
 def elu(z):
     """nn.ELU(alpha=1), nn_proc.py:63."""
     return np.where(z > 0, z, np.expm1(np.minimum(z, 0)))
@@ -150,8 +190,8 @@ def analysis_forward(d: Dims, Wr, Wi, x):
     Tc = (d.C + d.N) // d.H + 1
     assert Tc == d.T, f"conv output frames {Tc} != expected_time_frames {d.T}"
     fr = _frames(xpad, d.T, d.N, d.H)
-    re = fr @ Wr[:d.F].T
-    im = fr @ Wi[:d.F].T
+    re = _q(fr) @ _q(Wr[:d.F]).T
+    im = _q(fr) @ _q(Wi[:d.F]).T
     return re, im, fr
 
 
@@ -166,7 +206,7 @@ def ae_forward(d: Dims, P, prefix, v_btf, knobs, mode):
             kr = np.broadcast_to(knobs[:, None, :], (h.shape[0], h.shape[1], knobs.shape[1]))
             h = np.concatenate([h, kr], axis=2)
             acts[-1] = h
-        z = h @ W.T + b
+        z = _q(h) @ _q(W).T + b
         pre.append(z)
         h = elu(z)
         acts.append(h)
@@ -184,7 +224,7 @@ def synthesis_forward(d: Dims, Sr, Si, an_re, an_im):
     """cls_fe_dft.py:102-115: Hermitian mirror to N channels, two ConvTranspose1d summed, trim N."""
     Rf = np.concatenate([an_re, an_re[:, :, -2:0:-1]], axis=2)        # (B,OT,N)   :109
     If = np.concatenate([an_im, -an_im[:, :, -2:0:-1]], axis=2)       #            :110
-    fo = Rf @ Sr + If @ Si                                            # (B,OT,N) per-frame output
+    fo = _q(Rf) @ _q(Sr) + _q(If) @ _q(Si)                            # (B,OT,N) per-frame output
     B = an_re.shape[0]
     wave = np.zeros((B, (d.OT - 1) * d.H + d.N), dtype=fo.dtype)
     for t in range(d.OT):
@@ -329,9 +369,9 @@ def _ae_backward(d: Dims, P, prefix, cache, g_out_bof, grads):
         gz = g * np.where(z > 0, 1.0, np.exp(np.minimum(z, 0)))          # ELU'
         hin = acts[li]
         W = P[f"{prefix}.{name}.weight"]
-        grads[f"{prefix}.{name}.weight"] = np.einsum("bfo,bfi->oi", gz, hin, optimize=True)
+        grads[f"{prefix}.{name}.weight"] = np.einsum("bfo,bfi->oi", _q(gz), _q(hin), optimize=True)
         grads[f"{prefix}.{name}.bias"] = gz.sum(axis=(0, 1))
-        g = gz @ W
+        g = _q(gz) @ _q(W)
         if li == 4:
             g = g[:, :, : d.R // 4]                            # knobs carry no gradient
     if g_tail is not None:
@@ -351,10 +391,10 @@ def backward(d: Dims, fw, g_y_hat, g_mag_hat, g_mag=None):
     g_wave[:, d.N:-d.N] = 2 * g_y_hat
     g_fo = _frames(g_wave, d.OT, d.N, d.H)                   # (B,OT,N) gather = adjoint of overlap-add
     Rf, If = fw["Rf"], fw["If"]
-    grads[DFT_KEYS[2]] = np.einsum("btk,btn->kn", Rf, g_fo, optimize=True).reshape(d.N, 1, d.N)
-    grads[DFT_KEYS[3]] = np.einsum("btk,btn->kn", If, g_fo, optimize=True).reshape(d.N, 1, d.N)
-    gRf = g_fo @ Sr.T
-    gIf = g_fo @ Si.T
+    grads[DFT_KEYS[2]] = np.einsum("btk,btn->kn", _q(Rf), _q(g_fo), optimize=True).reshape(d.N, 1, d.N)
+    grads[DFT_KEYS[3]] = np.einsum("btk,btn->kn", _q(If), _q(g_fo), optimize=True).reshape(d.N, 1, d.N)
+    gRf = _q(g_fo) @ _q(Sr).T
+    gIf = _q(g_fo) @ _q(Si).T
     F = d.F
     g_re_o = gRf[:, :, :F].copy()
     g_im_o = gIf[:, :, :F].copy()
@@ -380,8 +420,8 @@ def backward(d: Dims, fw, g_y_hat, g_mag_hat, g_mag=None):
     fr = fw["fr"]
     gWr = np.zeros((d.N, d.N), dtype=g_re.dtype)
     gWi = np.zeros((d.N, d.N), dtype=g_re.dtype)
-    gWr[:F] = np.einsum("btk,btn->kn", g_re, fr, optimize=True)          # rows >= F: sliced off, zero
-    gWi[:F] = np.einsum("btk,btn->kn", g_im, fr, optimize=True)
+    gWr[:F] = np.einsum("btk,btn->kn", _q(g_re), _q(fr), optimize=True)  # rows >= F: sliced off, zero
+    gWi[:F] = np.einsum("btk,btn->kn", _q(g_im), _q(fr), optimize=True)
     grads[DFT_KEYS[0]] = gWr.reshape(d.N, 1, d.N)
     grads[DFT_KEYS[1]] = gWi.reshape(d.N, 1, d.N)
     return grads

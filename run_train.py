@@ -43,7 +43,7 @@ if __name__ == "__main__":
 
     parser = argparse.ArgumentParser(description="Trains neural network to reproduce input-output transformations.",
                                      formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    parser.add_argument('--apex', help="optimization setting to use with NVIDIA apex (ignored: fp32 + 3xTF32 tensor cores)", default="O0")
+    parser.add_argument('--apex', help="precision, in the reference's apex vocabulary: O0 = fp32-faithful (3xTF32 tensor cores); O1/O2/O3 = single-pass TF32 products", default="O0")
     parser.add_argument('-b', '--batch', type=int, help="batch size", default=200)
     parser.add_argument('--checkpoint', help='Name of model checkpoint .tar file', default="modelcheckpoint.tar")
     parser.add_argument('-c', '--compand', help='Turn on to use companded/decompanded audio', action='store_true')

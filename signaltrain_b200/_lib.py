@@ -62,6 +62,8 @@ _SIGNATURES = {
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p, ctypes.c_float,
                                      ctypes.POINTER(StAdam), c_float_p, ctypes.c_void_p]),
     "st_set_training": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "st_set_precision": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "st_get_precision": (ctypes.c_int, [ctypes.c_void_p]),
     "st_launch_count": (ctypes.c_long, [ctypes.c_void_p]),
     "st_profile_stage_count": (ctypes.c_int, []),
     "st_profile_stage_name": (ctypes.c_char_p, [ctypes.c_int]),

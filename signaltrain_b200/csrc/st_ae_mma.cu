@@ -32,6 +32,12 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     hi = to_tf32(x);
     lo = to_tf32(x - __uint_as_float(hi));
 }
+// PASSES = 3: exact two-term split (3xTF32).  PASSES = 1: reduced-precision mode (st_set_precision): hi only, one MMA per product.
+template <int PASSES>
+__device__ __forceinline__ void split_p(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = PASSES == 3 ? to_tf32(x - __uint_as_float(hi)) : 0u;
+}
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -45,7 +51,7 @@ __device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : __expf(z)
 //   A fragment (m16 x k8): a0 (row g, k t), a1 (row g+8, k t), a2 (row g, k t+4), a3 (row g+8, k t+4)
 //   B fragment (k8 x n8):  b0 (k t, n g), b1 (k t+4, n g)      with B[k][n] = W[n][k]
 //   C fragment (m16 x n8): c0 (row g, n 2t), c1 (row g, n 2t+1), c2 (row g+8, n 2t), c3 (row g+8, n 2t+1)
-template <int NT>
+template <int NT, int PASSES>
 __device__ __forceinline__ void layer_mma(const float* __restrict__ act, int ksteps, const float* __restrict__ W, int ld,
                                           const float* __restrict__ bias, float (&c)[2][NT][4], int g, int t) {
 #pragma unroll
@@ -61,10 +67,10 @@ __device__ __forceinline__ void layer_mma(const float* __restrict__ act, int kst
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
             const float* ap = act + (16 * mt + g) * RS + 8 * j + t;
-            split_tf32(ap[0], ahi[mt][0], alo[mt][0]);
-            split_tf32(ap[8 * RS], ahi[mt][1], alo[mt][1]);
-            split_tf32(ap[4], ahi[mt][2], alo[mt][2]);
-            split_tf32(ap[8 * RS + 4], ahi[mt][3], alo[mt][3]);
+            split_p<PASSES>(ap[0], ahi[mt][0], alo[mt][0]);
+            split_p<PASSES>(ap[8 * RS], ahi[mt][1], alo[mt][1]);
+            split_p<PASSES>(ap[4], ahi[mt][2], alo[mt][2]);
+            split_p<PASSES>(ap[8 * RS + 4], ahi[mt][3], alo[mt][3]);
         }
         // pass-major over groups of n-tiles: consecutive MMAs hit different accumulators (the three passes of one
         // accumulator are 2*NG instructions apart), so the tensor pipe is not serialised on accumulator latency
@@ -75,9 +81,10 @@ __device__ __forceinline__ void layer_mma(const float* __restrict__ act, int kst
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
                 const float* wp = W + (8 * (n0 + q) + g) * ld + 8 * j + t;
-                split_tf32(wp[0], bh[q][0], bl[q][0]);
-                split_tf32(wp[4], bh[q][1], bl[q][1]);
+                split_p<PASSES>(wp[0], bh[q][0], bl[q][0]);
+                split_p<PASSES>(wp[4], bh[q][1], bl[q][1]);
             }
+if (PASSES == 3) {
 #pragma unroll
             for (int q = 0; q < NG; ++q)
 #pragma unroll
@@ -86,6 +93,7 @@ __device__ __forceinline__ void layer_mma(const float* __restrict__ act, int kst
             for (int q = 0; q < NG; ++q)
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n0 + q], ahi[mt], bl[q][0], bl[q][1]);
+            }
 #pragma unroll
             for (int q = 0; q < NG; ++q)
 #pragma unroll
@@ -151,7 +159,7 @@ __device__ void stage_weights_mma(const MmaGeom& mg, const AeGeom& g, const AePa
 }
 
 // AE = 0: magnitude autoencoder ('sf' skip-filter).  AE = 1: phase autoencoder + residual + polar->rect.
-template <int NT9, int AE>
+template <int NT9, int AE, int PASSES>
 __global__ void __launch_bounds__(FWD_WARPS * 32, 1)
 ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __restrict__ spec,
                   const float* __restrict__ knobs, int B, float* __restrict__ mag_out, float* __restrict__ mag_hat,
@@ -203,25 +211,25 @@ ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
         // ---- fnn_enc .. fnn_enc4
         {
             float c[2][8][4];
-            layer_mma<8>(act, mg.ks[0], W + mg.off[0], mg.ld[0], bias + mg.boff[0], c, gq, t);
+            layer_mma<8, PASSES>(act, mg.ks[0], W + mg.off[0], mg.ld[0], bias + mg.boff[0], c, gq, t);
             store_act<8>(act, c, gq, t);
             if (save) save_tile<64>(act, save, R0, BF, mg.ss, mg.soff[0], lane);
         }
         {
             float c[2][4][4];
-            layer_mma<4>(act, 8, W + mg.off[1], mg.ld[1], bias + mg.boff[1], c, gq, t);
+            layer_mma<4, PASSES>(act, 8, W + mg.off[1], mg.ld[1], bias + mg.boff[1], c, gq, t);
             store_act<4>(act, c, gq, t);
             if (save) save_tile<32>(act, save, R0, BF, mg.ss, mg.soff[1], lane);
         }
         {
             float c[2][2][4];
-            layer_mma<2>(act, 4, W + mg.off[2], mg.ld[2], bias + mg.boff[2], c, gq, t);
+            layer_mma<2, PASSES>(act, 4, W + mg.off[2], mg.ld[2], bias + mg.boff[2], c, gq, t);
             store_act<2>(act, c, gq, t);
             if (save) save_tile<16>(act, save, R0, BF, mg.ss, mg.soff[2], lane);
         }
         {
             float c[2][2][4];
-            layer_mma<2>(act, 2, W + mg.off[3], mg.ld[3], bias + mg.boff[3], c, gq, t);
+            layer_mma<2, PASSES>(act, 2, W + mg.off[3], mg.ld[3], bias + mg.boff[3], c, gq, t);
             store_act<2>(act, c, gq, t);
         }
         // ---- knob concat (torch.cat, nn_proc.py:95-96): columns 16..31 = knobs, zero padded
@@ -236,25 +244,25 @@ ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
         }
         {
             float c[2][2][4];
-            layer_mma<2>(act, 4, W + mg.off[4], mg.ld[4], bias + mg.boff[4], c, gq, t);
+            layer_mma<2, PASSES>(act, 4, W + mg.off[4], mg.ld[4], bias + mg.boff[4], c, gq, t);
             store_act<2>(act, c, gq, t);
             if (save) save_tile<16>(act, save, R0, BF, mg.ss, mg.soff[4], lane);
         }
         {
             float c[2][2][4];
-            layer_mma<2>(act, 2, W + mg.off[5], mg.ld[5], bias + mg.boff[5], c, gq, t);
+            layer_mma<2, PASSES>(act, 2, W + mg.off[5], mg.ld[5], bias + mg.boff[5], c, gq, t);
             store_act<2>(act, c, gq, t);
             if (save) save_tile<16>(act, save, R0, BF, mg.ss, mg.soff[5], lane);
         }
         {
             float c[2][4][4];
-            layer_mma<4>(act, 2, W + mg.off[6], mg.ld[6], bias + mg.boff[6], c, gq, t);
+            layer_mma<4, PASSES>(act, 2, W + mg.off[6], mg.ld[6], bias + mg.boff[6], c, gq, t);
             store_act<4>(act, c, gq, t);
             if (save) save_tile<32>(act, save, R0, BF, mg.ss, mg.soff[6], lane);
         }
         {
             float c[2][8][4];
-            layer_mma<8>(act, 4, W + mg.off[7], mg.ld[7], bias + mg.boff[7], c, gq, t);
+            layer_mma<8, PASSES>(act, 4, W + mg.off[7], mg.ld[7], bias + mg.boff[7], c, gq, t);
             store_act<8>(act, c, gq, t);
             if (save) save_tile<64>(act, save, R0, BF, mg.ss, mg.soff[7], lane);
         }
@@ -262,7 +270,7 @@ ae_fwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
         //      copy of the transcendental code instead of one per accumulator register)
         {
             float c9[2][NT9][4];
-            layer_mma<NT9>(act, 8, W + mg.off[8], mg.ld[8], bias + mg.boff[8], c9, gq, t);
+            layer_mma<NT9, PASSES>(act, 8, W + mg.off[8], mg.ld[8], bias + mg.boff[8], c9, gq, t);
             store_act<NT9>(act, c9, gq, t);
         }
         {
@@ -307,7 +315,7 @@ __device__ __forceinline__ float elu_grad(float h) { return h > 0.f ? 1.f : h + 
 
 // Data gradient of one layer for the warp's own 32 rows:  c[row][i] = sum_o gz[row][o] * W[o][i]
 //   B fragment (k8 x n8) with B[k = o][n = i] = W[o][i]:  b0 = W[(8j+t)*ld + 8n+g],  b1 = W[(8j+t+4)*ld + 8n+g]
-template <int NT>
+template <int NT, int PASSES>
 __device__ __forceinline__ void layer_mma_T(const float* __restrict__ gz, int ksteps, const float* __restrict__ W, int ld,
                                             float (&c)[2][NT][4], int g, int t) {
 #pragma unroll
@@ -320,10 +328,10 @@ __device__ __forceinline__ void layer_mma_T(const float* __restrict__ gz, int ks
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
             const float* ap = gz + (16 * mt + g) * PS + 8 * j + t;
-            split_tf32(ap[0], ahi[mt][0], alo[mt][0]);
-            split_tf32(ap[8 * PS], ahi[mt][1], alo[mt][1]);
-            split_tf32(ap[4], ahi[mt][2], alo[mt][2]);
-            split_tf32(ap[8 * PS + 4], ahi[mt][3], alo[mt][3]);
+            split_p<PASSES>(ap[0], ahi[mt][0], alo[mt][0]);
+            split_p<PASSES>(ap[8 * PS], ahi[mt][1], alo[mt][1]);
+            split_p<PASSES>(ap[4], ahi[mt][2], alo[mt][2]);
+            split_p<PASSES>(ap[8 * PS + 4], ahi[mt][3], alo[mt][3]);
         }
         constexpr int NG = NT < 4 ? NT : 4;      // pass-major over groups of n-tiles (see layer_mma)
 #pragma unroll
@@ -332,9 +340,10 @@ __device__ __forceinline__ void layer_mma_T(const float* __restrict__ gz, int ks
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
                 const float* wp = W + (8 * j + t) * ld + 8 * (n0 + q) + g;
-                split_tf32(wp[0], bh[q][0], bl[q][0]);
-                split_tf32(wp[4 * ld], bh[q][1], bl[q][1]);
+                split_p<PASSES>(wp[0], bh[q][0], bl[q][0]);
+                split_p<PASSES>(wp[4 * ld], bh[q][1], bl[q][1]);
             }
+if (PASSES == 3) {
 #pragma unroll
             for (int q = 0; q < NG; ++q)
 #pragma unroll
@@ -343,6 +352,7 @@ __device__ __forceinline__ void layer_mma_T(const float* __restrict__ gz, int ks
             for (int q = 0; q < NG; ++q)
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) mma_tf32(c[mt][n0 + q], ahi[mt], bl[q][0], bl[q][1]);
+            }
 #pragma unroll
             for (int q = 0; q < NG; ++q)
 #pragma unroll
@@ -392,7 +402,7 @@ __device__ __forceinline__ void stage_h_wait() { asm volatile("cp.async.wait_gro
 //                                                 a2 (m g, k t+4), a3 (m g+8, k t+4)
 //   B = h from the staged plane (k = row, n = i): b0 (k t, n g) = H[(8ks+t)*PS + 8ni+g], b1 (k t+4, n g)
 // Pair p = warp + 8q -> (mo = p % MB, ni = p / MB); MB divides 8, so all of a warp's pairs share mo (one A fragment).
-template <int NPW>
+template <int NPW, int PASSES>
 __device__ __forceinline__ void wgrad_mma(float (&acc)[NPW][4], const float* __restrict__ gzp, const float* __restrict__ hpl,
                                           int MB, int NB, int warp, int g, int t) {
     const int P = MB * NB;
@@ -421,17 +431,18 @@ __device__ __forceinline__ void wgrad_mma(float (&acc)[NPW][4], const float* __r
 #pragma unroll
         for (int k = 0; k < KG; ++k) {
             const float* ap = pa + 8 * (ks0 + k) * PS;
-            split_tf32(ap[0], ahi[k][0], alo[k][0]);
-            split_tf32(ap[8], ahi[k][1], alo[k][1]);
-            split_tf32(ap[4 * PS], ahi[k][2], alo[k][2]);
-            split_tf32(ap[4 * PS + 8], ahi[k][3], alo[k][3]);
+            split_p<PASSES>(ap[0], ahi[k][0], alo[k][0]);
+            split_p<PASSES>(ap[8], ahi[k][1], alo[k][1]);
+            split_p<PASSES>(ap[4 * PS], ahi[k][2], alo[k][2]);
+            split_p<PASSES>(ap[4 * PS + 8], ahi[k][3], alo[k][3]);
             const float* bp = pb + 8 * (ks0 + k) * PS;
 #pragma unroll
             for (int q = 0; q < NPW; ++q) {
-                split_tf32(on[q] ? bp[nib[q]] : 0.f, bh[k][q][0], bl[k][q][0]);
-                split_tf32(on[q] ? bp[4 * PS + nib[q]] : 0.f, bh[k][q][1], bl[k][q][1]);
+                split_p<PASSES>(on[q] ? bp[nib[q]] : 0.f, bh[k][q][0], bl[k][q][0]);
+                split_p<PASSES>(on[q] ? bp[4 * PS + nib[q]] : 0.f, bh[k][q][1], bl[k][q][1]);
             }
         }
+        if (PASSES == 3) {
 #pragma unroll
         for (int k = 0; k < KG; ++k)
 #pragma unroll
@@ -440,6 +451,7 @@ __device__ __forceinline__ void wgrad_mma(float (&acc)[NPW][4], const float* __r
         for (int k = 0; k < KG; ++k)
 #pragma unroll
             for (int q = 0; q < NPW; ++q) mma_tf32(tmp[k][q], ahi[k], bl[k][q][0], bl[k][q][1]);
+        }
 #pragma unroll
         for (int k = 0; k < KG; ++k)
 #pragma unroll
@@ -496,7 +508,7 @@ __device__ __forceinline__ void bias_combine(float* __restrict__ db, const float
 }
 
 // AE = 0: magnitude autoencoder, AE = 1: phase autoencoder.  NT1 = n-tiles of the input track (4: T <= 32, 8: T <= 64).
-template <int NT1, int AE>
+template <int NT1, int AE, int PASSES>
 __global__ void __launch_bounds__(BWD_WARPS * 32, 1)
 ae_bwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __restrict__ spec, int B,
                   const float* __restrict__ save, const float* __restrict__ mag_hat, const float* __restrict__ phs_hat,
@@ -584,14 +596,14 @@ ae_bwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
         {                                                                                                                   \
             float c[2][NT_][4];                                                                                             \
             ST_T(1)                                                                                                         \
-            layer_mma_T<NT_>(MYCUR, KS_, W + mg.off[L], mg.ld[L], c, gq, t);                                                \
+            layer_mma_T<NT_, PASSES>(MYCUR, KS_, W + mg.off[L], mg.ld[L], c, gq, t);                                                \
             ST_T(2)                                                                                                         \
             bias_partial(bpart, MYCUR, OUTP_, warp, lane);                                                                  \
             ST_T(5)                                                                                                         \
             stage_h_wait();                                                                                                 \
             __syncthreads();                                                                                                \
             ST_T(3)                                                                                                         \
-            wgrad_mma<NPW_>(ACC, CUR, NXT, MB_, NB_, warp, gq, t);                                                          \
+            wgrad_mma<NPW_, PASSES>(ACC, CUR, NXT, MB_, NB_, warp, gq, t);                                                          \
             bias_combine(dbias + L * 64, bpart, OUTP_, threadIdx.x);                                                        \
             ST_T(4)                                                                                                         \
             __syncthreads();                                                                                                \
@@ -622,14 +634,14 @@ ae_bwd_mma_kernel(StDims d, AeGeom g, MmaGeom mg, AeParams p, const float* __res
         {
             float c[2][NT1][4];
             ST_T(1)
-            layer_mma_T<NT1>(my0, 8, W + mg.off[0], mg.ld[0], c, gq, t);
+            layer_mma_T<NT1, PASSES>(my0, 8, W + mg.off[0], mg.ld[0], c, gq, t);
             ST_T(2)
             bias_partial(bpart, my0, 64, warp, lane);
             ST_T(5)
             stage_h_wait();
             __syncthreads();
             ST_T(3)
-            wgrad_mma<4>(a1, plane0, plane1, 4, ks1, warp, gq, t);
+            wgrad_mma<4, PASSES>(a1, plane0, plane1, 4, ks1, warp, gq, t);
             bias_combine(dbias + 0 * 64, bpart, 64, threadIdx.x);
             ST_T(4)
             __syncthreads();
@@ -715,18 +727,18 @@ MmaGeom build_mma_geom(const AeGeom& g, int nt9) {
     return mg;
 }
 
-template <int NT9>
+template <int NT9, int PASSES>
 void launch_fwd_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const AeParams& pm, const AeParams& pp, const float* spec,
                      const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo, float* save_m,
                      float* save_p, int grid, size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(ae_fwd_mma_kernel<NT9, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ae_fwd_mma_kernel<NT9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(ae_fwd_mma_kernel<NT9, 0, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(ae_fwd_mma_kernel<NT9, 1, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         configured = true;
     }
-    ae_fwd_mma_kernel<NT9, 0><<<grid, FWD_WARPS * 32, smem, s>>>(d, g, mg, pm, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m);
-    ae_fwd_mma_kernel<NT9, 1><<<grid, FWD_WARPS * 32, smem, s>>>(d, g, mg, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_p);
+    ae_fwd_mma_kernel<NT9, 0, PASSES><<<grid, FWD_WARPS * 32, smem, s>>>(d, g, mg, pm, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m);
+    ae_fwd_mma_kernel<NT9, 1, PASSES><<<grid, FWD_WARPS * 32, smem, s>>>(d, g, mg, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_p);
 }
 
 }  // namespace
@@ -737,7 +749,7 @@ int st_ae_mma_record_floats(const StDims& d) { return 272 + 8 * (d.OT <= 16 ? 2 
 // Returns false when the geometry is outside what the tensor-core kernels cover (caller uses the SIMT kernel).
 bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
                               const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo,
-                              float* save_m, float* save_p, int sm_count, cudaStream_t s) {
+                              float* save_m, float* save_p, int sm_count, cudaStream_t s, int passes) {
     if (d.T > 64 || d.OT > 64 || d.K > 16) return false;
     const int nt9 = d.OT <= 16 ? 2 : (d.OT <= 32 ? 4 : 8);
     const MmaGeom mg = build_mma_geom(g, nt9);
@@ -745,27 +757,28 @@ bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& 
     if (smem > 227 * 1024) return false;
     const long tiles = ((long)B * d.F + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
     const int grid = (int)std::min<long>((tiles + FWD_WARPS - 1) / FWD_WARPS, sm_count);
-    if (nt9 == 2) launch_fwd_pair<2>(d, g, mg, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m, save_p, grid, smem, s);
-    else if (nt9 == 4) launch_fwd_pair<4>(d, g, mg, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m, save_p, grid, smem, s);
-    else launch_fwd_pair<8>(d, g, mg, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m, save_p, grid, smem, s);
+#define ST_FWD_PAIR(NT9_, P_) launch_fwd_pair<NT9_, P_>(d, g, mg, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, save_m, save_p, grid, smem, s)
+    if (passes == 1) { if (nt9 == 2) ST_FWD_PAIR(2, 1); else if (nt9 == 4) ST_FWD_PAIR(4, 1); else ST_FWD_PAIR(8, 1); }
+    else             { if (nt9 == 2) ST_FWD_PAIR(2, 3); else if (nt9 == 4) ST_FWD_PAIR(4, 3); else ST_FWD_PAIR(8, 3); }
+#undef ST_FWD_PAIR
     return true;
 }
 
 namespace {
-template <int NT1>
+template <int NT1, int PASSES>
 void launch_bwd_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const AeParams& pm, const AeParams& pp, const float* spec,
                      int B, const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat, const float* g_ri,
                      const float* g_mag_hat, const float* g_mag, float* tail_ws, float* g_spec, float* g_spec_lo, float* partials,
                      long long* timing, int grid, size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(ae_bwd_mma_kernel<NT1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ae_bwd_mma_kernel<NT1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(ae_bwd_mma_kernel<NT1, 0, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(ae_bwd_mma_kernel<NT1, 1, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         configured = true;
     }
-    ae_bwd_mma_kernel<NT1, 0><<<grid, BWD_WARPS * 32, smem, s>>>(d, g, mg, pm, spec, B, save_m, mag_hat, phs_hat, g_ri, g_mag_hat,
+    ae_bwd_mma_kernel<NT1, 0, PASSES><<<grid, BWD_WARPS * 32, smem, s>>>(d, g, mg, pm, spec, B, save_m, mag_hat, phs_hat, g_ri, g_mag_hat,
                                                                  g_mag, tail_ws, g_spec, g_spec_lo, partials, timing);
-    ae_bwd_mma_kernel<NT1, 1><<<grid, BWD_WARPS * 32, smem, s>>>(d, g, mg, pp, spec, B, save_p, mag_hat, phs_hat, g_ri, g_mag_hat,
+    ae_bwd_mma_kernel<NT1, 1, PASSES><<<grid, BWD_WARPS * 32, smem, s>>>(d, g, mg, pp, spec, B, save_p, mag_hat, phs_hat, g_ri, g_mag_hat,
                                                                  g_mag, tail_ws, g_spec, g_spec_lo, partials, timing ? timing + 8 : nullptr);
 }
 }  // namespace
@@ -776,18 +789,17 @@ void launch_bwd_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const 
 int st_launch_ae_backward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, int B,
                               const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat,
                               const float* g_ri, const float* g_mag_hat, const float* g_mag, float* tail_ws, float* g_spec,
-                              float* g_spec_lo, float* partials, long long* timing, int sm_count, cudaStream_t s) {
+                              float* g_spec_lo, float* partials, long long* timing, int sm_count, cudaStream_t s, int passes) {
     if (d.T > 64 || d.OT > 16 || d.K > 16) return 0;
     const MmaGeom mg = build_mma_geom(g, 2);
     const size_t smem = sizeof(float) * ((size_t)mg.wfloats + mg.bfloats + 2 * (size_t)CTA_ROWS * PS + ST_AE_LAYERS * 64 + BWD_WARPS * 64);
     if (smem > 227 * 1024) return 0;
     const long nct = ((long)B * d.F + CTA_ROWS - 1) / CTA_ROWS;
     const int grid = (int)std::min<long>(nct, sm_count);
-    if (mg.ks[0] <= 4)
-        launch_bwd_pair<4>(d, g, mg, pm, pp, spec, B, save_m, save_p, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, tail_ws, g_spec,
-                           g_spec_lo, partials, timing, grid, smem, s);
-    else
-        launch_bwd_pair<8>(d, g, mg, pm, pp, spec, B, save_m, save_p, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, tail_ws, g_spec,
-                           g_spec_lo, partials, timing, grid, smem, s);
+#define ST_BWD_PAIR(NT1_, P_) launch_bwd_pair<NT1_, P_>(d, g, mg, pm, pp, spec, B, save_m, save_p, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, \
+                                                         tail_ws, g_spec, g_spec_lo, partials, timing, grid, smem, s)
+    if (passes == 1) { if (mg.ks[0] <= 4) ST_BWD_PAIR(4, 1); else ST_BWD_PAIR(8, 1); }
+    else             { if (mg.ks[0] <= 4) ST_BWD_PAIR(4, 3); else ST_BWD_PAIR(8, 3); }
+#undef ST_BWD_PAIR
     return grid;
 }

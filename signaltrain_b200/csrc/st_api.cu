@@ -27,6 +27,9 @@ struct st_handle {
     float *spec = nullptr, *ri = nullptr, *ri_lo = nullptr, *fo = nullptr;
     float *mag_hat_ws = nullptr, *phs_hat_ws = nullptr, *gwave = nullptr, *gwave_lo = nullptr, *g_ri = nullptr;
     float *g_spec = nullptr, *g_spec_lo = nullptr;
+    int passes = 3;               // st_set_precision: 3 = fp32 fidelity (3xTF32 GEMMs, exact-fp32 FFMA2 autoencoders);
+                                  // 1 = reduced precision (single-pass TF32 products in the GEMMs and the autoencoder chains)
+    bool tf32_ae_mma = true;      // reduced mode: autoencoders on the single-pass mma.sync kernels (ST_TF32_AE_FFMA2=1 keeps FFMA2)
     bool use_tc = true;           // tcgen05/TMA GEMMs (falls back to the FFMA GEMM per call when a shape is not covered)
     float *part_a = nullptr, *part_s = nullptr, *ae_part = nullptr;
     float *yhat_ws = nullptr, *gy_ws = nullptr, *gmh_ws = nullptr;   // fused train step only
@@ -198,6 +201,7 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     if (const char* e = getenv("ST_DISABLE_MMA_BACKWARD")) h->use_mma_bwd = !(e[0] == '1');
     if (const char* e = getenv("ST_ENABLE_TCGEN05_AE")) h->use_tc_ae = (e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_FFMA2_AE")) h->use_f2_fwd = !(e[0] == '1');
+    if (const char* e = getenv("ST_TF32_AE_FFMA2")) h->tf32_ae_mma = !(e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_FFMA2_AE_BWD")) h->use_f2_bwd = !(e[0] == '1');
     build_geom(d, h->g);
     if (st_ae_configure(h, d, h->g)) {
@@ -375,7 +379,7 @@ static int analysis_only(st_handle* h, const float* x, const float* Wr, const fl
     int r = -1;
     if (h->use_tc) {
         TcOperand A{h->xpad, h->xpad_lo, MT, d.N, d.H}, W{h->wcat, h->wcat_lo, F2, d.N, d.N};
-        r = st_launch_gemm_tc(false, false, A, W, h->spec, F2, MT, F2, d.N, 1, 0, true, h->sm_count, s);
+        r = st_launch_gemm_tc(false, false, A, W, h->spec, F2, MT, F2, d.N, 1, 0, h->passes == 3, h->sm_count, s, h->passes);
     }
     if (r < 0) {
         GemmOperand A{h->xpad, h->xpad_lo, d.H}, W{h->wcat, h->wcat_lo, d.N};
@@ -399,7 +403,7 @@ static int synthesis_only(st_handle* h, const float* re, const float* im, const 
     int r = -1;
     if (h->use_tc) {
         TcOperand R{h->ri, h->ri_lo, MO, F2, F2}, S{h->sfold, h->sfold_lo, F2, d.N, d.N};
-        r = st_launch_gemm_tc(false, true, R, S, h->fo, d.N, MO, d.N, F2, 1, 0, true, h->sm_count, s);
+        r = st_launch_gemm_tc(false, true, R, S, h->fo, d.N, MO, d.N, F2, 1, 0, h->passes == 3, h->sm_count, s, h->passes);
     }
     if (r < 0) {
         GemmOperand R{h->ri, h->ri_lo, F2}, S{h->sfold, h->sfold_lo, d.N};
@@ -443,7 +447,7 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         int r = -1;
         if (h->use_tc) {
             TcOperand A{h->xpad, h->xpad_lo, MT, d.N, d.H}, W{h->wcat, h->wcat_lo, F2, d.N, d.N};
-            r = st_launch_gemm_tc(false, false, A, W, h->spec, F2, MT, F2, d.N, 1, 0, /*promote=*/true, h->sm_count, s);
+            r = st_launch_gemm_tc(false, false, A, W, h->spec, F2, MT, F2, d.N, 1, 0, /*promote=*/h->passes == 3, h->sm_count, s, h->passes);
         }
         if (r < 0) {
             GemmOperand A{h->xpad, h->xpad_lo, d.H}, W{h->wcat, h->wcat_lo, d.N};
@@ -463,13 +467,14 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
             done = st_launch_ae_forward_tc(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
                                            save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->ae_timing ? h->ae_timing + 16 : nullptr,
                                            h->sm_count, s);
-        if (!acts && !done && h->use_f2_fwd)
+        // reduced-precision mode: the mma.sync chain with ONE TF32 MMA per product (no split) beats the exact FFMA2 chain
+        if (!acts && !done && h->use_f2_fwd && !(h->passes == 1 && h->tf32_ae_mma))
             done = st_launch_ae_forward_f2(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
                                            save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr,
                                            h->ae_timing ? h->ae_timing + 16 : nullptr, h->sm_count, s);
         if (!acts && !done)
             done = st_launch_ae_forward_mma(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
-                                            save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->sm_count, s);
+                                            save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->sm_count, s, h->passes);
         if (!done)
             st_launch_ae_forward(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo, acts,
                                  h->ae_grid, s);
@@ -484,7 +489,7 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         int r = -1;
         if (h->use_tc) {
             TcOperand R{h->ri, h->ri_lo, MO, F2, F2}, S{h->sfold, h->sfold_lo, F2, d.N, d.N};
-            r = st_launch_gemm_tc(false, true, R, S, h->fo, d.N, MO, d.N, F2, 1, 0, /*promote=*/true, h->sm_count, s);
+            r = st_launch_gemm_tc(false, true, R, S, h->fo, d.N, MO, d.N, F2, 1, 0, /*promote=*/h->passes == 3, h->sm_count, s, h->passes);
         }
         if (r < 0) {
             GemmOperand R{h->ri, h->ri_lo, F2}, S{h->sfold, h->sfold_lo, d.N};
@@ -558,7 +563,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         int r = -1;
         if (h->use_tc) {
             TcOperand G{h->gwave, h->gwave_lo, MO, d.N, d.H}, S{h->sfold, h->sfold_lo, F2, d.N, d.N};
-            r = st_launch_gemm_tc(false, false, G, S, h->g_ri, F2, MO, F2, d.N, 1, 0, /*promote=*/false, h->sm_count, s);
+            r = st_launch_gemm_tc(false, false, G, S, h->g_ri, F2, MO, F2, d.N, 1, 0, /*promote=*/false, h->sm_count, s, h->passes);
         }
         if (r < 0) {
             GemmOperand G{h->gwave, h->gwave_lo, d.H}, S{h->sfold, h->sfold_lo, d.N};
@@ -571,7 +576,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         if (h->use_tc) {
             TcOperand R{h->ri, h->ri_lo, MO, F2, F2}, G{h->gwave, h->gwave_lo, MO, d.N, d.H};
             ss = st_launch_gemm_tc(true, true, R, G, h->part_s, d.N, F2, d.N, MO, std::min(kMaxSplits, std::max(1, MO / 512)), plane,
-                                   /*promote=*/false, h->sm_count, s);
+                                   /*promote=*/false, h->sm_count, s, h->passes);
         }
         if (ss < 0) {
             GemmOperand R{h->ri, h->ri_lo, F2}, G{h->gwave, h->gwave_lo, d.H};
@@ -595,12 +600,12 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         AeParams pm, pp;
         split_params(params, pm, pp);
         int gr = 0;
-        if (h->have_saves && h->use_f2_bwd)
+        if (h->have_saves && h->use_f2_bwd && !(h->passes == 1 && h->tf32_ae_mma))
             gr = st_launch_ae_backward_f2(d, h->g, pm, pp, h->spec, B, h->ae_save_m, h->ae_save_p, h->mag_hat_ws, h->phs_hat_ws,
                                           h->g_ri, g_mag_hat, g_mag, h->gtrack_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_timing, h->sm_count, s);
         if (gr == 0 && h->have_saves)
             gr = st_launch_ae_backward_mma(d, h->g, pm, pp, h->spec, B, h->ae_save_m, h->ae_save_p, h->mag_hat_ws, h->phs_hat_ws,
-                                           h->g_ri, g_mag_hat, g_mag, h->tail_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_timing, h->sm_count, s);
+                                           h->g_ri, g_mag_hat, g_mag, h->tail_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_timing, h->sm_count, s, h->passes);
         if (gr > 0)
             part_ctas = gr;
         else
@@ -631,7 +636,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         if (h->use_tc) {
             TcOperand Gs{h->g_spec, h->g_spec_lo, MT, F2, F2}, X{h->xpad, h->xpad_lo, MT, d.N, d.H};
             sa = st_launch_gemm_tc(true, true, Gs, X, h->part_a, d.N, F2, d.N, MT, std::min(kMaxSplits, std::max(1, MT / 512)), plane,
-                                   /*promote=*/false, h->sm_count, s);
+                                   /*promote=*/false, h->sm_count, s, h->passes);
         }
         if (sa < 0) {
             GemmOperand Gs{h->g_spec, h->g_spec_lo, F2}, X{h->xpad, h->xpad_lo, d.H};
@@ -793,6 +798,18 @@ extern "C" int st_debug_read(st_handle* h, const char* name, float* dst, long n)
     return 0;
 }
 
+extern "C" int st_set_precision(st_handle* h, int mode) {
+    if (!h) return 1;
+    if (mode != ST_PRECISION_FP32 && mode != ST_PRECISION_TF32)
+        return st_fail_msg(h, "st_set_precision: unknown mode %d (0 = fp32, 1 = tf32)", mode);
+    if (mode == ST_PRECISION_TF32 && !h->use_tc)
+        return st_fail_msg(h, "st_set_precision: the reduced-precision mode needs the tcgen05 GEMMs (ST_DISABLE_TCGEN05 is set)");
+    h->passes = mode == ST_PRECISION_TF32 ? 1 : 3;
+    h->fwdB = 0;                  // a backward must not mix modes with the forward that saved its activations
+    return 0;
+}
+extern "C" int st_get_precision(const st_handle* h) { return h ? (h->passes == 1 ? ST_PRECISION_TF32 : ST_PRECISION_FP32) : -1; }
+
 extern "C" int st_set_training(st_handle* h, int on) {
     if (!h) return 1;
     h->training = on != 0;
@@ -832,7 +849,7 @@ extern "C" int st_profile_read(st_handle* h, float* ms, long* calls) {
 //   a_mn / b_mn: 0 = K-major ([rows = M or N][K], leading dim ld), 1 = MN-major ([rows = K][M or N]).
 //   use_tc: 1 = tcgen05/TMA kernel, 0 = FFMA kernel.  Returns the number of split planes written into C
 //   (plane stride = M * ldc), or -1.
-extern "C" int st_debug_gemm(st_handle* h, int use_tc /*0 FFMA, 1 tcgen05, 2 tcgen05 promoted*/, int a_mn, int b_mn, const float* a_hi, const float* a_lo, long a_ld,
+extern "C" int st_debug_gemm(st_handle* h, int use_tc /*0 FFMA, 1 tcgen05, 2 tcgen05 promoted, 3 tcgen05 single-pass TF32 (hi planes only)*/, int a_mn, int b_mn, const float* a_hi, const float* a_lo, long a_ld,
                              const float* b_hi, const float* b_lo, long b_ld, float* C, long ldc, int M, int N, int K,
                              int splits, void* stream) {
     if (!h) return -1;
@@ -841,7 +858,7 @@ extern "C" int st_debug_gemm(st_handle* h, int use_tc /*0 FFMA, 1 tcgen05, 2 tcg
     int r;
     if (use_tc) {
         TcOperand A{a_hi, a_lo, a_mn ? K : M, a_mn ? M : K, a_ld}, B{b_hi, b_lo, b_mn ? K : N, b_mn ? N : K, b_ld};
-        r = st_launch_gemm_tc(a_mn != 0, b_mn != 0, A, B, C, ldc, M, N, K, splits, (long)M * ldc, use_tc == 2, h->sm_count, s);
+        r = st_launch_gemm_tc(a_mn != 0, b_mn != 0, A, B, C, ldc, M, N, K, splits, (long)M * ldc, use_tc == 2, h->sm_count, s, use_tc == 3 ? 1 : 3);
     } else {
         GemmOperand A{a_hi, a_lo, a_ld}, B{b_hi, b_lo, b_ld};
         r = st_launch_gemm(!a_mn, !b_mn, A, B, C, ldc, M, N, K, splits, (long)M * ldc, s);
@@ -903,7 +920,7 @@ extern "C" int st_dct_analysis(st_handle* h, const float* x, const float* w, con
     int r = -1;
     if (h->use_tc) {
         TcOperand A{xh, xl, MT, wsz, hop}, W{wh, wl, sz, wsz, wsz};
-        r = st_launch_gemm_tc(false, false, A, W, tmp, sz, (int)MT, sz, wsz, 1, 0, true, h->sm_count, s);
+        r = st_launch_gemm_tc(false, false, A, W, tmp, sz, (int)MT, sz, wsz, 1, 0, h->passes == 3, h->sm_count, s, h->passes);
     }
     if (r < 0) {
         GemmOperand A{xh, xl, hop}, W{wh, wl, wsz};
@@ -933,7 +950,7 @@ extern "C" int st_dct_synthesis(st_handle* h, const float* x_ft, const float* w,
     int r = -1;
     if (h->use_tc) {
         TcOperand A{ah, al, M, sz, sz}, S{wh, wl, sz, wsz, wsz};
-        r = st_launch_gemm_tc(false, true, A, S, fo, wsz, (int)M, wsz, sz, 1, 0, true, h->sm_count, s);
+        r = st_launch_gemm_tc(false, true, A, S, fo, wsz, (int)M, wsz, sz, 1, 0, h->passes == 3, h->sm_count, s, h->passes);
     }
     if (r < 0) {
         GemmOperand A{ah, al, sz}, S{wh, wl, wsz};

@@ -122,8 +122,9 @@ struct TcOperand {
 int st_tc_pick_bn(int n);
 // returns split planes written, or -1 when the shape is not covered (caller falls back to st_launch_gemm)
 // promote: start a fresh TMEM accumulator every k-block and sum the partials in fp32 registers (forward GEMMs)
+// passes: 3 = exact (hi, lo) operands, 3xTF32 (fp32 fidelity);  1 = hi planes only, single-pass TF32 (reduced precision mode)
 int st_launch_gemm_tc(bool a_mn_major, bool b_mn_major, const TcOperand& A, const TcOperand& B, float* C, long ldc, int M,
-                      int N, int K, int splits, long split_stride, bool promote, int sm_count, cudaStream_t s);
+                      int N, int K, int splits, long split_stride, bool promote, int sm_count, cudaStream_t s, int passes = 3);
 
 // st_ae.cu
 size_t st_ae_fwd_smem(const StDims& d, const AeGeom& g);
@@ -143,7 +144,7 @@ void st_launch_ae_grad_reduce(const AeGeom& g, const float* partials, int ncta, 
 int st_ae_mma_record_floats(const StDims& d);      // floats per row of the saved-activation record
 bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
                               const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri_hi, float* ri_lo,
-                              float* save_m, float* save_p, int sm_count, cudaStream_t s);
+                              float* save_m, float* save_p, int sm_count, cudaStream_t s, int passes = 3);
 
 // st_ae_tc.cu: tcgen05 / TMEM autoencoder forward (same contract and record layout; T <= 32, OT <= 16)
 bool st_launch_ae_forward_tc(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
@@ -156,7 +157,8 @@ bool st_launch_ae_forward_f2(const StDims& d, const AeGeom& g, const AeParams& p
 int st_launch_ae_backward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, int B,
                               const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat,
                               const float* g_ri, const float* g_mag_hat, const float* g_mag, float* tail_ws, float* g_spec_hi,
-                              float* g_spec_lo, float* partials, long long* timing /*nullable: 16 counters*/, int sm_count, cudaStream_t s);
+                              float* g_spec_lo, float* partials, long long* timing /*nullable: 16 counters*/, int sm_count, cudaStream_t s,
+                              int passes = 3);
 
 // st_ae_f2_bwd.cu: warp-specialised packed-fp32 backward from the same records (production path; T <= 32, OT <= 16).
 // Returns the number of per-CTA partial-gradient vectors written (0: geometry not covered).

@@ -86,6 +86,7 @@ struct TcParams {
     int kb_per_chunk;              // k-blocks accumulated in TMEM before promotion to fp32 registers
     long split_stride;
     int stages;
+    int passes;                    // 3: exact (hi, lo) pairs, 3xTF32;  1: hi planes only, one kind::tf32 UMMA per k-step
 };
 
 template <bool A_MN, bool B_MN, bool MC>
@@ -95,7 +96,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-    const uint32_t stage_bytes = 2u * (A_BYTES + b_bytes);
+    const bool exact = p.passes == 3;          // single pass: a stage holds the hi planes only (half the bytes, more stages)
+    const uint32_t stage_bytes = (exact ? 2u : 1u) * (A_BYTES + b_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;                     // [stages]  TMA -> MMA
     uint64_t* empty = bars + p.stages;         // [stages]  MMA -> TMA
@@ -142,39 +144,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sA_hi = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sA_lo = sA_hi + A_BYTES;
-                    uint8_t* sB_hi = sA_lo + A_BYTES;
-                    uint8_t* sB_lo = sB_hi + b_bytes;
+                    uint8_t* sA_lo = sA_hi + A_BYTES;                         // (exact only)
+                    uint8_t* sB_hi = sA_hi + (exact ? 2u : 1u) * A_BYTES;
+                    uint8_t* sB_lo = sB_hi + b_bytes;                         // (exact only)
                     mbar_expect_tx(&full[stage], stage_bytes);
                     const int k0 = kb * BKF;
                     if (!A_MN) {
                         tma_load_2d(sA_hi, &tmAh, &full[stage], k0, m0);
-                        tma_load_2d(sA_lo, &tmAl, &full[stage], k0, m0);
+                        if (exact) tma_load_2d(sA_lo, &tmAl, &full[stage], k0, m0);
                     } else {
 #pragma unroll
                         for (int g = 0; g < BM / 32; ++g) {
                             tma_load_2d(sA_hi + g * 4096, &tmAh, &full[stage], m0 + 32 * g, k0);
-                            tma_load_2d(sA_lo + g * 4096, &tmAl, &full[stage], m0 + 32 * g, k0);
+                            if (exact) tma_load_2d(sA_lo + g * 4096, &tmAl, &full[stage], m0 + 32 * g, k0);
                         }
                     }
                     if (MC) {                 // my half of the B tile, into both CTAs (the peer sends the other half)
                         if (!B_MN) {
                             const int hr = p.BN >> 1;                       // rows per half (a multiple of the 8-row swizzle atom)
                             tma_load_2d_mc(sB_hi + rank * hr * 128, &tmBh, &full[stage], k0, n0 + (int)rank * hr, 0x3);
-                            tma_load_2d_mc(sB_lo + rank * hr * 128, &tmBl, &full[stage], k0, n0 + (int)rank * hr, 0x3);
+                            if (exact) tma_load_2d_mc(sB_lo + rank * hr * 128, &tmBl, &full[stage], k0, n0 + (int)rank * hr, 0x3);
                         } else {
                             for (int g = (int)rank; g < p.BN / 32; g += 2) {
                                 tma_load_2d_mc(sB_hi + g * 4096, &tmBh, &full[stage], n0 + 32 * g, k0, 0x3);
-                                tma_load_2d_mc(sB_lo + g * 4096, &tmBl, &full[stage], n0 + 32 * g, k0, 0x3);
+                                if (exact) tma_load_2d_mc(sB_lo + g * 4096, &tmBl, &full[stage], n0 + 32 * g, k0, 0x3);
                             }
                         }
                     } else if (!B_MN) {
                         tma_load_2d(sB_hi, &tmBh, &full[stage], k0, n0);
-                        tma_load_2d(sB_lo, &tmBl, &full[stage], k0, n0);
+                        if (exact) tma_load_2d(sB_lo, &tmBl, &full[stage], k0, n0);
                     } else {
                         for (int g = 0; g < p.BN / 32; ++g) {
                             tma_load_2d(sB_hi + g * 4096, &tmBh, &full[stage], n0 + 32 * g, k0);
-                            tma_load_2d(sB_lo + g * 4096, &tmBl, &full[stage], n0 + 32 * g, k0);
+                            if (exact) tma_load_2d(sB_lo + g * 4096, &tmBl, &full[stage], n0 + 32 * g, k0);
                         }
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -206,16 +208,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                         mbar_wait(&full[stage], phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t sA_hi = smem_u32(smem + (size_t)stage * stage_bytes);
-                        const uint32_t sA_lo = sA_hi + A_BYTES, sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + b_bytes;
+                        const uint32_t sA_lo = sA_hi + A_BYTES, sB_hi = sA_hi + (exact ? 2u : 1u) * A_BYTES, sB_lo = sB_hi + b_bytes;
 #pragma unroll
                         for (int ks = 0; ks < BKF / 8; ++ks) {
                             const uint32_t ao = A_MN ? ks * 1024 : ks * 32;   // next 8 k: 8 rows of 128 B | 32 B inside the span
                             const uint32_t bo = B_MN ? ks * 1024 : ks * 32;
                             const uint64_t ah = make_desc(sA_hi + ao, A_MN), al = make_desc(sA_lo + ao, A_MN);
                             const uint64_t bh = make_desc(sB_hi + bo, B_MN), bl = make_desc(sB_lo + bo, B_MN);
-                            umma_tf32(tmem_d, al, bh, idesc, accumulate);
-                            umma_tf32(tmem_d, ah, bl, idesc, 1u);
-                            umma_tf32(tmem_d, ah, bh, idesc, 1u);
+                            if (exact) {
+                                umma_tf32(tmem_d, al, bh, idesc, accumulate);
+                                umma_tf32(tmem_d, ah, bl, idesc, 1u);
+                                umma_tf32(tmem_d, ah, bh, idesc, 1u);
+                            } else {
+                                umma_tf32(tmem_d, ah, bh, idesc, accumulate);
+                            }
                             accumulate = 1u;
                         }
                         if (MC) umma_commit_mc(&empty[stage], 0x3);        // ... in BOTH CTAs: each also writes the other's stage
@@ -380,7 +386,8 @@ static int pick_bn_for(int n, int tiles_m, int splits, bool b_mn, int sm_count) 
 // A: K-major -> A.rows = M, A.cols = K;  MN-major -> A.rows = K, A.cols = M.   Same for B with N.
 // Returns the number of split-K planes written, or -1 if this shape cannot take the tensor-core path.
 int st_launch_gemm_tc(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand& B, float* C, long ldc, int M, int N, int K,
-                      int splits, long split_stride, bool promote, int sm_count, cudaStream_t s) {
+                      int splits, long split_stride, bool promote, int sm_count, cudaStream_t s, int passes) {
+    if (passes != 1) passes = 3;
     if (splits < 1) splits = 1;
     const int BN = pick_bn_for(N, (M + BM - 1) / BM, splits, b_mn, sm_count > 0 ? sm_count : 148);
     if (BN == 0) return -1;
@@ -397,8 +404,9 @@ int st_launch_gemm_tc(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand&
     p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.split_stride = split_stride;
     p.kb_per_chunk = promote ? 1 : p.kb_per_split;
-    const size_t stage_bytes = 2 * ((size_t)A_BYTES + (size_t)BN * 128);
-    p.stages = (int)std::min<size_t>(4, (227 * 1024 - 2048) / stage_bytes);
+    p.passes = passes;
+    const size_t stage_bytes = (passes == 3 ? 2 : 1) * ((size_t)A_BYTES + (size_t)BN * 128);
+    p.stages = (int)std::min<size_t>(passes == 3 ? 4 : 5, (227 * 1024 - 2048) / stage_bytes);
     if (p.stages < 2) return -1;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
     // cluster (B-multicast) mode, opt-in (ST_GEMM_MULTICAST=1): measured no gain on the K-major GEMMs and a 25-35 % loss on the

@@ -177,6 +177,20 @@ class Engine:
                  "st_dct_synthesis")
         return wave
 
+    PRECISIONS = {"fp32": 0, "tf32": 1}
+
+    def set_precision(self, mode):
+        """"fp32" (default): 3xTF32 GEMMs + exact-fp32 autoencoder chains, waveforms within 1e-5 of the reference.
+        "tf32": one tensor-core TF32 multiply per product (fp32 storage / accumulation / loss / optimiser) -- the
+        mixed-precision class the reference reaches through apex (train.py:133-136,169,184)."""
+        if mode not in self.PRECISIONS:
+            raise ValueError(f"signaltrain_b200: precision must be one of {sorted(self.PRECISIONS)}, got {mode!r}")
+        self._ok(self.lib.st_set_precision(self.h, self.PRECISIONS[mode]), "st_set_precision")
+
+    @property
+    def precision(self):
+        return {v: k for k, v in self.PRECISIONS.items()}[self.lib.st_get_precision(self.h)]
+
     def set_training(self, on):
         self._ok(self.lib.st_set_training(self.h, int(bool(on))), "st_set_training")
 

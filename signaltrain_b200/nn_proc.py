@@ -85,6 +85,15 @@ class AsymMPAEC(nn.Module):
         self._engines = {}
         self._ticket = 0
         self._last_B = 0
+        self.precision = "fp32"
+
+    def set_precision(self, mode):
+        """"fp32" | "tf32" (Engine.set_precision); applies to existing and future engines of this model."""
+        if mode not in Engine.PRECISIONS:
+            raise ValueError(f"signaltrain_b200: precision must be one of {sorted(Engine.PRECISIONS)}, got {mode!r}")
+        self.precision = mode
+        for eng in self._engines.values():
+            eng.set_precision(mode)
 
     # ---- engine plumbing ---------------------------------------------------------------------
     def _geometry(self, chunk):
@@ -103,6 +112,8 @@ class AsymMPAEC(nn.Module):
         eng = self._engines.get(key)
         if eng is None:
             eng = Engine(self._geometry(x.shape[1]), x.device)
+            if self.precision != "fp32":
+                eng.set_precision(self.precision)
             self._engines[key] = eng
         return eng
 
@@ -165,6 +176,10 @@ class st_model(nn.Module):
 
     def clip_grad_norm_(self):
         return self.mpaec.clip_grad_norm_()
+
+    def set_precision(self, mode):
+        self.mpaec.set_precision(mode)
+        return self
 
     def forward(self, x_cuda, knobs_cuda, return_acts=False):
         return self.mpaec.forward(x_cuda, knobs_cuda, return_acts=return_acts)

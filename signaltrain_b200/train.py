@@ -240,8 +240,12 @@ def train(effect=None, epochs=100, n_data_points=200000, batch_size=20, device=N
     if device.type != "cuda":
         raise RuntimeError("signaltrain_b200.train: this train step runs on a CUDA (B200) device only; "
                            "there is no CPU fallback")
-    if apex_opt not in (None, "O0"):
-        print(f"*** NOTE: apex_opt={apex_opt} ignored; signaltrain_b200 trains in fp32 with split-precision tensor-core math")
+    # the reference's only precision knob (train.py:133-136,169,184): "O0" = fp32; "O1".."O3" = apex mixed precision.
+    # Here: "O0" -> fp32-faithful products (3xTF32); anything else -> single-pass TF32 products, fp32 everything else.
+    precision = "fp32" if apex_opt in (None, "O0") else "tf32"
+    if precision != "fp32":
+        print(f"*** NOTE: apex_opt={apex_opt}: reduced-precision mode (single-pass TF32 tensor-core products; fp32 storage, "
+              "accumulation, loss and optimiser)")
     print(f'SignalTrain (B200) training began at {time.ctime()}. Options:')
     print(f'    epochs = {epochs}, n_data_points = {n_data_points}, batch_size = {batch_size}')
     print(f'    scale_factor = {scale_factor}, shrink_factor = {shrink_factor}')
@@ -254,6 +258,7 @@ def train(effect=None, epochs=100, n_data_points=200000, batch_size=20, device=N
         scale_factor, shrink_factor = rv['scale_factor'], rv['shrink_factor']
         sr = rv['sr']
     model = nn_proc.st_model(scale_factor=scale_factor, shrink_factor=shrink_factor, num_knobs=num_knobs, sr=sr)
+    model.set_precision(precision)
     if state_dict != {}:
         model.load_state_dict(state_dict)
     chunk_size, out_chunk_size = model.in_chunk_size, model.out_chunk_size
