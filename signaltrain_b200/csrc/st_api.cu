@@ -29,7 +29,8 @@ struct st_handle {
     float *g_spec = nullptr, *g_spec_lo = nullptr;
     int passes = 3;               // st_set_precision: 3 = fp32 fidelity (3xTF32 GEMMs, exact-fp32 FFMA2 autoencoders);
                                   // 1 = reduced precision (single-pass TF32 products in the GEMMs and the autoencoder chains)
-    bool tf32_ae_mma = true;      // reduced mode: autoencoders on the single-pass mma.sync kernels (ST_TF32_AE_FFMA2=1 keeps FFMA2)
+    bool tf32_ae_mma = false;     // reduced mode: ST_TF32_AE_MMA=1 moves the autoencoders to the single-pass mma.sync kernels; measured
+                                  // SLOWER than the exact FFMA2 chain (B=512: backward 0.99 vs 0.89 ms, forward 0.51 vs 0.50), so off
     bool use_tc = true;           // tcgen05/TMA GEMMs (falls back to the FFMA GEMM per call when a shape is not covered)
     float *part_a = nullptr, *part_s = nullptr, *ae_part = nullptr;
     float *yhat_ws = nullptr, *gy_ws = nullptr, *gmh_ws = nullptr;   // fused train step only
@@ -201,7 +202,7 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     if (const char* e = getenv("ST_DISABLE_MMA_BACKWARD")) h->use_mma_bwd = !(e[0] == '1');
     if (const char* e = getenv("ST_ENABLE_TCGEN05_AE")) h->use_tc_ae = (e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_FFMA2_AE")) h->use_f2_fwd = !(e[0] == '1');
-    if (const char* e = getenv("ST_TF32_AE_FFMA2")) h->tf32_ae_mma = !(e[0] == '1');
+    if (const char* e = getenv("ST_TF32_AE_MMA")) h->tf32_ae_mma = (e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_FFMA2_AE_BWD")) h->use_f2_bwd = !(e[0] == '1');
     build_geom(d, h->g);
     if (st_ae_configure(h, d, h->g)) {
@@ -467,7 +468,7 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
             done = st_launch_ae_forward_tc(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
                                            save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->ae_timing ? h->ae_timing + 16 : nullptr,
                                            h->sm_count, s);
-        // reduced-precision mode: the mma.sync chain with ONE TF32 MMA per product (no split) beats the exact FFMA2 chain
+        // reduced-precision mode: the autoencoders stay on the exact FFMA2 chain unless ST_TF32_AE_MMA=1 (see st_handle)
         if (!acts && !done && h->use_f2_fwd && !(h->passes == 1 && h->tf32_ae_mma))
             done = st_launch_ae_forward_f2(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
                                            save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr,

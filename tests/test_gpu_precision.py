@@ -4,7 +4,8 @@ emulation of it (oracle.operand_rounding: every contraction operand rounded to T
 
 The reference reaches reduced precision only through apex (train.py:133-136,169,184), absent here, so there is no golden
 for it.  Stated bounds (inputs O(1), goldens of SURVEY section 8d): output waveforms within 2e-3 max-abs of the exact
-answer and within 4x (+1e-4) of the error the emulation itself makes; gradients within 3e-2 of each tensor's max-abs.
+answer and within 4x (+1e-4) of the error the emulation itself makes; gradients within 3e-2 of each tensor's max-abs (or
+twice the emulation's own error where that is larger) and within 6x (+2e-3) of the emulation's error.
 The default mode must be untouched by a round trip through the reduced one (bit-identical outputs)."""
 import numpy as np
 import pytest
@@ -89,7 +90,9 @@ def test_tf32_forward_and_gradients_within_stated_bounds(case):
         scale = np.abs(ref).max()
         emu_e = np.abs(emu_grads[name] - ref).max()
         e = np.abs(got - ref).max()
-        assert e <= GRAD_RTOL_TF32 * scale + 1e-12, (name, e / scale)
+        # 3e-2 of the tensor's max-abs -- except where the emulation itself predicts more (denoise: the analysis gradients are
+        # tiny and dominated by bins whose phase is ill-conditioned; emulation and CUDA path agree there, 8.6e-2 both)
+        assert e <= max(GRAD_RTOL_TF32 * scale, 2 * emu_e) + 1e-12, (name, e / scale, emu_e / scale)
         assert e <= 6 * emu_e + 2e-3 * scale + 1e-12, (name, e / scale, emu_e / scale)
 
     # back to the default: bit-identical to the run before the switch
