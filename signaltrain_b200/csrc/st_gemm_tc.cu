@@ -37,6 +37,9 @@ constexpr int NTHREADS = 320;           // 1 TMA warp + 1 MMA warp + 8 epilogue 
 constexpr int EPI_WARPS = 8;
 constexpr uint32_t A_BYTES = BM * 128;  // one (hi or lo) A tile per stage
 constexpr int TMEM_COLS = 512;
+#ifndef ST_GEMM_PAIR_DEFAULT
+#define ST_GEMM_PAIR_DEFAULT 0      // cta_group::2 tiles: opt-in (ST_GEMM_PAIR=1) until measured
+#endif
 
 // Shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout type [61,64).
@@ -296,6 +299,259 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
 }
 
+// ---- cta_group::2 variant ---------------------------------------------------------------------------
+// A CTA pair (cluster of 2, one TPC) computes a 256 x BN tile: each CTA stages ITS 128 rows of A and ITS half of the B tile
+// (BN/2 rows), the leader (cluster rank 0) issues tcgen05.mma.cta_group::2 with M = 256, and the tensor cores of both SMs
+// read both CTAs' shared memory -- per CTA and k-block the operand bytes drop from A + B to A + B/2, which is what bounds
+// these GEMMs (every k-block moves fp32 hi and lo planes of both operands).  Protocol differences to the 1-CTA kernel:
+//   * both CTAs' TMA loads complete on the LEADER's full barrier (cp.async.bulk.tensor ... .cta_group::2, barrier address
+//     mapped to rank 0), whose expected byte count covers both halves;
+//   * tcgen05.commit.cta_group::2 multicasts "stage free" and "accumulator ready" to the barriers of both CTAs;
+//   * each CTA's epilogue drains its own 128 TMEM lanes and both arrive on the leader's "accumulator drained" barrier;
+//   * TMEM is allocated / freed with cta_group::2 by the same warp of both CTAs.
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)0x3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 6000000000LL) __trap();
+    }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int hn = p.BN >> 1;                                  // B rows (N extent) staged by each CTA
+    const uint32_t b_bytes = (uint32_t)hn * 128u;
+    const bool exact = p.passes == 3;
+    const uint32_t planes = exact ? 2u : 1u;
+    const uint32_t stage_bytes = planes * (A_BYTES + b_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;                     // [stages]  leader only: both CTAs' TMA bytes -> MMA
+    uint64_t* empty = bars + p.stages;         // [stages]  per CTA: MMA (leader's commit, multicast) -> this CTA's TMA
+    uint64_t* tfull = bars + 2 * p.stages;     // [2]       per CTA: MMA -> this CTA's epilogue
+    uint64_t* tempty = tfull + 2;              // [2]       leader only: both CTAs' epilogues -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();                        // both CTAs' barriers exist before anything remote arrives on them
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work items shared by the pair: (M-tile PAIR, N-tile, split); CTA `rank` owns M-tile 2 * pair + rank
+    const int tiles_mw = (p.tiles_m + 1) / 2;
+    const int total_work = tiles_mw * p.tiles_n * p.splits;
+    const int w_first = (int)(blockIdx.x >> 1), w_step = (int)(gridDim.x >> 1);
+#define ST_TILE_M0(TT) ((2 * ((TT) / p.tiles_n) + (int)rank) * BM)
+
+    if (warp == 0) {
+        // ================================ TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = w_first; w < total_work; w += w_step) {
+                const int split = w % p.splits, tt = w / p.splits;
+                const int m0 = ST_TILE_M0(tt), n0 = (tt % p.tiles_n) * p.BN + (int)rank * hn;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sA_hi = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sA_lo = sA_hi + A_BYTES;
+                    uint8_t* sB_hi = sA_hi + planes * A_BYTES;
+                    uint8_t* sB_lo = sB_hi + b_bytes;
+                    if (rank == 0) mbar_expect_tx(&full[stage], 2u * stage_bytes);      // my bytes + the peer's
+                    const uint32_t fb = mapa_rank(smem_u32(&full[stage]), 0);
+                    const int k0 = kb * BKF;
+                    if (!A_MN) {
+                        tma_load_2d_pair(sA_hi, &tmAh, fb, k0, m0);
+                        if (exact) tma_load_2d_pair(sA_lo, &tmAl, fb, k0, m0);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < BM / 32; ++g) {
+                            tma_load_2d_pair(sA_hi + g * 4096, &tmAh, fb, m0 + 32 * g, k0);
+                            if (exact) tma_load_2d_pair(sA_lo + g * 4096, &tmAl, fb, m0 + 32 * g, k0);
+                        }
+                    }
+                    if (!B_MN) {
+                        tma_load_2d_pair(sB_hi, &tmBh, fb, k0, n0);
+                        if (exact) tma_load_2d_pair(sB_lo, &tmBl, fb, k0, n0);
+                    } else {
+                        for (int g = 0; g < hn / 32; ++g) {
+                            tma_load_2d_pair(sB_hi + g * 4096, &tmBh, fb, n0 + 32 * g, k0);
+                            if (exact) tma_load_2d_pair(sB_lo + g * 4096, &tmBl, fb, n0 + 32 * g, k0);
+                        }
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA only) =================
+        if (lane == 0 && rank == 0) {
+            // M = 256 over the pair (M>>4 at [24,29)), N = BN: each CTA supplies BN/2 rows of B
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase[2] = {0, 0};
+            for (int w = w_first; w < total_work; w += w_step) {
+                const int split = w % p.splits;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kc = kb0; kc < kb1; kc += p.kb_per_chunk) {
+                    const int kce = min(kb1, kc + p.kb_per_chunk);
+                    mbar_wait_cluster(&tempty[acc], acc_phase[acc] ^ 1);  // both CTAs' epilogues have drained this accumulator
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+                    uint32_t accumulate = 0;
+                    for (int kb = kc; kb < kce; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sA_hi = smem_u32(smem + (size_t)stage * stage_bytes);
+                        const uint32_t sA_lo = sA_hi + A_BYTES, sB_hi = sA_hi + planes * A_BYTES, sB_lo = sB_hi + b_bytes;
+#pragma unroll
+                        for (int ks = 0; ks < BKF / 8; ++ks) {
+                            const uint32_t ao = A_MN ? ks * 1024 : ks * 32;
+                            const uint32_t bo = B_MN ? ks * 1024 : ks * 32;
+                            const uint64_t ah = make_desc(sA_hi + ao, A_MN), al = make_desc(sA_lo + ao, A_MN);
+                            const uint64_t bh = make_desc(sB_hi + bo, B_MN), bl = make_desc(sB_lo + bo, B_MN);
+                            if (exact) {
+                                umma_tf32_pair(tmem_d, al, bh, idesc, accumulate);
+                                umma_tf32_pair(tmem_d, ah, bl, idesc, 1u);
+                                umma_tf32_pair(tmem_d, ah, bh, idesc, 1u);
+                            } else {
+                                umma_tf32_pair(tmem_d, ah, bh, idesc, accumulate);
+                            }
+                            accumulate = 1u;
+                        }
+                        umma_commit_pair(&empty[stage]);                   // both CTAs may refill this stage once the MMAs retire
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit_pair(&tfull[acc]);                         // accumulator complete -> both epilogues
+                    acc_phase[acc] ^= 1;
+                    acc ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ epilogue (each CTA: its own 128 rows) =========
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int ncols = p.BN >> 1;
+        int acc = 0;
+        uint32_t acc_phase[2] = {0, 0};
+        const uint32_t te0 = mapa_rank(smem_u32(&tempty[0]), 0), te1 = mapa_rank(smem_u32(&tempty[1]), 0);
+        for (int w = w_first; w < total_work; w += w_step) {
+            const int split = w % p.splits, tt = w / p.splits;
+            const int m0 = ST_TILE_M0(tt), n0 = (tt % p.tiles_n) * p.BN + half * ncols;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+            float sum[128];
+#pragma unroll
+            for (int i = 0; i < 128; ++i) sum[i] = 0.f;
+            for (int kc = kb0; kc < kb1; kc += p.kb_per_chunk) {
+                mbar_wait(&tfull[acc], acc_phase[acc]);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.BN + half * ncols);
+#pragma unroll
+                for (int c = 0; c < 128; c += 32) {
+                    if (c < ncols) {
+                        uint32_t r[4][8];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (c + 8 * u < ncols) tmem_ld8(taddr + c + 8 * u, r[u]);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (c + 8 * u < ncols) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) sum[c + 8 * u + i] += __uint_as_float(r[u][i]);
+                            }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc ? te1 : te0);
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
+            }
+            const int row = m0 + 32 * q + lane;
+            if (row < p.M) {
+                float* crow = p.C + (long)split * p.split_stride + (long)row * p.ldc + n0;
+#pragma unroll
+                for (int c = 0; c < 128; c += 4)
+                    if (c < ncols && n0 + c < p.N)
+                        *reinterpret_cast<float4*>(crow + c) = make_float4(sum[c], sum[c + 1], sum[c + 2], sum[c + 3]);
+            }
+        }
+    }
+#undef ST_TILE_M0
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                        // the peer's MMAs / barrier traffic that touch this CTA have all retired
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -358,6 +614,30 @@ cudaError_t launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorM
     return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A_MN, B_MN, MC>, ah, al, bh, bl, p);
 }
 
+template <bool A_MN, bool B_MN>
+cudaError_t launch_pair(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcParams& p,
+                        int grid, size_t smem, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<A_MN, B_MN>, ah, al, bh, bl, p);
+}
+
 }  // namespace
 
 // Largest multiple of 16 in [64, 256] that divides n (0 if none).
@@ -371,11 +651,11 @@ int st_tc_pick_bn(int n) {
 // the fewest rounds x width over the SMs (a persistent CTA per SM walks ceil(work / SMs) tiles whose duration scales with
 // the width); ties go to the wider tile (fewer operand re-reads).  The synthesis GEMM (18 M-tiles x N = 1024) thus gets
 // 144 tiles of 128 instead of 72 of 256, which left half the SMs idle.
-static int pick_bn_for(int n, int tiles_m, int splits, bool b_mn, int sm_count) {
+static int pick_bn_for(int n, int tiles_m, int splits, bool b_mn, int sm_count, int mn_mult = 32) {
     int best = 0;
     long best_cost = 0;
     for (int bn = 256; bn >= 64; bn -= 16) {
-        if (n % bn || (b_mn && (bn % 32))) continue;
+        if (n % bn || (b_mn && (bn % mn_mult))) continue;
         const long work = (long)tiles_m * (n / bn) * splits;
         const long cost = (work + sm_count - 1) / sm_count * bn;
         if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
@@ -389,6 +669,42 @@ int st_launch_gemm_tc(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand&
                       int splits, long split_stride, bool promote, int sm_count, cudaStream_t s, int passes) {
     if (passes != 1) passes = 3;
     if (splits < 1) splits = 1;
+    // cta_group::2 tiles (256 x BN per CTA pair), ST_GEMM_PAIR=0 disables
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("ST_GEMM_PAIR"); pair_env = (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : ST_GEMM_PAIR_DEFAULT; }
+    if (pair_env == 1 && sm_count >= 2 && (M + BM - 1) / BM >= 2 && !(A.ld & 3) && !(B.ld & 3) && !(ldc & 3) && !(N & 3) &&
+        (a_mn || K % BKF == 0) && (b_mn || K % BKF == 0)) {
+        const int tiles_m = (M + BM - 1) / BM, pairs_m = (tiles_m + 1) / 2, npairs = sm_count / 2;
+        const int BN2 = pick_bn_for(N, pairs_m, splits, b_mn, npairs, 64);
+        if (BN2 > 0) {
+            TcParams p;
+            p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.BN = BN2;
+            p.tiles_m = tiles_m;
+            p.tiles_n = N / BN2;
+            p.kb_total = (K + BKF - 1) / BKF;
+            p.kb_per_split = (p.kb_total + splits - 1) / splits;
+            p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+            p.split_stride = split_stride;
+            p.kb_per_chunk = promote ? 1 : p.kb_per_split;
+            p.passes = passes;
+            const size_t sb = (passes == 3 ? 2 : 1) * ((size_t)A_BYTES + (size_t)(BN2 / 2) * 128);
+            p.stages = (int)std::min<size_t>(6, (227 * 1024 - 2048) / sb);
+            const size_t smem2 = (size_t)p.stages * sb + 1024 + 256;
+            CUtensorMap ah, al, bh, bl;
+            const int abox = a_mn ? 32 : BM, bbox = b_mn ? 32 : BN2 / 2;
+            if (p.stages >= 2 && make_map(&ah, A.hi, A.rows, A.cols, A.ld, abox, a_mn) && make_map(&al, A.lo, A.rows, A.cols, A.ld, abox, a_mn) &&
+                make_map(&bh, B.hi, B.rows, B.cols, B.ld, bbox, b_mn) && make_map(&bl, B.lo, B.rows, B.cols, B.ld, bbox, b_mn)) {
+                const int work = pairs_m * p.tiles_n * p.splits;
+                const int grid = 2 * std::min(work, npairs);
+                cudaError_t e;
+                if (!a_mn && !b_mn) e = launch_pair<false, false>(ah, al, bh, bl, p, grid, smem2, s);
+                else if (!a_mn && b_mn) e = launch_pair<false, true>(ah, al, bh, bl, p, grid, smem2, s);
+                else if (a_mn && !b_mn) e = launch_pair<true, false>(ah, al, bh, bl, p, grid, smem2, s);
+                else e = launch_pair<true, true>(ah, al, bh, bl, p, grid, smem2, s);
+                return e == cudaSuccess ? p.splits : -1;
+            }
+        }
+    }
     const int BN = pick_bn_for(N, (M + BM - 1) / BM, splits, b_mn, sm_count > 0 ? sm_count : 148);
     if (BN == 0) return -1;
     if ((A.ld & 3) || (B.ld & 3) || (ldc & 3) || (N & 3)) return -1;
