@@ -38,7 +38,7 @@ constexpr int EPI_WARPS = 8;
 constexpr uint32_t A_BYTES = BM * 128;  // one (hi or lo) A tile per stage
 constexpr int TMEM_COLS = 512;
 #ifndef ST_GEMM_PAIR_DEFAULT
-#define ST_GEMM_PAIR_DEFAULT 0      // cta_group::2 tiles: opt-in (ST_GEMM_PAIR=1) until measured
+#define ST_GEMM_PAIR_DEFAULT 1      // cta_group::2 tiles on by default (measured: the five GEMMs 0.267 -> 0.249 ms; ST_GEMM_PAIR=0 = 1-CTA kernel)
 #endif
 
 // Shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
@@ -92,14 +92,14 @@ struct TcParams {
     int passes;                    // 3: exact (hi, lo) pairs, 3xTF32;  1: hi planes only, one kind::tf32 UMMA per k-step
 };
 
-template <bool A_MN, bool B_MN, bool MC>
+template <bool A_MN, bool B_MN, bool MC, int PASSES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-    const bool exact = p.passes == 3;          // single pass: a stage holds the hi planes only (half the bytes, more stages)
+    constexpr bool exact = PASSES == 3;        // single pass: a stage holds the hi planes only (half the bytes, more stages)
     const uint32_t stage_bytes = (exact ? 2u : 1u) * (A_BYTES + b_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;                     // [stages]  TMA -> MMA
@@ -354,7 +354,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int PASSES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
@@ -362,8 +362,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int hn = p.BN >> 1;                                  // B rows (N extent) staged by each CTA
     const uint32_t b_bytes = (uint32_t)hn * 128u;
-    const bool exact = p.passes == 3;
-    const uint32_t planes = exact ? 2u : 1u;
+    constexpr bool exact = PASSES == 3;
+    constexpr uint32_t planes = exact ? 2u : 1u;
     const uint32_t stage_bytes = planes * (A_BYTES + b_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;                     // [stages]  leader only: both CTAs' TMA bytes -> MMA
@@ -586,17 +586,17 @@ bool make_map(CUtensorMap* tm, const float* base, long rows, long cols, long ld,
     return r == CUDA_SUCCESS;
 }
 
-template <bool A_MN, bool B_MN, bool MC>
-cudaError_t launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcParams& p,
+template <bool A_MN, bool B_MN, bool MC, int PASSES>
+cudaError_t launch_p(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcParams& p,
                    int grid, size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, MC, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     if (!MC) {
-        gemm_tc_kernel<A_MN, B_MN, MC><<<grid, NTHREADS, smem, s>>>(ah, al, bh, bl, p);
+        gemm_tc_kernel<A_MN, B_MN, MC, PASSES><<<grid, NTHREADS, smem, s>>>(ah, al, bh, bl, p);
         return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg = {};
@@ -611,15 +611,15 @@ cudaError_t launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorM
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A_MN, B_MN, MC>, ah, al, bh, bl, p);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A_MN, B_MN, MC, PASSES>, ah, al, bh, bl, p);
 }
 
-template <bool A_MN, bool B_MN>
-cudaError_t launch_pair(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcParams& p,
+template <bool A_MN, bool B_MN, int PASSES>
+cudaError_t launch_pair_p(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcParams& p,
                         int grid, size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<A_MN, B_MN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -635,7 +635,20 @@ cudaError_t launch_pair(const CUtensorMap& ah, const CUtensorMap& al, const CUte
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<A_MN, B_MN>, ah, al, bh, bl, p);
+    return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<A_MN, B_MN, PASSES>, ah, al, bh, bl, p);
+}
+
+template <bool A_MN, bool B_MN, bool MC>
+cudaError_t launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcParams& p,
+                   int grid, size_t smem, cudaStream_t s) {
+    return p.passes == 3 ? launch_p<A_MN, B_MN, MC, 3>(ah, al, bh, bl, p, grid, smem, s)
+                         : launch_p<A_MN, B_MN, MC, 1>(ah, al, bh, bl, p, grid, smem, s);
+}
+template <bool A_MN, bool B_MN>
+cudaError_t launch_pair(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcParams& p,
+                        int grid, size_t smem, cudaStream_t s) {
+    return p.passes == 3 ? launch_pair_p<A_MN, B_MN, 3>(ah, al, bh, bl, p, grid, smem, s)
+                         : launch_pair_p<A_MN, B_MN, 1>(ah, al, bh, bl, p, grid, smem, s);
 }
 
 }  // namespace
@@ -675,17 +688,34 @@ int st_launch_gemm_tc(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand&
     if (pair_env == 1 && sm_count >= 2 && (M + BM - 1) / BM >= 2 && !(A.ld & 3) && !(B.ld & 3) && !(ldc & 3) && !(N & 3) &&
         (a_mn || K % BKF == 0) && (b_mn || K % BKF == 0)) {
         const int tiles_m = (M + BM - 1) / BM, pairs_m = (tiles_m + 1) / 2, npairs = sm_count / 2;
-        const int BN2 = pick_bn_for(N, pairs_m, splits, b_mn, npairs, 64);
+        // tile width and split count together: minimise the operand bytes one CTA pulls in over its rounds of work items
+        // (A tile + half B tile per k-block, plus the tile's store), the quantity these GEMMs are bound by
+        const int kb_total = (K + BKF - 1) / BKF;
+        int BN2 = 0, SP2 = 1;
+        double best = 0;
+        for (int bn = 256; bn >= 64; bn -= 16) {
+            if (N % bn || (b_mn ? (bn % 64) : ((bn / 2) % 8))) continue;
+            for (int sp = splits; sp >= 1; --sp) {
+                const int kbps = (kb_total + sp - 1) / sp;
+                if ((kb_total + kbps - 1) / kbps != sp) continue;
+                if (sp < splits && 2 * sp < splits) break;            // keep at least half the requested split-K parallelism
+                const long work = (long)pairs_m * (N / bn) * sp;
+                const long rounds = (work + npairs - 1) / npairs;
+                const double cost = (double)rounds * ((double)kbps * (A_BYTES + bn / 2 * 128) + 0.5 * BM * bn * 4 + 8192.0);
+                if (BN2 == 0 || cost < best) { BN2 = bn; SP2 = sp; best = cost; }
+            }
+        }
         if (BN2 > 0) {
             TcParams p;
             p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.BN = BN2;
             p.tiles_m = tiles_m;
             p.tiles_n = N / BN2;
-            p.kb_total = (K + BKF - 1) / BKF;
-            p.kb_per_split = (p.kb_total + splits - 1) / splits;
+            p.kb_total = kb_total;
+            p.kb_per_split = (p.kb_total + SP2 - 1) / SP2;
             p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
             p.split_stride = split_stride;
-            p.kb_per_chunk = promote ? 1 : p.kb_per_split;
+            // promoted accumulation every TWO k-blocks (24 MMA steps): the pair's "accumulator drained" handshake crosses SMs
+            p.kb_per_chunk = promote ? 2 : p.kb_per_split;
             p.passes = passes;
             const size_t sb = (passes == 3 ? 2 : 1) * ((size_t)A_BYTES + (size_t)(BN2 / 2) * 128);
             p.stages = (int)std::min<size_t>(6, (227 * 1024 - 2048) / sb);
