@@ -29,6 +29,8 @@ struct st_handle {
     float *g_spec = nullptr, *g_spec_lo = nullptr;
     int passes = 3;               // st_set_precision: 3 = fp32 fidelity (3xTF32 GEMMs, exact-fp32 FFMA2 autoencoders);
                                   // 1 = reduced precision (single-pass TF32 products in the GEMMs and the autoencoder chains)
+    bool fuse_tail = true;        // st_train_step: fused overlap-add + loss + padded gradient kernel and fused finalize + L1 norm
+                                  // (ST_DISABLE_FUSED_TAIL=1 -> the separate kernels the piecewise entry points use)
     bool tf32_ae_mma = false;     // reduced mode: ST_TF32_AE_MMA=1 moves the autoencoders to the single-pass mma.sync kernels; measured
                                   // SLOWER than the exact FFMA2 chain (B=512: backward 0.99 vs 0.89 ms, forward 0.51 vs 0.50), so off
     bool use_tc = true;           // tcgen05/TMA GEMMs (falls back to the FFMA GEMM per call when a shape is not covered)
@@ -202,6 +204,7 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     if (const char* e = getenv("ST_DISABLE_MMA_BACKWARD")) h->use_mma_bwd = !(e[0] == '1');
     if (const char* e = getenv("ST_ENABLE_TCGEN05_AE")) h->use_tc_ae = (e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_FFMA2_AE")) h->use_f2_fwd = !(e[0] == '1');
+    if (const char* e = getenv("ST_DISABLE_FUSED_TAIL")) h->fuse_tail = !(e[0] == '1');
     if (const char* e = getenv("ST_TF32_AE_MMA")) h->tf32_ae_mma = (e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_FFMA2_AE_BWD")) h->use_f2_bwd = !(e[0] == '1');
     build_geom(d, h->g);
@@ -498,7 +501,7 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         }
     }
     ST_LAUNCH_OK(h);
-    {
+    if (y_hat) {       // st_train_step passes NULL: its fused tail kernel does the overlap-add together with the loss
         StageScope sc(h, SG_OLA, 1, s);
         st_launch_overlap_add(d, h->fo, x, B, y_hat, acts ? acts[28] : nullptr, acts ? acts[29] : nullptr, s);
     }
@@ -542,8 +545,11 @@ extern "C" int st_mae(st_handle* h, const float* a, const float* b, long n, floa
 
 // phase: 0 = the whole backward; 1 = "begin": up to and including the FINAL synthesis gradients (grads[2], grads[3]), so a
 // data-parallel caller can start their allreduce; 2 = "finish": the autoencoders and the analysis gradients.
+// fused_clip (st_train_step only): gwave already holds the padded 2*dL/dy_hat (written by the fused forward tail), and the
+// final DFT-gradient pass also produces the L1 norm / clip coefficient for the Adam launch that follows.
 static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat, int B,
-                         const float* const* params, float* const* grads, cudaStream_t s, int phase = 0) {
+                         const float* const* params, float* const* grads, cudaStream_t s, int phase = 0,
+                         const st_adam* fused_clip = nullptr) {
     const StDims& d = h->d;
     if (B != h->fwdB || B > h->maxB)
         return st_fail_msg(h, "st_backward: batch %d does not match the preceding st_forward (%d)", B, h->fwdB);
@@ -553,7 +559,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
     int ss = -1, sa = -1;
     if (phase != 2) {
     // adjoint of (*2, trim [N:-N]): zero-padded 2*g
-    {
+    if (!fused_clip) {
         StageScope sc(h, SG_PAD_G, 1, s);
         // adjoint of (*2, trim [N:-N]): zero-padded 2*g, window stride Sg = OTp*H
         st_launch_pad_split(g_y_hat, h->gwave, h->gwave_lo, B, d.L, d.N, d.Sg, 2.0f, s);
@@ -647,7 +653,12 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
     ST_LAUNCH_OK(h);
     {
         StageScope sc(h, SG_FINALIZE, 1, s);
-        st_launch_finalize_dft_grads(d, h->part_a, h->part_s, sa, ss, grads[0], grads[1], grads[2], grads[3], phase == 2 ? 1 : 3, s);
+        if (fused_clip && phase == 0)
+            st_launch_finalize_norm(d, h->part_a, h->part_s, sa, ss, grads[0], grads[1], grads[2], grads[3], fused_clip->grad_scale,
+                                    fused_clip->max_norm, h->small + SM_TOTAL_NORM, h->small + SM_COEF, h->small + SM_NORM,
+                                    h->counters + CT_NORM, s);
+        else
+            st_launch_finalize_dft_grads(d, h->part_a, h->part_s, sa, ss, grads[0], grads[1], grads[2], grads[3], phase == 2 ? 1 : 3, s);
     }
     if (beside) ST_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));        // all 40 gradients are complete on the caller's stream
     ST_LAUNCH_OK(h);
@@ -702,11 +713,12 @@ extern "C" int st_clip_grad_norm(st_handle* h, float* const* grads, float max_no
 }
 
 static int adam_impl(st_handle* h, float* const* params, const float* const* grads, float* const* m, float* const* v,
-                     const st_adam* hp, bool live_only, cudaStream_t s) {
+                     const st_adam* hp, bool live_only, cudaStream_t s, bool coef_ready = false) {
     if (hp->step < 1) return st_fail_msg(h, "st_adam_step: step must be >= 1 (got %d)", hp->step);
     ST_CUDA_OK(cudaSetDevice(h->device));
     const float* coef = nullptr;
-    if (hp->max_norm > 0.f) {
+    if (hp->max_norm > 0.f && coef_ready) coef = h->small + SM_COEF;      // written by the fused finalize pass of st_train_step
+    if (hp->max_norm > 0.f && !coef_ready) {
         const float* g[4] = {grads[0], grads[1], grads[2], grads[3]};
         {
             StageScope sc(h, SG_L1NORM, 1, s);
@@ -760,6 +772,19 @@ extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const
         return 1;
     cudaStream_t s = (cudaStream_t)stream;
     if (ensure_workspace(h, batch)) return 1;
+    if (h->fuse_tail) {
+        // forward without its overlap-add; one kernel then does overlap-add + residual + loss + both loss gradients and writes
+        // the padded (hi, lo) 2*dL/dy_hat operand; the last DFT-gradient pass also yields the clip coefficient
+        if (forward_impl(h, x, knobs, batch, params, nullptr, nullptr, nullptr, nullptr, s)) return 1;
+        {
+            StageScope sc(h, SG_LOSS, 1, s);
+            st_launch_ola_loss(h->d, h->fo, x, y, h->mag_hat_ws, sbf, l1_coef, batch, loss, h->gwave, h->gwave_lo, h->gmh_ws,
+                               h->small + SM_LOSS, h->counters + CT_LOSS, s);
+        }
+        ST_LAUNCH_OK(h);
+        if (backward_impl(h, h->gy_ws, nullptr, h->gmh_ws, batch, params, grads, s, 0, hp)) return 1;
+        return adam_impl(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/true, s, /*coef_ready=*/true);
+    }
     if (forward_impl(h, x, knobs, batch, params, h->yhat_ws, nullptr, nullptr, nullptr, s)) return 1;
     {
         StageScope sc(h, SG_LOSS, 1, s);

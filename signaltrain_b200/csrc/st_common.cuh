@@ -177,6 +177,14 @@ void st_launch_crop_windows(const float* cx, const float* cy, const long* off, c
 void st_launch_loss(const StDims& d, const float* y_hat, const float* y, const float* mag_hat, const float* sbf,
                     float l1_coef, int B, float* loss, float* g_y_hat, float* g_mag_hat, float* scratch,
                     unsigned* counter, cudaStream_t s);
+// fused forward tail of st_train_step: overlap-add + residual + loss + both loss gradients + padded (hi, lo) 2*dL/dy_hat
+void st_launch_ola_loss(const StDims& d, const float* fo, const float* x, const float* y, const float* mag_hat, const float* sbf,
+                        float l1_coef, int B, float* loss, float* gwave_hi, float* gwave_lo, float* g_mag_hat, float* scratch,
+                        unsigned* counter, cudaStream_t s);
+// fused split-K sum + un-fold of the DFT gradients and their L1 norm / clip coefficient (st_train_step)
+void st_launch_finalize_norm(const StDims& d, const float* pa, const float* ps, int sa, int ss, float* gWr, float* gWi, float* gSr,
+                             float* gSi, float grad_scale, float max_norm, float* norm_out, float* coef_out, float* scratch,
+                             unsigned* counter, cudaStream_t s);
 void st_launch_mae(const float* a, const float* b, long n, float* out, float* scratch, unsigned* counter, cudaStream_t s);
 void st_launch_l1_norm4(const float* const g[4], long n_each, long live_rows_a, long row_len, float grad_scale,
                         float max_norm, float* norm_out, float* coef_out, float* scratch, unsigned* counter, cudaStream_t s);

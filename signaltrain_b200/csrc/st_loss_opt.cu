@@ -101,6 +101,117 @@ loss_kernel(StDims d, const float* __restrict__ y_hat, const float* __restrict__
     });
 }
 
+// Fused tail of the forward for the whole-step entry point (st_train_step): overlap-add + trim + input residual + *2
+// (overlap_add_kernel, st_frontend.cu), log-cosh / weighted-L1 loss with both gradients (loss_kernel above) and the zero-padded
+// 2*dL/dy_hat operand of the synthesis gradient GEMMs (pad_split_kernel), in one pass: y_hat and dL/dy_hat never touch HBM.
+// Same arithmetic per element as the three kernels it replaces; only the summation order of the loss differs.
+__global__ void __launch_bounds__(256)
+ola_loss_kernel(StDims d, const float* __restrict__ fo, const float* __restrict__ x, const float* __restrict__ y,
+                const float* __restrict__ mag_hat, const float* __restrict__ sbf, float l1_coef, int B, float* __restrict__ loss,
+                float* __restrict__ gwave_hi, float* __restrict__ gwave_lo, float* __restrict__ g_m, float* scratch, unsigned* counter) {
+    const long n1 = (long)B * d.L, n2 = (long)B * d.OT * d.F;
+    const float inv1 = 1.f / (float)n1, inv2 = 1.f / (float)n2;
+    const long stride = (long)gridDim.x * blockDim.x;
+    const int l4 = d.L >> 2;
+    float acc[2] = {0.f, 0.f};
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)B * l4; i += stride) {
+        const int b = (int)(i / l4);
+        const int j = (int)(i - (long)b * l4) << 2;
+        const int t_lo = j / d.H + 1;                       // frames covering output sample j (see overlap_add_kernel)
+        int t_hi = (j + d.N) / d.H;
+        if (t_hi > d.OT - 1) t_hi = d.OT - 1;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = t_lo; t <= t_hi; ++t) {
+            const float4 v = *reinterpret_cast<const float4*>(fo + ((long)b * d.OTp + t) * d.N + (j + d.N - t * d.H));
+            w.x += v.x; w.y += v.y; w.z += v.z; w.w += v.w;
+        }
+        const float4 xr = *reinterpret_cast<const float4*>(x + (long)b * d.C + (d.C - d.L) + j);
+        const float4 yh = make_float4((w.x + xr.x * 0.5f) * 2.f, (w.y + xr.y * 0.5f) * 2.f, (w.z + xr.z * 0.5f) * 2.f,
+                                      (w.w + xr.w * 0.5f) * 2.f);                        // nn_proc.py:332,340
+        const float4 a = *reinterpret_cast<const float4*>(y + (long)b * d.L + j);
+        const float dx = a.x - yh.x, dy = a.y - yh.y, dz = a.z - yh.z, dw = a.w - yh.w;
+        acc[0] += (logcosh_f(dx) + logcosh_f(dy)) + (logcosh_f(dz) + logcosh_f(dw));
+        float4 hi, lo;                                       // 2 * dL/dy_hat = 2 * (-tanh(y - y_hat) / n), as a tf32 pair
+        st_split_tf32(-tanhf(dx) * inv1 * 2.f, hi.x, lo.x);
+        st_split_tf32(-tanhf(dy) * inv1 * 2.f, hi.y, lo.y);
+        st_split_tf32(-tanhf(dz) * inv1 * 2.f, hi.z, lo.z);
+        st_split_tf32(-tanhf(dw) * inv1 * 2.f, hi.w, lo.w);
+        const long o = (long)b * d.Sg + d.N + j;             // the pad columns around it stay zero (zeroed at allocation)
+        *reinterpret_cast<float4*>(gwave_hi + o) = hi;
+        *reinterpret_cast<float4*>(gwave_lo + o) = lo;
+    }
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const float s = sbf ? sbf[i % d.F] : 1.f;
+        const float v = mag_hat[i] * s;
+        acc[1] += fabsf(v);
+        g_m[i] = l1_coef * inv2 * s * (float)((v > 0.f) - (v < 0.f));
+    }
+    grid_finish<2>(acc, scratch, counter, [&](const double* s) {
+        loss[0] = (float)(s[0] / (double)n1 + (double)l1_coef * s[1] / (double)n2);
+    });
+}
+
+// Fused split-K sum + Hermitian un-fold of the four DFT gradients (finalize_dft_grads_kernel, st_frontend.cu) and the L1
+// norm / clip coefficient over them (l1_norm4_kernel below) for st_train_step: the gradients are summed while they are
+// written instead of being read back by a second kernel.
+__global__ void __launch_bounds__(256)
+finalize_norm_kernel(StDims d, const float* __restrict__ pa, const float* __restrict__ ps, int sa, int ss, float* __restrict__ gWr,
+                     float* __restrict__ gWi, float* __restrict__ gSr, float* __restrict__ gSi, float grad_scale, float max_norm,
+                     float* __restrict__ norm_out, float* __restrict__ coef_out, float* scratch, unsigned* counter) {
+    const int n4 = d.N >> 2;
+    const long plane = 2L * d.Fp * d.N;
+    const long total = (long)d.N * n4;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[1] = {0.f};
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / n4);
+        const int c = (int)(i - (long)k * n4) << 2;
+        const long o = (long)k * d.N + c;
+        if (k >= d.F) {                                      // dead analysis rows (cls_fe_dft.py:55-56)
+            *reinterpret_cast<float4*>(gWr + o) = z4;
+            *reinterpret_cast<float4*>(gWi + o) = z4;
+            continue;
+        }
+        float4 ar = z4, ai = z4, sr = z4, si = z4;
+        for (int s = 0; s < sa; ++s) {
+            const float4 a = *reinterpret_cast<const float4*>(pa + s * plane + (long)k * d.N + c);
+            const float4 b = *reinterpret_cast<const float4*>(pa + s * plane + (long)(d.Fp + k) * d.N + c);
+            ar.x += a.x; ar.y += a.y; ar.z += a.z; ar.w += a.w;
+            ai.x += b.x; ai.y += b.y; ai.z += b.z; ai.w += b.w;
+        }
+        for (int s = 0; s < ss; ++s) {
+            const float4 a = *reinterpret_cast<const float4*>(ps + s * plane + (long)k * d.N + c);
+            const float4 b = *reinterpret_cast<const float4*>(ps + s * plane + (long)(d.Fp + k) * d.N + c);
+            sr.x += a.x; sr.y += a.y; sr.z += a.z; sr.w += a.w;
+            si.x += b.x; si.y += b.y; si.z += b.z; si.w += b.w;
+        }
+        *reinterpret_cast<float4*>(gWr + o) = ar;
+        *reinterpret_cast<float4*>(gWi + o) = ai;
+        *reinterpret_cast<float4*>(gSr + o) = sr;
+        *reinterpret_cast<float4*>(gSi + o) = si;
+        const float na = (fabsf(ar.x) + fabsf(ar.y)) + (fabsf(ar.z) + fabsf(ar.w)) + (fabsf(ai.x) + fabsf(ai.y)) + (fabsf(ai.z) + fabsf(ai.w));
+        const float ns = (fabsf(sr.x) + fabsf(sr.y)) + (fabsf(sr.z) + fabsf(sr.w)) + (fabsf(si.x) + fabsf(si.y)) + (fabsf(si.z) + fabsf(si.w));
+        float mult = 1.f;
+        if (k >= 1 && k <= d.F - 2) {                        // mirrored synthesis rows (cls_fe_dft.py:109-110)
+            const long om = (long)(d.N - k) * d.N + c;
+            *reinterpret_cast<float4*>(gSr + om) = sr;
+            *reinterpret_cast<float4*>(gSi + om) = make_float4(-si.x, -si.y, -si.z, -si.w);
+            mult = 2.f;
+        }
+        acc[0] += na + mult * ns;
+    }
+    grid_finish<1>(acc, scratch, counter, [&](const double* s) {
+        const double total_norm = s[0] * (double)grad_scale;
+        if (norm_out) norm_out[0] = (float)total_norm;
+        float cf = 1.f;
+        if (max_norm > 0.f) {
+            const double cc = (double)max_norm / (total_norm + 1e-6);
+            cf = cc < 1.0 ? (float)cc : 1.f;
+        }
+        coef_out[0] = cf;
+    });
+}
+
 __global__ void __launch_bounds__(256)
 mae_kernel(const float* __restrict__ a, const float* __restrict__ b, long n, float* __restrict__ out, float* scratch,
            unsigned* counter) {
@@ -220,6 +331,19 @@ void st_launch_loss(const StDims& d, const float* y_hat, const float* y, const f
     const long n = (long)B * d.OT * d.F;
     loss_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, s>>>(d, y_hat, y, mag_hat, sbf, l1_coef, B, loss, g_y_hat, g_mag_hat,
                                                             scratch, counter);
+}
+void st_launch_ola_loss(const StDims& d, const float* fo, const float* x, const float* y, const float* mag_hat, const float* sbf,
+                        float l1_coef, int B, float* loss, float* gwave_hi, float* gwave_lo, float* g_mag_hat, float* scratch,
+                        unsigned* counter, cudaStream_t s) {
+    const long n = (long)B * d.OT * d.F;
+    ola_loss_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, s>>>(d, fo, x, y, mag_hat, sbf, l1_coef, B, loss, gwave_hi, gwave_lo,
+                                                                g_mag_hat, scratch, counter);
+}
+void st_launch_finalize_norm(const StDims& d, const float* pa, const float* ps, int sa, int ss, float* gWr, float* gWi, float* gSr,
+                             float* gSi, float grad_scale, float max_norm, float* norm_out, float* coef_out, float* scratch,
+                             unsigned* counter, cudaStream_t s) {
+    finalize_norm_kernel<<<148 * 4, 256, 0, s>>>(d, pa, ps, sa, ss, gWr, gWi, gSr, gSi, grad_scale, max_norm, norm_out, coef_out,
+                                                 scratch, counter);
 }
 void st_launch_mae(const float* a, const float* b, long n, float* out, float* scratch, unsigned* counter, cudaStream_t s) {
     mae_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, s>>>(a, b, n, out, scratch, counter);

@@ -376,3 +376,37 @@ def test_backward_in_two_calls_is_bit_identical():
     assert torch.equal(early[0], whole[2]) and torch.equal(early[1], whole[3])
     with pytest.raises(RuntimeError):
         eng.backward(_t(y), None, None, params, parts, part="finish")          # no begin before it
+
+
+@pytest.mark.parametrize("case", ["comp4c_c8192_k4_b3", "comp2k_c16384_k2_b2"])
+def test_fused_step_tail_matches_the_piecewise_entry_points(case):
+    """st_train_step runs a fused forward tail (overlap-add + residual + loss + loss gradients + padded 2*dL/dy_hat in one
+    kernel) and a fused DFT-gradient finalisation + L1 norm; st_forward / st_loss / st_backward / st_adam_step run the separate
+    kernels.  Same arithmetic per element: all 40 gradients must be bit-identical, the loss and the clip coefficient differ
+    only by summation order, so parameters after the update agree to one Adam step of fp32 noise."""
+    g, d = load_case(case)
+    P = initial_params(g, d)
+    x, y, knobs = _t(g["step0/x"]), _t(g["step0/y"].astype(np.float32)), _t(g["step0/knobs"])
+    sbf = _t(O.scale_by_freq(d.F))
+    eng = _engine(d)
+    out = []
+    for fused in (True, False):
+        params = _dev_params(P, d)
+        grads = [torch.full_like(p, float("nan")) for p in params]
+        m = [torch.zeros_like(p) for p in params]
+        v = [torch.zeros_like(p) for p in params]
+        hp = eng.adam_hp(lr=1e-4, step=1, max_norm=1.0)
+        if fused:
+            loss = eng.train_step(x, y, knobs, params, grads, m, v, sbf, 2e-6, hp)
+        else:
+            y_hat, _, mag_hat, _ = eng.forward(x, knobs, params)
+            loss, g_y, g_m = eng.loss(y_hat, y, mag_hat, sbf, 2e-6)
+            eng.backward(g_y, None, g_m, params, grads)
+            eng.adam_step(params, grads, m, v, hp)
+        out.append((loss.item(), [t.clone() for t in grads], [t.clone() for t in params]))
+    (lf, gf, pf), (lu, gu, pu) = out
+    assert abs(lf - lu) < 2e-7 * max(1.0, abs(lu)), (lf, lu)
+    for i, (a, b) in enumerate(zip(gf, gu)):
+        assert torch.equal(a, b), (i, (a - b).abs().max().item())
+    for i, (a, b) in enumerate(zip(pf, pu)):
+        assert (a - b).abs().max().item() <= (8e-9 if i < 4 else 0.0), (i, (a - b).abs().max().item())   # DFT: <= 2 ulp of 0.034
