@@ -438,10 +438,13 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         if (beside) ST_CUDA_OK(cudaEventRecord(h->ev_join, sp));
     }
     {
-        StageScope sc(h, SG_PAD_X, 1 + (d.K > 0), s);
+        // the knobs are copied only for the SIMT backward, which recomputes the chain; the record-based backward kernels
+        // (every geometry with OT <= 16 when training) read them from the saved activations
+        const bool keep_knobs = d.K > 0 && (acts || !(h->training && h->use_mma_bwd) || d.OT > 16);
+        StageScope sc(h, SG_PAD_X, 1 + keep_knobs, s);
         // x/2 with the conv padding, as (hi, lo), window stride Sx = Tp*H (frame (b,t) = row b*Tp+t of a stride-H view)
         st_launch_pad_split(x, h->xpad, h->xpad_lo, B, d.C, d.N, d.Sx, 0.5f, s);
-        if (d.K > 0) ST_CUDA_OK(cudaMemcpyAsync(h->knobs_ws, knobs, (long)B * d.K * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (keep_knobs) ST_CUDA_OK(cudaMemcpyAsync(h->knobs_ws, knobs, (long)B * d.K * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     if (beside) ST_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
     ST_LAUNCH_OK(h);
