@@ -170,6 +170,14 @@ int st_train_step(st_handle* h, const float* x, const float* y, const float* kno
                   float* const* exp_avg_sq, const float* scale_by_freq, float l1_coef,
                   const st_adam* hp, float* loss, void* stream);
 
+/* The same iteration WITHOUT the update, for data-parallel callers: forward, calc_loss and backward (train.py:112-138) with
+ * the fused forward tail of st_train_step; all ST_NUM_PARAMS gradients are written and loss[0] receives the scalar loss.  The
+ * caller then sums the gradients over its ranks and calls st_adam_step with grad_scale = 1/world_size and max_norm = 1
+ * (the L1 clip of nn_proc.py:299-302 is a function of the AVERAGED gradients, so it must follow the exchange). */
+int st_grad_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch,
+                 float* const* params, float* const* grads, const float* scale_by_freq, float l1_coef,
+                 float* loss, void* stream);
+
 /* Measurement support (bench.py): number of kernels / device copies this handle has launched, and per-stage
  * device time bracketed with CUDA events on the launching stream.  st_profile_read synchronises the device,
  * fills ms[i] / calls[i] for i < st_profile_stage_count() with the totals since the previous read, and resets. */

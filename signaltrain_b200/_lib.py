@@ -61,6 +61,8 @@ _SIGNATURES = {
     "st_train_step": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p, ctypes.c_float,
                                      ctypes.POINTER(StAdam), c_float_p, ctypes.c_void_p]),
+    "st_grad_step": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.c_void_p, c_float_p, ctypes.c_float, c_float_p, ctypes.c_void_p]),
     "st_set_training": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "st_set_precision": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "st_get_precision": (ctypes.c_int, [ctypes.c_void_p]),

@@ -548,11 +548,12 @@ extern "C" int st_mae(st_handle* h, const float* a, const float* b, long n, floa
 
 // phase: 0 = the whole backward; 1 = "begin": up to and including the FINAL synthesis gradients (grads[2], grads[3]), so a
 // data-parallel caller can start their allreduce; 2 = "finish": the autoencoders and the analysis gradients.
-// fused_clip (st_train_step only): gwave already holds the padded 2*dL/dy_hat (written by the fused forward tail), and the
-// final DFT-gradient pass also produces the L1 norm / clip coefficient for the Adam launch that follows.
+// gwave_ready (st_train_step / st_grad_step): gwave already holds the padded 2*dL/dy_hat, written by the fused forward tail.
+// fused_clip (st_train_step only): the final DFT-gradient pass also produces the L1 norm / clip coefficient for the Adam launch
+// that follows.
 static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat, int B,
                          const float* const* params, float* const* grads, cudaStream_t s, int phase = 0,
-                         const st_adam* fused_clip = nullptr) {
+                         bool gwave_ready = false, const st_adam* fused_clip = nullptr) {
     const StDims& d = h->d;
     if (B != h->fwdB || B > h->maxB)
         return st_fail_msg(h, "st_backward: batch %d does not match the preceding st_forward (%d)", B, h->fwdB);
@@ -562,7 +563,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
     int ss = -1, sa = -1;
     if (phase != 2) {
     // adjoint of (*2, trim [N:-N]): zero-padded 2*g
-    if (!fused_clip) {
+    if (!gwave_ready) {
         StageScope sc(h, SG_PAD_G, 1, s);
         // adjoint of (*2, trim [N:-N]): zero-padded 2*g, window stride Sg = OTp*H
         st_launch_pad_split(g_y_hat, h->gwave, h->gwave_lo, B, d.L, d.N, d.Sg, 2.0f, s);
@@ -763,6 +764,32 @@ extern "C" int st_adam_step(st_handle* h, float* const* params, const float* con
     return adam_impl(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/false, (cudaStream_t)stream);
 }
 
+// forward without its overlap-add; one kernel then does overlap-add + residual + loss + both loss gradients and writes the
+// padded (hi, lo) 2*dL/dy_hat operand; then the whole backward.  With fused_clip the last DFT-gradient pass also yields the
+// clip coefficient (single-GPU step); without it the gradients are left for the caller's allreduce.
+static int grad_step_impl(st_handle* h, const float* x, const float* y, const float* knobs, int batch, float* const* params,
+                          float* const* grads, const float* sbf, float l1_coef, float* loss, cudaStream_t s, const st_adam* fused_clip) {
+    if (forward_impl(h, x, knobs, batch, params, nullptr, nullptr, nullptr, nullptr, s)) return 1;
+    {
+        StageScope sc(h, SG_LOSS, 1, s);
+        st_launch_ola_loss(h->d, h->fo, x, y, h->mag_hat_ws, sbf, l1_coef, batch, loss, h->gwave, h->gwave_lo, h->gmh_ws,
+                           h->small + SM_LOSS, h->counters + CT_LOSS, s);
+    }
+    ST_LAUNCH_OK(h);
+    return backward_impl(h, h->gy_ws, nullptr, h->gmh_ws, batch, params, grads, s, 0, /*gwave_ready=*/true, fused_clip);
+}
+
+extern "C" int st_grad_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch, float* const* params,
+                            float* const* grads, const float* sbf, float l1_coef, float* loss, void* stream) {
+    if (!h) return 1;
+    if (!x || !y || !knobs || !loss) return st_fail_msg(h, "st_grad_step: null argument");
+    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_grad_step(params)") ||
+        check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_grad_step(grads)"))
+        return 1;
+    if (ensure_workspace(h, batch)) return 1;
+    return grad_step_impl(h, x, y, knobs, batch, params, grads, sbf, l1_coef, loss, (cudaStream_t)stream, nullptr);
+}
+
 extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch,
                              float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                              const float* sbf, float l1_coef, const st_adam* hp, float* loss, void* stream) {
@@ -776,16 +803,7 @@ extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const
     cudaStream_t s = (cudaStream_t)stream;
     if (ensure_workspace(h, batch)) return 1;
     if (h->fuse_tail) {
-        // forward without its overlap-add; one kernel then does overlap-add + residual + loss + both loss gradients and writes
-        // the padded (hi, lo) 2*dL/dy_hat operand; the last DFT-gradient pass also yields the clip coefficient
-        if (forward_impl(h, x, knobs, batch, params, nullptr, nullptr, nullptr, nullptr, s)) return 1;
-        {
-            StageScope sc(h, SG_LOSS, 1, s);
-            st_launch_ola_loss(h->d, h->fo, x, y, h->mag_hat_ws, sbf, l1_coef, batch, loss, h->gwave, h->gwave_lo, h->gmh_ws,
-                               h->small + SM_LOSS, h->counters + CT_LOSS, s);
-        }
-        ST_LAUNCH_OK(h);
-        if (backward_impl(h, h->gy_ws, nullptr, h->gmh_ws, batch, params, grads, s, 0, hp)) return 1;
+        if (grad_step_impl(h, x, y, knobs, batch, params, grads, sbf, l1_coef, loss, s, hp)) return 1;
         return adam_impl(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/true, s, /*coef_ready=*/true);
     }
     if (forward_impl(h, x, knobs, batch, params, h->yhat_ws, nullptr, nullptr, nullptr, s)) return 1;

@@ -279,6 +279,21 @@ class Engine:
                                         _ptr(loss), self._stream()), "st_train_step")
         return loss
 
+    def grad_step(self, x, y, knobs, params, grads, sbf, l1_coef, loss_out=None):
+        """forward + loss + backward in one call (st_grad_step): gradients into `grads`, no update -- the data-parallel step."""
+        g = self.g
+        B = x.shape[0]
+        _check(x, "x", (B, g.C), self.device)
+        _check(y, "y", (B, g.L), self.device)
+        _check(knobs, "knobs", (B, g.K), self.device)
+        if sbf is not None:
+            _check(sbf, "scale_by_freq", (g.F,), self.device)
+        loss = loss_out if loss_out is not None else torch.empty((), device=self.device, dtype=torch.float32)
+        self._ok(self.lib.st_grad_step(self.h, _ptr(x), _ptr(y), _ptr(knobs), B, self.table(params, "params"),
+                                       self.table(grads, "grads"), _ptr(sbf), float(l1_coef), _ptr(loss), self._stream()),
+                 "st_grad_step")
+        return loss
+
     def launch_count(self):
         return int(self.lib.st_launch_count(self.h))
 

@@ -67,11 +67,12 @@ class FusedTrainer:
             eng.train_step(x, y, knobs, self.params, self.grads, self.m, self.v, self.sbf, self.l1_lambda / 10, hp,
                            loss_out=self.loss_buf)
         else:
-            y_hat, _, mag_hat, _ = eng.forward(x, knobs, self.params)
-            loss, g_y, g_m = eng.loss(y_hat, y, mag_hat, self.sbf, self.l1_lambda / 10)
-            if self.reducer is None:
-                self.reducer = parallel.GradReducer(self._fb, [tuple(p.shape) for p in self.params], eng.g.F, self.pg)
             mode = os.environ.get("ST_DP_EXCHANGE", "whole")
+            if mode in ("overlap", "sliced"):
+                y_hat, _, mag_hat, _ = eng.forward(x, knobs, self.params)
+                loss, g_y, g_m = eng.loss(y_hat, y, mag_hat, self.sbf, self.l1_lambda / 10)
+                if self.reducer is None:
+                    self.reducer = parallel.GradReducer(self._fb, [tuple(p.shape) for p in self.params], eng.g.F, self.pg)
             if mode == "overlap":                 # synthesis pair reduced while the rest of the backward runs
                 eng.backward(g_y, None, g_m, self.params, self.grads, part="begin")
                 self.reducer.start_synthesis()
@@ -81,11 +82,12 @@ class FusedTrainer:
                 eng.backward(g_y, None, g_m, self.params, self.grads)
                 self.reducer.start_synthesis()
                 scale = self.reducer.finish()
-            else:                                 # default: ONE allreduce of the whole flat buffer (16.8 MB).  Measured on
-                # 2 B200s (ms/step): whole 1.011, sliced 1.056, overlap 1.060 -- at this size NCCL is launch / latency
-                # bound, so four smaller collectives cost more than the 25 % of payload they save, and the overlapped one
-                # cannot get SMs while the autoencoder backward holds them all
-                eng.backward(g_y, None, g_m, self.params, self.grads)
+            else:                                 # default: st_grad_step (forward + fused loss tail + backward in one call),
+                # then ONE allreduce of the whole flat buffer (16.8 MB).  Measured on 2 B200s (ms/step, v7): whole 1.011,
+                # sliced 1.056, overlap 1.060 -- at this size NCCL is launch / latency bound, so four smaller collectives
+                # cost more than the 25 % of payload they save, and the overlapped one cannot get SMs while the
+                # autoencoder backward holds them all
+                loss = eng.grad_step(x, y, knobs, self.params, self.grads, self.sbf, self.l1_lambda / 10, loss_out=self.loss_buf)
                 scale = parallel.allreduce_sum_(self.flat_grads, self.pg)
             hp = eng.adam_hp(self.lr, step_no, grad_scale=scale, max_norm=1.0)
             eng.adam_step(self.params, self.grads, self.m, self.v, hp)

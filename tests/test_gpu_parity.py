@@ -390,21 +390,29 @@ def test_fused_step_tail_matches_the_piecewise_entry_points(case):
     sbf = _t(O.scale_by_freq(d.F))
     eng = _engine(d)
     out = []
-    for fused in (True, False):
+    for fused in (True, "grad_step", False):
         params = _dev_params(P, d)
         grads = [torch.full_like(p, float("nan")) for p in params]
         m = [torch.zeros_like(p) for p in params]
         v = [torch.zeros_like(p) for p in params]
         hp = eng.adam_hp(lr=1e-4, step=1, max_norm=1.0)
-        if fused:
+        if fused is True:
             loss = eng.train_step(x, y, knobs, params, grads, m, v, sbf, 2e-6, hp)
+        elif fused == "grad_step":       # the data-parallel route: st_grad_step, (allreduce), st_adam_step
+            loss = eng.grad_step(x, y, knobs, params, grads, sbf, 2e-6)
+            eng.adam_step(params, grads, m, v, hp)
         else:
             y_hat, _, mag_hat, _ = eng.forward(x, knobs, params)
             loss, g_y, g_m = eng.loss(y_hat, y, mag_hat, sbf, 2e-6)
             eng.backward(g_y, None, g_m, params, grads)
             eng.adam_step(params, grads, m, v, hp)
         out.append((loss.item(), [t.clone() for t in grads], [t.clone() for t in params]))
-    (lf, gf, pf), (lu, gu, pu) = out
+    (lf, gf, pf), (lg, gg, pg), (lu, gu, pu) = out
+    assert lg == lf                                              # same loss kernel
+    for i, (a, b) in enumerate(zip(gg, gu)):
+        assert torch.equal(a, b), ("grad_step", i)
+    for i, (a, b) in enumerate(zip(pg, pu)):
+        assert torch.equal(a, b), ("grad_step params", i)        # same norm kernel as the piecewise route: bit-identical update
     assert abs(lf - lu) < 2e-7 * max(1.0, abs(lu)), (lf, lu)
     for i, (a, b) in enumerate(zip(gf, gu)):
         assert torch.equal(a, b), (i, (a - b).abs().max().item())
