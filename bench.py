@@ -46,6 +46,25 @@ WORKLOADS = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line: keep a private handle on the real stdout and point fd 1 at stderr, so that
+    anything libraries print there (NCCL's version banner, extension build chatter) cannot land in front of the line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -178,7 +197,7 @@ def run_reference(args):
                              "sample": f"{steps} full train steps of B={B} windows (oracle/st_oracle.py Trainer, float32, "
                                        f"numpy/BLAS on {threads} threads)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_native(args):
@@ -331,7 +350,7 @@ def run_native(args):
     if cpu_fps is not None:
         line["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port", "ms_per_step": cpu_ms,
                                 "sample": f"3 full train steps of B={B} windows by oracle/st_oracle.py (float32 numpy/BLAS, {cores} threads)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -347,6 +366,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
