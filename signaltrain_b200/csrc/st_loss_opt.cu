@@ -1,6 +1,8 @@
 // Loss (loss_functions.py:9-10,22-23,26-43), L1 gradient clip (nn_proc.py:299-302) and Adam
 // (torch.optim.Adam as constructed at train.py:228).  All HBM-streaming: float4 loads, warp-shuffle
 // block reductions, and a deterministic last-block final reduction (fixed summation order, no float atomics).
+#include <algorithm>
+
 #include "st_common.cuh"
 
 namespace {
@@ -140,11 +142,32 @@ ola_loss_kernel(StDims d, const float* __restrict__ fo, const float* __restrict_
         *reinterpret_cast<float4*>(gwave_hi + o) = hi;
         *reinterpret_cast<float4*>(gwave_lo + o) = lo;
     }
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n2; i += stride) {
+    // weighted-L1 term, four bins per thread (the flat (b, t, f) index runs over f fastest; F is odd, so rows are not 16-byte
+    // aligned but the flat array is)
+    const long n2v = n2 >> 2;
+    const float c2 = l1_coef * inv2;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n2v; i += stride) {
+        const float4 mh = *reinterpret_cast<const float4*>(mag_hat + 4 * i);
+        int f = (int)((4 * i) % d.F);
+        const float m[4] = {mh.x, mh.y, mh.z, mh.w};
+        float g[4], a = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float s = sbf ? __ldg(sbf + f) : 1.f;
+            const float v = m[e] * s;
+            a += fabsf(v);
+            g[e] = c2 * s * (float)((v > 0.f) - (v < 0.f));
+            if (++f == d.F) f = 0;
+        }
+        acc[1] += a;
+        *reinterpret_cast<float4*>(g_m + 4 * i) = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n2 & 3)) {
+        const long i = 4 * n2v + threadIdx.x;
         const float s = sbf ? sbf[i % d.F] : 1.f;
         const float v = mag_hat[i] * s;
         acc[1] += fabsf(v);
-        g_m[i] = l1_coef * inv2 * s * (float)((v > 0.f) - (v < 0.f));
+        g_m[i] = c2 * s * (float)((v > 0.f) - (v < 0.f));
     }
     grid_finish<2>(acc, scratch, counter, [&](const double* s) {
         loss[0] = (float)(s[0] / (double)n1 + (double)l1_coef * s[1] / (double)n2);
@@ -335,8 +358,8 @@ void st_launch_loss(const StDims& d, const float* y_hat, const float* y, const f
 void st_launch_ola_loss(const StDims& d, const float* fo, const float* x, const float* y, const float* mag_hat, const float* sbf,
                         float l1_coef, int B, float* loss, float* gwave_hi, float* gwave_lo, float* g_mag_hat, float* scratch,
                         unsigned* counter, cudaStream_t s) {
-    const long n = (long)B * d.OT * d.F;
-    ola_loss_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, s>>>(d, fo, x, y, mag_hat, sbf, l1_coef, B, loss, gwave_hi, gwave_lo,
+    const long n = std::max((long)B * d.OT * d.F / 4, (long)B * (d.L / 4));      // float4 items of the larger loop
+    ola_loss_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(d, fo, x, y, mag_hat, sbf, l1_coef, B, loss, gwave_hi, gwave_lo,
                                                                 g_mag_hat, scratch, counter);
 }
 void st_launch_finalize_norm(const StDims& d, const float* pa, const float* ps, int sa, int ss, float* gWr, float* gWi, float* gSr,

@@ -418,3 +418,32 @@ def test_fused_step_tail_matches_the_piecewise_entry_points(case):
         assert torch.equal(a, b), (i, (a - b).abs().max().item())
     for i, (a, b) in enumerate(zip(pf, pu)):
         assert (a - b).abs().max().item() <= (8e-9 if i < 4 else 0.0), (i, (a - b).abs().max().item())   # DFT: <= 2 ulp of 0.034
+
+
+@pytest.mark.parametrize("B", [12, 37])
+def test_whole_step_vs_oracle_at_batches_that_use_pair_tiles(B):
+    """The golden cases hold 2-3 windows (one 128-row tile: the 1-CTA GEMM kernel serves the forward there).  At B = 12 / 37 the
+    forward GEMMs run on cta_group::2 tiles (324 / 999 frame rows = 3 / 8 tiles, i.e. a half-empty last pair / exact pairs), and
+    the fused step tail sees a ragged batch.  Forward, loss and all 40 gradients (st_grad_step) against the float64 oracle."""
+    d = O.model_dims(1, 4, 4)
+    P = O.init_params(d, seed=218)
+    rng = np.random.RandomState(B)
+    t = np.arange(d.C) / 44100.0
+    x = (0.4 * np.sin(2 * np.pi * rng.uniform(60, 3000, (B, 1)) * t + rng.uniform(0, 6.28, (B, 1)))
+         + 0.05 * rng.standard_normal((B, d.C))).astype(np.float32)
+    y = np.tanh(1.5 * x[:, -d.L:]).astype(np.float32)
+    knobs = rng.uniform(-0.5, 0.5, (B, d.K)).astype(np.float32)
+    sbf = O.scale_by_freq(d.F)
+    eng = _engine(d)
+    params = _dev_params(P, d)
+    y_hat, _, mag_hat, _ = eng.forward(_t(x), _t(knobs), params)
+    ref_loss, ref_grads, fw = O.loss_and_grads(d, P, x, y, knobs, sbf)
+    np.testing.assert_allclose(y_hat.cpu().numpy(), fw["y_hat"], atol=WAVE_TOL)
+    np.testing.assert_allclose(mag_hat.cpu().numpy(), fw["mag_hat"], atol=2e-5)
+    grads = [torch.full_like(p, float("nan")) for p in params]
+    loss = eng.grad_step(_t(x), _t(y), _t(knobs), params, grads, _t(sbf), 2e-5 / 10)
+    assert abs(loss.item() - ref_loss) < 2e-6
+    for (name, _), gt in zip(O.param_order(d), grads):
+        got, ref = gt.cpu().numpy(), ref_grads[name]
+        assert np.isfinite(got).all(), name
+        assert np.abs(got - ref).max() <= GRAD_RTOL * np.abs(ref).max() + 1e-12, (name, np.abs(got - ref).max() / np.abs(ref).max())
