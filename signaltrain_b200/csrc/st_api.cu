@@ -607,7 +607,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
     int part_ctas = h->ae_grid;
     {   // both autoencoders: back-propagate, dL/d(re|im) -> g_spec, per-CTA weight-gradient partials.  Tensor-core path
         // from the saved activations when the forward wrote them; otherwise the SIMT kernel recomputes the chain.
-        StageScope sc(h, SG_AE_BWD, 2, s);
+        StageScope sc(h, SG_AE_BWD, (h->have_saves && h->use_f2_bwd) ? 3 : 2, s);   // FFMA2 route: two chain kernels + ae_input_grad
         AeParams pm, pp;
         split_params(params, pm, pp);
         int gr = 0;
