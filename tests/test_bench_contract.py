@@ -1,0 +1,43 @@
+"""CPU: bench.py's reference arm (the reference's algorithm on the host cores, oracle port) prints exactly ONE JSON line on
+stdout with the keys the driver reads, and runs nothing else there; the native arm refuses to run without a CUDA device."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, cwd=ROOT, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line():
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--batch", "4")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("audio frames/sec per train step")
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_other_ranks_print_nothing():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       capture_output=True, text=True, cwd=ROOT, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_native_arm_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    r = _run("--steps", "1", "--warmup", "1")
+    assert r.returncode != 0 and r.stdout.strip() == ""
+    assert "no CPU fallback" in r.stderr
