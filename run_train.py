@@ -41,21 +41,27 @@ if __name__ == "__main__":
     device = torch.device("cuda:0")
     torch.cuda.manual_seed(218)
 
-    parser = argparse.ArgumentParser(description="Trains neural network to reproduce input-output transformations.",
+    # the reference's command line (run_train.py:32-47): same flags, short forms and defaults; help text is this repo's
+    FLAGS = [
+        (('--apex',), dict(default="O0", help="precision in apex vocabulary: O0 = fp32-faithful (3xTF32 tensor cores), "
+                                              "O1/O2/O3 = single-pass TF32 products (fp32 storage, loss, optimiser)")),
+        (('-b', '--batch'), dict(type=int, default=200, help="windows per step")),
+        (('--checkpoint',), dict(default="modelcheckpoint.tar", help="checkpoint file to resume from / write to")),
+        (('-c', '--compand'), dict(action='store_true', help="accepted for compatibility (companding is a data-layer option)")),
+        (('--effect',), dict(default="comp_4c", help=f"audio effect to learn: {', '.join(sorted(st.data.EFFECTS))} built in")),
+        (('--epochs',), dict(type=int, default=1000, help="passes over --num windows")),
+        (('--lrmax',), dict(type=float, default=1e-4, help="peak of the 1-cycle learning-rate schedule")),
+        (('-n', '--num'), dict(type=int, default=200000, help="windows per epoch")),
+        (('--path',), dict(default=None, help="dataset directory (Train/ and Val/ with input_*/target_* files); none = synthetic")),
+        (('--sr',), dict(type=int, default=44100, help="sample rate in Hz")),
+        (('--scale',), dict(type=float, default=1.0, help="input chunk = 8192 x scale")),
+        (('--shrink',), dict(type=int, default=4, help="output chunk = input chunk / shrink")),
+        (('-t', '--target',), dict(default="stream", help="target alignment: chunk or stream")),
+    ]
+    parser = argparse.ArgumentParser(description="Train the SignalTrain model on a B200 (signaltrain_b200 train step).",
                                      formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    parser.add_argument('--apex', help="precision, in the reference's apex vocabulary: O0 = fp32-faithful (3xTF32 tensor cores); O1/O2/O3 = single-pass TF32 products", default="O0")
-    parser.add_argument('-b', '--batch', type=int, help="batch size", default=200)
-    parser.add_argument('--checkpoint', help='Name of model checkpoint .tar file', default="modelcheckpoint.tar")
-    parser.add_argument('-c', '--compand', help='Turn on to use companded/decompanded audio', action='store_true')
-    parser.add_argument('--effect', help='Name of effect to use', default="comp_4c")
-    parser.add_argument('--epochs', type=int, help='Number of epochs to run', default=1000)
-    parser.add_argument('--lrmax', type=float, help="max learning rate", default=1e-4)
-    parser.add_argument('-n', '--num', type=int, help='Number of "data points" (audio clips) per epoch', default=200000)
-    parser.add_argument('--path', help='Directory to pull input (and maybe target) data from', default=None)
-    parser.add_argument('--sr', type=int, help='Sampling rate', default=44100)
-    parser.add_argument('--scale', type=float, help='Scale factor (of input size & whole model)', default=1.0)
-    parser.add_argument('--shrink', type=int, help='Shink output chunk relative to input by this divisor', default=4)
-    parser.add_argument('-t', '--target', help="type of target: chunk or stream", default="stream")
+    for names, spec in FLAGS:
+        parser.add_argument(*names, **spec)
     args = parser.parse_args()
     print("Command line: ", " ".join(sys.argv[:]))
 
