@@ -731,7 +731,8 @@ int st_launch_gemm_tc(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand&
                 else if (!a_mn && b_mn) e = launch_pair<false, true>(ah, al, bh, bl, p, grid, smem2, s);
                 else if (a_mn && !b_mn) e = launch_pair<true, false>(ah, al, bh, bl, p, grid, smem2, s);
                 else e = launch_pair<true, true>(ah, al, bh, bl, p, grid, smem2, s);
-                return e == cudaSuccess ? p.splits : -1;
+                if (e == cudaSuccess) return p.splits;
+                cudaGetLastError();          // a refused cluster launch is not fatal: the 1-CTA kernel below takes the shape
             }
         }
     }
