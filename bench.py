@@ -301,8 +301,7 @@ def run_native(args):
             dist.destroy_process_group()
         return
 
-    from oracle import st_oracle as O
-    d = O.model_dims(CHUNK_SCALE, SHRINK, KNOBS)
+    d = eng.g                          # geometry of the measured handle (C, N, H, T, OT, L, F, K)
     peaks = measured_peaks()
     work = stage_work(d, B)
     step_sum = sum(v[0] for v in stages.values())
