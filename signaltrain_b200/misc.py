@@ -2,6 +2,7 @@
 the reference's `signaltrain/misc.py:21,38`.  A checkpoint is one `torch.save`d dict -- the 40-tensor `state_dict` under the
 reference's keys plus run metadata -- so files written here load in the reference's tools (`predict_long`, the demo) and vice
 versa.  Unlike the reference (TODO at `train.py:229`) the optimizer state stored in the file is restored by `train()`."""
+import collections
 import os
 import sys
 
@@ -29,7 +30,8 @@ def save_checkpoint(checkpointname, model, epoch, parallel, optimizer, effect, s
     record['sr'] = sr
     record['epoch'] = epoch + 1
     record['optimizer'] = optimizer.state_dict()
-    record['state_dict'] = {key: t.detach().cpu() for key, t in core.state_dict().items()}     # device-independent file
+    # an OrderedDict like nn.Module.state_dict(), with CPU copies so that the file loads on any box
+    record['state_dict'] = collections.OrderedDict((key, t.detach().cpu()) for key, t in core.state_dict().items())
     print(f'\nsaving model to {checkpointname}', end="")
     torch.save(record, checkpointname)
 

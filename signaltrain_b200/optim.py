@@ -10,7 +10,9 @@ class Adam(torch.optim.Optimizer):
             raise NotImplementedError("signaltrain_b200.optim.Adam: weight_decay must be 0 (train.py:228)")
         self._model = model
         params = model.ordered_parameters()
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0))
+        # the group carries every key torch.optim.Adam's does, so a checkpoint's optimizer entry loads into either class
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                                      capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False))
         self._step = 0
 
     def _state_lists(self):

@@ -49,3 +49,39 @@ def assert_params_close_after_adam(got, ref, name, atol=3e-6, hard=2.5e-5, frac=
     diff = np.abs(np.asarray(got, dtype=np.float64) - np.asarray(ref, dtype=np.float64))
     assert diff.max() <= hard, (name, diff.max())
     assert (diff > atol).mean() <= frac, (name, (diff > atol).mean(), diff.max())
+
+
+def _describe(value):
+    """JSON-able description of one checkpoint value: type, and shape/dtype or the value itself when small."""
+    import torch
+    if isinstance(value, torch.Tensor):
+        return {"type": "Tensor", "shape": list(value.shape), "dtype": str(value.dtype)}
+    if isinstance(value, np.ndarray):
+        return {"type": "ndarray", "shape": list(value.shape), "dtype": str(value.dtype), "value": value.tolist()}
+    if isinstance(value, (list, tuple)):
+        return {"type": type(value).__name__,
+                "value": [v if isinstance(v, (int, float, str, bool, type(None))) else str(v) for v in value]}
+    if isinstance(value, (int, float, str, bool, type(None))):
+        return {"type": type(value).__name__, "value": value}
+    return {"type": type(value).__name__}
+
+
+def checkpoint_manifest(ckpt):
+    """Structure of a `modelcheckpoint.tar` dict (misc.py:21-35): must match tests/golden/make_checkpoint_manifest.py's use."""
+    opt = ckpt["optimizer"]
+    group = opt["param_groups"][0]
+    first = opt["state"][group["params"][0]]
+    return {
+        "top_level": {k: _describe(v) if k not in ("state_dict", "optimizer") else {"type": type(v).__name__} for k, v in ckpt.items()},
+        "state_dict": [[k, list(v.shape), str(v.dtype)] for k, v in ckpt["state_dict"].items()],
+        "optimizer": {
+            "keys": sorted(opt.keys()),
+            "n_param_groups": len(opt["param_groups"]),
+            "param_group_keys": sorted(group.keys()),
+            "param_group_values": {k: _describe(v) for k, v in group.items() if k != "params"},
+            "params": list(group["params"]),
+            "n_state": len(opt["state"]),
+            "state_entry": {k: _describe(v) for k, v in first.items()},
+            "state_shapes": [list(opt["state"][i]["exp_avg"].shape) for i in group["params"]],
+        },
+    }
