@@ -73,3 +73,16 @@ def test_sliding_window_mirror():
     from signaltrain_b200.predict_long import sliding_window
     np.testing.assert_array_equal(sliding_window(np.arange(10), 5, overlap=2), [[0, 1, 2, 3, 4], [3, 4, 5, 6, 7], [6, 7, 8, 9, 0]])
     assert sliding_window(np.arange(8), 4, overlap=0).shape == (2, 4)
+
+
+def test_learningrate_mirror_matches_reference_probes():
+    """learningrate.py:14-52: the host LUT of the product package against values of the reference's own function
+    (stored with the goldens by tests/golden/make_goldens.py)."""
+    import signaltrain_b200 as st
+    from tests.helpers import load_case
+    g, _ = load_case("comp4c_c8192_k4_b3")
+    lrs, moms = st.learningrate.get_1cycle_schedule(lr_max=1e-4, n_data_points=200000, epochs=1000, batch_size=200)
+    assert len(lrs) == len(moms) == int(g["meta/lr_sched_len"])
+    np.testing.assert_allclose(lrs[:8], g["meta/lr_sched_head"], rtol=1e-12)
+    np.testing.assert_allclose(lrs[g["meta/lr_sched_probe_idx"]], g["meta/lr_sched_probe"], rtol=1e-12)
+    assert moms.min() >= 0.85 - 1e-12 and moms.max() <= 0.95 + 1e-12 and np.isclose(moms[0], 0.95)
