@@ -15,6 +15,10 @@
 //                              forward GEMMs (1e-5 waveform budget) the issuer starts a fresh TMEM accumulator every k-block
 //                              and these warps add the 12-step partial sums in round-to-nearest fp32 registers
 //                              ("promoted accumulation"); the gradient GEMMs accumulate all of K in TMEM.
+// Two kernels share this structure: gemm_tc2_kernel (default) runs it on CTA PAIRS -- tcgen05.mma.cta_group::2, a 256 x BN tile
+// per pair, each CTA staging its 128 rows of A and half of B (see the comment above that kernel) -- and gemm_tc_kernel is the
+// 1-CTA form (128 x BN tile; ST_GEMM_PAIR=0, shapes with a single M-tile, or a refused cluster launch).  PASSES = 1 is the
+// reduced-precision mode: hi planes only, one UMMA per k-step.
 // Operands may be K-major ([row][k], one 128-row x 32-float box per stage) or MN-major ([k][row], 32x32 boxes); the frame
 // gather of Conv1d / ConvTranspose1d (cls_fe_dft.py:28-31,78-82) is a 2-D tensor map whose row stride is the hop (rows
 // overlap), so frames are never materialised.
