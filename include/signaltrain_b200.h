@@ -201,6 +201,10 @@ int st_debug_gemm(st_handle* h, int use_tc, int a_mn, int b_mn, const float* a_h
                   const float* b_hi, const float* b_lo, long b_ld, float* C, long ldc, int M, int N, int K, int splits,
                   void* stream);
 long st_debug_numel(st_handle* h, const char* name);
+/* Host-only (no device work): launch plan of the five front-end contractions (analysis, synthesis, synthesis dgrad, synthesis
+ * wgrad, analysis wgrad) for this geometry and batch on a chip of sm_count SMs (<= 0: 148): out[5][4] =
+ * {1 = cta_group::2 kernel | 0 = 1-CTA kernel, tile width BN, split-K planes, grid size}. */
+int st_debug_gemm_plan(const st_config* cfg, int batch, int sm_count, int* out);
 
 #ifdef __cplusplus
 }

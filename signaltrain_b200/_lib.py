@@ -77,6 +77,7 @@ _SIGNATURES = {
                                      ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "st_debug_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_long]),
     "st_debug_numel": (ctypes.c_long, [ctypes.c_void_p, ctypes.c_char_p]),
+    "st_debug_gemm_plan": (ctypes.c_int, [ctypes.POINTER(StConfig), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
 }
 
 _lib = None

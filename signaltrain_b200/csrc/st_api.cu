@@ -818,6 +818,27 @@ extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const
     return adam_impl(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/true, s);
 }
 
+// Host-only: the launch plan of the five front-end contractions of THIS geometry at a batch size (no device work, so the CPU
+// test suite can check the tile / split-K heuristic): out[5][4] = {pair kernel?, BN, split-K planes, grid} for
+// analysis, synthesis, synthesis dgrad, synthesis wgrad, analysis wgrad.  sm_count <= 0: the handle's device.
+extern "C" int st_debug_gemm_plan(const st_config* cfg, int batch, int sm_count, int* out) {
+    if (!cfg || !out || batch <= 0) return 1;
+    const int N = cfg->ft, H = cfg->hop, F = N / 2 + 1;
+    int Fp = round_up(F, 16);
+    while (st_tc_pick_bn(2 * Fp) < 128) Fp += 16;
+    const int L = (cfg->frames_out - 1) * H - N;
+    const int Tp = (cfg->chunk + 2 * N + H - 1) / H, OTp = (L + 2 * N + H - 1) / H;
+    const int MT = batch * Tp, MO = batch * OTp, F2 = 2 * Fp;
+    if (sm_count <= 0) sm_count = 148;
+    int rc = 0;
+    rc |= st_tc_plan(false, MT, F2, N, 1, sm_count, out + 0);
+    rc |= st_tc_plan(true, MO, N, F2, 1, sm_count, out + 4);
+    rc |= st_tc_plan(false, MO, F2, N, 1, sm_count, out + 8);
+    rc |= st_tc_plan(true, F2, N, MO, std::min(kMaxSplits, std::max(1, MO / 512)), sm_count, out + 12);
+    rc |= st_tc_plan(true, F2, N, MT, std::min(kMaxSplits, std::max(1, MT / 512)), sm_count, out + 16);
+    return rc ? 1 : 0;
+}
+
 extern "C" long st_debug_numel(st_handle* h, const char* name) {
     if (!h || !name) return -1;
     const StDims& d = h->d;

@@ -120,6 +120,8 @@ struct TcOperand {
     long rows, cols, ld;
 };
 int st_tc_pick_bn(int n);
+// host-only launch plan of a shape: out = {pair kernel?, BN, split-K planes, grid}; -1 when not covered (no CUDA call)
+int st_tc_plan(bool b_mn_major, int M, int N, int K, int splits, int sm_count, int out[4]);
 // returns split planes written, or -1 when the shape is not covered (caller falls back to st_launch_gemm)
 // promote: start a fresh TMEM accumulator every k-block and sum the partials in fp32 registers (forward GEMMs)
 // passes: 3 = exact (hi, lo) operands, 3xTF32 (fp32 fidelity);  1 = hi planes only, single-pass TF32 (reduced precision mode)

@@ -680,6 +680,50 @@ static int pick_bn_for(int n, int tiles_m, int splits, bool b_mn, int sm_count, 
     return best;
 }
 
+// cta_group::2 kernel: tile width and split-K count together -- minimise the operand bytes one CTA pulls in over its rounds of
+// work items (A tile + half B tile per k-block, plus the tile's store), the quantity these GEMMs are bound by.  BN = 0: no width
+// fits (N not divisible, or half the tile is not a whole number of swizzle atoms / 32-column slabs).
+static void pick_pair_tile(int N, int pairs_m, int npairs, int kb_total, int splits, bool b_mn, int* bn_out, int* splits_out) {
+    int BN2 = 0, SP2 = 1;
+    double best = 0;
+    for (int bn = 256; bn >= 64; bn -= 16) {
+        if (N % bn || (b_mn ? (bn % 64) : ((bn / 2) % 8))) continue;
+        for (int sp = splits; sp >= 1; --sp) {
+            const int kbps = (kb_total + sp - 1) / sp;
+            if ((kb_total + kbps - 1) / kbps != sp) continue;
+            if (sp < splits && 2 * sp < splits) break;            // keep at least half the requested split-K parallelism
+            const long work = (long)pairs_m * (N / bn) * sp;
+            const long rounds = (work + npairs - 1) / npairs;
+            const double cost = (double)rounds * ((double)kbps * (A_BYTES + bn / 2 * 128) + 0.5 * BM * bn * 4 + 8192.0);
+            if (BN2 == 0 || cost < best) { BN2 = bn; SP2 = sp; best = cost; }
+        }
+    }
+    *bn_out = BN2;
+    *splits_out = SP2;
+}
+
+// Host-only view of the launch plan (no CUDA call): which kernel a shape gets, its tile width, split-K planes and grid.
+// out = {pair (1 | 0), BN, splits, grid}; returns 0, or -1 when the tensor-core path does not cover the shape.
+int st_tc_plan(bool b_mn, int M, int N, int K, int splits, int sm_count, int out[4]) {
+    if (splits < 1) splits = 1;
+    const int tiles_m = (M + BM - 1) / BM, kb_total = (K + BKF - 1) / BKF;
+    if (ST_GEMM_PAIR_DEFAULT == 1 && sm_count >= 2 && tiles_m >= 2) {
+        const int pairs_m = (tiles_m + 1) / 2, npairs = sm_count / 2;
+        int bn = 0, sp = 1;
+        pick_pair_tile(N, pairs_m, npairs, kb_total, splits, b_mn, &bn, &sp);
+        if (bn > 0) {
+            const long work = (long)pairs_m * (N / bn) * sp;
+            out[0] = 1; out[1] = bn; out[2] = sp; out[3] = 2 * (int)std::min<long>(work, npairs);
+            return 0;
+        }
+    }
+    const int bn = pick_bn_for(N, tiles_m, splits, b_mn, sm_count > 0 ? sm_count : 148);
+    if (bn == 0) return -1;
+    const int kbps = (kb_total + splits - 1) / splits, sp = (kb_total + kbps - 1) / kbps;
+    out[0] = 0; out[1] = bn; out[2] = sp; out[3] = (int)std::min<long>((long)tiles_m * (N / bn) * sp, sm_count);
+    return 0;
+}
+
 // A: K-major -> A.rows = M, A.cols = K;  MN-major -> A.rows = K, A.cols = M.   Same for B with N.
 // Returns the number of split-K planes written, or -1 if this shape cannot take the tensor-core path.
 int st_launch_gemm_tc(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand& B, float* C, long ldc, int M, int N, int K,
@@ -692,23 +736,9 @@ int st_launch_gemm_tc(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand&
     if (pair_env == 1 && sm_count >= 2 && (M + BM - 1) / BM >= 2 && !(A.ld & 3) && !(B.ld & 3) && !(ldc & 3) && !(N & 3) &&
         (a_mn || K % BKF == 0) && (b_mn || K % BKF == 0)) {
         const int tiles_m = (M + BM - 1) / BM, pairs_m = (tiles_m + 1) / 2, npairs = sm_count / 2;
-        // tile width and split count together: minimise the operand bytes one CTA pulls in over its rounds of work items
-        // (A tile + half B tile per k-block, plus the tile's store), the quantity these GEMMs are bound by
         const int kb_total = (K + BKF - 1) / BKF;
         int BN2 = 0, SP2 = 1;
-        double best = 0;
-        for (int bn = 256; bn >= 64; bn -= 16) {
-            if (N % bn || (b_mn ? (bn % 64) : ((bn / 2) % 8))) continue;
-            for (int sp = splits; sp >= 1; --sp) {
-                const int kbps = (kb_total + sp - 1) / sp;
-                if ((kb_total + kbps - 1) / kbps != sp) continue;
-                if (sp < splits && 2 * sp < splits) break;            // keep at least half the requested split-K parallelism
-                const long work = (long)pairs_m * (N / bn) * sp;
-                const long rounds = (work + npairs - 1) / npairs;
-                const double cost = (double)rounds * ((double)kbps * (A_BYTES + bn / 2 * 128) + 0.5 * BM * bn * 4 + 8192.0);
-                if (BN2 == 0 || cost < best) { BN2 = bn; SP2 = sp; best = cost; }
-            }
-        }
+        pick_pair_tile(N, pairs_m, npairs, kb_total, splits, b_mn, &BN2, &SP2);
         if (BN2 > 0) {
             TcParams p;
             p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.BN = BN2;
