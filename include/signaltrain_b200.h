@@ -136,6 +136,14 @@ int st_loss(st_handle* h, const float* y_hat, const float* y, const float* mag_h
             const float* scale_by_freq, float l1_coef, int batch,
             float* loss, float* g_y_hat, float* g_mag_hat, void* stream);
 
+/* The same loss for tensors that do not come from this handle's model: wave tensors (batch, n_wave), spectra
+ * (batch, n_frames, n_bins) -- e.g. utils/lr_finder.py:38 passes the INPUT magnitude (B, T, F) as mag_hat.
+ * n_wave must be a multiple of 4.  Nothing but the three sizes is taken from the call; the handle only lends its
+ * reduction scratch and device. */
+int st_loss_shaped(st_handle* h, const float* y_hat, const float* y, const float* mag_hat,
+                   const float* scale_by_freq, float l1_coef, int batch, int n_wave, int n_frames, int n_bins,
+                   float* loss, float* g_y_hat, float* g_mag_hat, void* stream);
+
 /* loss_functions.mae (loss_functions.py:22-23) -- validation metric, train.py:58. */
 int st_mae(st_handle* h, const float* a, const float* b, long n, float* out, void* stream);
 

@@ -48,6 +48,8 @@ _SIGNATURES = {
                                   c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
     "st_loss": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_float, ctypes.c_int,
                                c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
+    "st_loss_shaped": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_float, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
     "st_mae": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_long, c_float_p, ctypes.c_void_p]),
     "st_backward": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p,
                                    ctypes.c_void_p, ctypes.c_void_p]),

@@ -94,6 +94,22 @@ struct StageScope {
 
 static thread_local char g_create_err[1024] = "";
 
+// Every entry point runs on the handle's device and puts the caller's current device back on return (a process may hold
+// engines on several GPUs, and torch allocates on the CURRENT device).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+        else prev = -1;                                  // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ST_ON_DEVICE(h)                                                                   \
+    DeviceGuard guard__((h)->device);                                                     \
+    if (!guard__.ok) return st_fail_msg(h, "cudaSetDevice(%d) failed", (h)->device)
+
 // offsets inside h->small (floats)
 enum { SM_LOSS = 0, SM_NORM = 2400, SM_MAE = 3008, SM_TOTAL_NORM = 4200, SM_COEF = 4201, SM_FLOATS = 4352 };
 enum { CT_LOSS = 0, CT_NORM = 1, CT_MAE = 2, CT_COUNT = 4 };
@@ -173,8 +189,9 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     const int L = (OT - 1) * H - N;
     if (L <= 0 || L > C || (L & 3)) return st_fail_msg(nullptr, "st_create: invalid output size L=%d", L);
 
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) return st_fail_cuda(nullptr, e, "cudaSetDevice", __FILE__, __LINE__);
+    DeviceGuard guard(device);
+    if (!guard.ok) return st_fail_msg(nullptr, "st_create: cudaSetDevice(%d) failed", device);
+    cudaError_t e;
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return st_fail_cuda(nullptr, e, "cudaGetDeviceProperties", __FILE__, __LINE__);
@@ -286,7 +303,7 @@ static void free_batch_buffers(st_handle* h) {
 
 extern "C" void st_destroy(st_handle* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     free_batch_buffers(h);
     if (h->dct_ws) cudaFree(h->dct_ws);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -365,6 +382,7 @@ static int check_ptrs(st_handle* h, const void* const* p, int n, const char* wha
 
 extern "C" int st_init_frontend(st_handle* h, float* const* params, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (check_ptrs(h, (const void* const*)params, 4, "st_init_frontend(params)")) return 1;
     ST_CUDA_OK(cudaSetDevice(h->device));
     st_launch_init_frontend(h->d, params[0], params[1], params[2], params[3], reinterpret_cast<float*>(h->win), (cudaStream_t)stream);
@@ -516,6 +534,7 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
 extern "C" int st_forward(st_handle* h, const float* x, const float* knobs, int batch, const float* const* params,
                           float* y_hat, float* mag, float* mag_hat, float* const* acts, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!x || !knobs || !y_hat) return st_fail_msg(h, "st_forward: null x / knobs / y_hat");
     if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_forward(params)")) return 1;
     if (acts && check_ptrs(h, (const void* const*)acts, ST_NUM_ACTS, "st_forward(acts)")) return 1;
@@ -525,6 +544,7 @@ extern "C" int st_forward(st_handle* h, const float* x, const float* knobs, int 
 extern "C" int st_loss(st_handle* h, const float* y_hat, const float* y, const float* mag_hat, const float* sbf,
                        float l1_coef, int batch, float* loss, float* g_y_hat, float* g_mag_hat, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!y_hat || !y || !mag_hat || !loss) return st_fail_msg(h, "st_loss: null argument");
     if (batch <= 0) return st_fail_msg(h, "st_loss: batch must be positive");
     ST_CUDA_OK(cudaSetDevice(h->device));
@@ -537,8 +557,29 @@ extern "C" int st_loss(st_handle* h, const float* y_hat, const float* y, const f
     return 0;
 }
 
+extern "C" int st_loss_shaped(st_handle* h, const float* y_hat, const float* y, const float* mag_hat, const float* sbf,
+                              float l1_coef, int batch, int n_wave, int n_frames, int n_bins, float* loss, float* g_y_hat,
+                              float* g_mag_hat, void* stream) {
+    if (!h) return 1;
+    ST_ON_DEVICE(h);
+    if (!y_hat || !y || !mag_hat || !loss) return st_fail_msg(h, "st_loss_shaped: null argument");
+    if (batch <= 0 || n_wave <= 0 || n_frames <= 0 || n_bins <= 0 || (n_wave & 3))
+        return st_fail_msg(h, "st_loss_shaped: need batch, n_frames, n_bins > 0 and n_wave a positive multiple of 4 (got %d, %d, %d, %d)",
+                           batch, n_frames, n_bins, n_wave);
+    StDims d = h->d;
+    d.L = n_wave; d.OT = n_frames; d.F = n_bins;
+    {
+        StageScope sc(h, SG_LOSS, 1, (cudaStream_t)stream);
+        st_launch_loss(d, y_hat, y, mag_hat, sbf, l1_coef, batch, loss, g_y_hat, g_mag_hat, h->small + SM_LOSS,
+                       h->counters + CT_LOSS, (cudaStream_t)stream);
+    }
+    ST_LAUNCH_OK(h);
+    return 0;
+}
+
 extern "C" int st_mae(st_handle* h, const float* a, const float* b, long n, float* out, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!a || !b || !out || n <= 0) return st_fail_msg(h, "st_mae: bad argument");
     ST_CUDA_OK(cudaSetDevice(h->device));
     st_launch_mae(a, b, n, out, h->small + SM_MAE, h->counters + CT_MAE, (cudaStream_t)stream);
@@ -672,6 +713,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
 extern "C" int st_backward(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat, int batch,
                            const float* const* params, float* const* grads, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!g_y_hat) return st_fail_msg(h, "st_backward: null g_y_hat");
     if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_backward(params)")) return 1;
     if (check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_backward(grads)")) return 1;
@@ -681,6 +723,7 @@ extern "C" int st_backward(st_handle* h, const float* g_y_hat, const float* g_ma
 extern "C" int st_backward_begin(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat, int batch,
                                  const float* const* params, float* const* grads, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!g_y_hat) return st_fail_msg(h, "st_backward_begin: null g_y_hat");
     if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_backward_begin(params)")) return 1;
     if (check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_backward_begin(grads)")) return 1;
@@ -691,6 +734,7 @@ extern "C" int st_backward_begin(st_handle* h, const float* g_y_hat, const float
 extern "C" int st_backward_finish(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat, int batch,
                                   const float* const* params, float* const* grads, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (h->bwd_ss < 0) return st_fail_msg(h, "st_backward_finish: no st_backward_begin before it");
     if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_backward_finish(params)")) return 1;
     if (check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_backward_finish(grads)")) return 1;
@@ -701,6 +745,7 @@ extern "C" int st_backward_finish(st_handle* h, const float* g_y_hat, const floa
 
 extern "C" int st_clip_grad_norm(st_handle* h, float* const* grads, float max_norm, float* total_norm, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (check_ptrs(h, (const void* const*)grads, 4, "st_clip_grad_norm(grads)")) return 1;
     ST_CUDA_OK(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
@@ -755,6 +800,7 @@ static int adam_impl(st_handle* h, float* const* params, const float* const* gra
 extern "C" int st_adam_step(st_handle* h, float* const* params, const float* const* grads, float* const* exp_avg,
                             float* const* exp_avg_sq, const st_adam* hp, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!hp) return st_fail_msg(h, "st_adam_step: null hyper-parameters");
     if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_adam_step(params)") ||
         check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_adam_step(grads)") ||
@@ -782,6 +828,7 @@ static int grad_step_impl(st_handle* h, const float* x, const float* y, const fl
 extern "C" int st_grad_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch, float* const* params,
                             float* const* grads, const float* sbf, float l1_coef, float* loss, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!x || !y || !knobs || !loss) return st_fail_msg(h, "st_grad_step: null argument");
     if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_grad_step(params)") ||
         check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_grad_step(grads)"))
@@ -794,6 +841,7 @@ extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const
                              float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                              const float* sbf, float l1_coef, const st_adam* hp, float* loss, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!x || !y || !knobs || !hp || !loss) return st_fail_msg(h, "st_train_step: null argument");
     if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_train_step(params)") ||
         check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_train_step(grads)") ||
@@ -868,6 +916,7 @@ extern "C" int st_debug_read(st_handle* h, const char* name, float* dst, long n)
 
 extern "C" int st_set_precision(st_handle* h, int mode) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (mode != ST_PRECISION_FP32 && mode != ST_PRECISION_TF32)
         return st_fail_msg(h, "st_set_precision: unknown mode %d (0 = fp32, 1 = tf32)", mode);
     if (mode == ST_PRECISION_TF32 && !h->use_tc)
@@ -880,6 +929,7 @@ extern "C" int st_get_precision(const st_handle* h) { return h ? (h->passes == 1
 
 extern "C" int st_set_training(st_handle* h, int on) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     h->training = on != 0;
     return 0;
 }
@@ -890,6 +940,7 @@ extern "C" const char* st_profile_stage_name(int i) { return (i >= 0 && i < SG_C
 
 extern "C" int st_profile(st_handle* h, int enable) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     h->prof_on = enable != 0;
     return 0;
 }
@@ -939,6 +990,7 @@ extern "C" int st_debug_gemm(st_handle* h, int use_tc /*0 FFMA, 1 tcgen05, 2 tcg
 // (backward: 8 regions x {magnitude, phase}; then tcgen05 forward: 4 regions x 2; 24 values).  Reading resets them.  out may be NULL.
 extern "C" int st_debug_ae_timing(st_handle* h, int on, long long* out_host) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     ST_CUDA_OK(cudaSetDevice(h->device));
     ST_CUDA_OK(cudaDeviceSynchronize());
     if (on && !h->ae_timing) {
@@ -970,6 +1022,7 @@ static long up4(long n) { return (n + 3) / 4 * 4; }
 extern "C" int st_dct_analysis(st_handle* h, const float* x, const float* w, const float* bias, int batch, int chunk, int ft_size,
                                int w_size, int hop, float* out, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!x || !w || !bias || !out) return st_fail_msg(h, "st_dct_analysis: null argument");
     if (batch <= 0 || chunk <= 0 || ft_size <= 0 || w_size <= 0 || hop <= 0 || (chunk & 3) || (ft_size & 3) || (w_size & 31) || (hop & 3))
         return st_fail_msg(h, "st_dct_analysis: sizes must be positive, chunk / ft_size / hop multiples of 4, w_size of 32");
@@ -1003,6 +1056,7 @@ extern "C" int st_dct_analysis(st_handle* h, const float* x, const float* w, con
 extern "C" int st_dct_synthesis(st_handle* h, const float* x_ft, const float* w, int batch, int frames, int ft_size, int w_size,
                                 int hop, float* wave, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!x_ft || !w || !wave) return st_fail_msg(h, "st_dct_synthesis: null argument");
     if (batch <= 0 || frames <= 0 || ft_size <= 0 || w_size <= 0 || hop <= 0 || (ft_size & 31) || (w_size & 3) || (hop & 3))
         return st_fail_msg(h, "st_dct_synthesis: sizes must be positive, ft_size a multiple of 32, w_size / hop of 4");
@@ -1033,6 +1087,7 @@ extern "C" int st_dct_synthesis(st_handle* h, const float* x_ft, const float* w,
 // ---- data step in front of the path -------------------------------------------------------
 extern "C" int st_compressor_4c(st_handle* h, const float* x, const double* knobs_wc, int batch, int n, double sr, float* y, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!x || !knobs_wc || !y) return st_fail_msg(h, "st_compressor_4c: null argument");
     if (batch <= 0 || n <= 0 || !(sr > 0)) return st_fail_msg(h, "st_compressor_4c: batch, n and sr must be positive");
     if (dct_workspace(h, (long)batch * n)) return 1;
@@ -1045,6 +1100,7 @@ extern "C" int st_compressor_4c(st_handle* h, const float* x, const double* knob
 extern "C" int st_crop_windows(st_handle* h, const float* corpus_x, const float* corpus_y, long corpus_len, const long* offsets_host,
                                const float* signs, int batch, int chunk, int y_size, float* x, float* y, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!corpus_x || !corpus_y || !offsets_host || !x || !y) return st_fail_msg(h, "st_crop_windows: null argument");
     if (batch <= 0 || chunk <= 0 || y_size <= 0 || y_size > chunk) return st_fail_msg(h, "st_crop_windows: need 0 < y_size <= chunk");
     for (int b = 0; b < batch; ++b)
@@ -1066,6 +1122,7 @@ extern "C" int st_crop_windows(st_handle* h, const float* corpus_x, const float*
 extern "C" int st_analysis(st_handle* h, const float* x, const float* w_real, const float* w_imag, int batch, float* an_real,
                            float* an_imag, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!x || !w_real || !w_imag || !an_real || !an_imag) return st_fail_msg(h, "st_analysis: null argument");
     return analysis_only(h, x, w_real, w_imag, batch, an_real, an_imag, (cudaStream_t)stream);
 }
@@ -1073,6 +1130,7 @@ extern "C" int st_analysis(st_handle* h, const float* x, const float* w_real, co
 extern "C" int st_synthesis(st_handle* h, const float* real, const float* imag, const float* w_real, const float* w_imag, int batch,
                             float* wave, void* stream) {
     if (!h) return 1;
+    ST_ON_DEVICE(h);
     if (!real || !imag || !w_real || !w_imag || !wave) return st_fail_msg(h, "st_synthesis: null argument");
     return synthesis_only(h, real, imag, w_real, w_imag, batch, wave, (cudaStream_t)stream);
 }

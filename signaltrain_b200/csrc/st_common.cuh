@@ -170,6 +170,16 @@ int st_launch_ae_backward_f2(const StDims& d, const AeGeom& g, const AeParams& p
                              float* g_spec_lo, float* partials, long long* timing /*nullable: 16 counters*/, int sm_count,
                              cudaStream_t s);
 
+// st_ae_tm.cu: tcgen05 autoencoders with TMEM-resident activations (production path; T <= 64, OT <= 16, K <= 8).
+// Forward: both autoencoders of a 128-row tile in one CTA, no saved activations.  Returns false when the geometry is not covered.
+// wpack: workspace of st_ae_tm_pack_floats() floats holding the shared-memory image of the weights; rebuilt on s_pack when pack is set.
+// dbg (nullable, tests only): [2][9][128][64] layer outputs of tile 0.
+long st_ae_tm_pack_floats();
+bool st_launch_ae_forward_tm(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
+                             const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo,
+                             float* wpack, float* dbg, long long* timing /*nullable: 256 counters*/, int sm_count,
+                             bool pack, cudaStream_t s_pack, cudaStream_t s);
+
 // st_data.cu
 void st_launch_compressor_4c(const float* x, const double* knobs_wc, int B, int n, double sr, float* scratch, float* y, cudaStream_t s);
 void st_launch_crop_windows(const float* cx, const float* cy, const long* off, const float* sign, int B, int C, int L, float* ox,

@@ -60,6 +60,17 @@ class Engine:
     _registry = []          # weak references to live engines (loss_functions looks engines up by shape)
 
     @classmethod
+    def any_on(cls, device):
+        """Some live engine on `device` (for the geometry-free reductions), or None."""
+        for ref in list(cls._registry):
+            e = ref()
+            if e is None:
+                cls._registry.remove(ref)
+            elif e.device == device:
+                return e
+        return None
+
+    @classmethod
     def find(cls, device, L, OT=None, F=None):
         for ref in list(cls._registry):
             e = ref()
@@ -225,6 +236,25 @@ class Engine:
         g_m = torch.empty_like(mag_hat) if want_grads else None
         self._ok(self.lib.st_loss(self.h, _ptr(y_hat), _ptr(y), _ptr(mag_hat), _ptr(sbf), float(l1_coef), B, _ptr(loss),
                                   _ptr(g_y), _ptr(g_m), self._stream()), "st_loss")
+        return loss, g_y, g_m
+
+    def loss_shaped(self, y_hat, y, mag_hat, sbf, l1_coef, want_grads=True):
+        """calc_loss for tensors of any (B, n_wave) / (B, n_frames, n_bins) shape (utils/lr_finder.py:38 passes the input
+        magnitude as mag_hat): only the sizes are read off the tensors, the handle lends scratch and device."""
+        B, n_wave = y_hat.shape
+        _check(y_hat, "y_hat", (B, n_wave), self.device)
+        _check(y, "y", (B, n_wave), self.device)
+        if mag_hat.dim() != 3 or mag_hat.shape[0] != B:
+            raise RuntimeError(f"signaltrain_b200: mag_hat must be (B, frames, bins), got {tuple(mag_hat.shape)}")
+        _check(mag_hat, "mag_hat", device=self.device)
+        n_frames, n_bins = int(mag_hat.shape[1]), int(mag_hat.shape[2])
+        if sbf is not None:
+            _check(sbf, "scale_by_freq", (n_bins,), self.device)
+        loss = torch.empty((), device=self.device, dtype=torch.float32)
+        g_y = torch.empty_like(y_hat) if want_grads else None
+        g_m = torch.empty_like(mag_hat) if want_grads else None
+        self._ok(self.lib.st_loss_shaped(self.h, _ptr(y_hat), _ptr(y), _ptr(mag_hat), _ptr(sbf), float(l1_coef), B, int(n_wave),
+                                         n_frames, n_bins, _ptr(loss), _ptr(g_y), _ptr(g_m), self._stream()), "st_loss_shaped")
         return loss, g_y, g_m
 
     def mae(self, a, b):

@@ -7,50 +7,25 @@ from .engine import Engine, Geometry
 _engines = {}
 
 
-def _engine_like(y_hat, mag_hat=None):
-    """A loss-only engine for tensors that did not come from a model on this device (geometry only matters
-    through L and (OT, F), which are read off the tensor shapes)."""
-    if not y_hat.is_cuda:
+def _engine_on(t):
+    """An engine on the tensor's device: the model's if one lives there, else a small default-geometry handle kept per
+    device.  The loss / MAE reductions take their sizes from the tensors (st_loss_shaped), not from the handle."""
+    if not t.is_cuda:
         raise RuntimeError("signaltrain_b200.loss_functions: CUDA tensors only (no CPU fallback)")
-    dev = y_hat.device if y_hat.device.index is not None else torch.device("cuda", torch.cuda.current_device())
-    found = Engine.find(dev, int(y_hat.shape[1]), *((int(mag_hat.shape[1]), int(mag_hat.shape[2])) if mag_hat is not None else ()))
-    if found is not None:          # tensors produced by a model on this device: share its engine
-        return found
-    key = (y_hat.device.index, tuple(y_hat.shape[1:]), None if mag_hat is None else tuple(mag_hat.shape[1:]))
-    eng = _engines.get(key)
+    dev = t.device if t.device.index is not None else torch.device("cuda", torch.cuda.current_device())
+    eng = Engine.any_on(dev)
     if eng is None:
-        g = Geometry.__new__(Geometry)
-        L = int(y_hat.shape[1])
-        if mag_hat is not None:
-            OT, F = int(mag_hat.shape[1]), int(mag_hat.shape[2])
-        else:
-            OT, F = 9, 513
-        N = 2 * (F - 1)
-        H = (L + N) // (OT - 1)
-        if (OT - 1) * H - N != L:
-            raise RuntimeError(f"calc_loss: shapes y_hat {tuple(y_hat.shape)} / mag_hat "
-                               f"{None if mag_hat is None else tuple(mag_hat.shape)} do not describe a SignalTrain model")
-        C = None
-        for T in range(OT, 65):      # any chunk consistent with (N, H, T) will do for a loss-only handle
-            c = (T - 1) * H - N
-            if c >= L and c % 4 == 0 and (c + N) // H + 1 == T:
-                C = c
-                break
-        if C is None:
-            raise RuntimeError("calc_loss: cannot derive a consistent geometry for a loss-only engine")
-        g.C, g.N, g.H, g.T, g.OT, g.L, g.F, g.K, g.R = C, N, H, T, OT, L, F, 1, 64
-        g.intended_out_chunk = L
-        eng = Engine(g, y_hat.device)
-        _engines[key] = eng
+        eng = _engines.get(dev.index)
+        if eng is None:
+            eng = _engines[dev.index] = Engine(Geometry(1, 4, 1), dev)
     return eng
 
 
 class _CalcLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y_hat, y, mag_hat, sbf, l1_coef):
-        eng = _engine_like(y_hat, mag_hat)
-        need = y_hat.requires_grad or mag_hat.requires_grad
-        loss, g_y, g_m = eng.loss(y_hat.contiguous(), y.contiguous(), mag_hat.contiguous(), sbf, l1_coef, want_grads=True)
+        eng = _engine_on(y_hat)
+        loss, g_y, g_m = eng.loss_shaped(y_hat.contiguous(), y.contiguous(), mag_hat.contiguous(), sbf, l1_coef, want_grads=True)
         ctx.save_for_backward(g_y, g_m)
         return loss
 
@@ -87,14 +62,14 @@ def calc_loss(y_hat, y_cuda, mag_hat, batch_size=20, scale_by_freq=None, l1_lamb
 
 
 def logcosh(y_hat, y):
-    eng = _engine_like(y_hat)
-    mh = torch.zeros((y_hat.shape[0], eng.g.OT, eng.g.F), device=y_hat.device)
-    loss, _, _ = eng.loss(y_hat.contiguous(), y.float().contiguous(), mh, None, 0.0, want_grads=False)
+    eng = _engine_on(y_hat)
+    mh = torch.zeros((y_hat.shape[0], 1, 4), device=y_hat.device)
+    loss, _, _ = eng.loss_shaped(y_hat.contiguous(), y.float().contiguous(), mh, None, 0.0, want_grads=False)
     return loss
 
 
 def mae(x, x_hat):
     if not x.is_cuda:
         raise RuntimeError("signaltrain_b200.loss_functions: CUDA tensors only (no CPU fallback)")
-    eng = next(iter(_engines.values()), None) or _engine_like(x if x.dim() == 2 else x.reshape(x.shape[0], -1))
+    eng = _engine_on(x)
     return eng.mae(x.float().contiguous(), x_hat.float().contiguous())

@@ -15,6 +15,14 @@ class Adam(torch.optim.Optimizer):
                                       capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False))
         self._step = 0
 
+    def load_state_dict(self, state_dict):
+        """torch's loader restores exp_avg / exp_avg_sq / step per parameter; the fused step reads its counter from
+        `_step`, so it is taken from the restored state (bias correction must continue where the checkpoint stopped)."""
+        super().load_state_dict(state_dict)
+        params = self._model.ordered_parameters()
+        steps = [float(self.state[p]["step"]) for p in params if "step" in self.state.get(p, {})]
+        self._step = int(max(steps)) if steps else 0
+
     def _state_lists(self):
         params = self._model.ordered_parameters()
         m, v = [], []
