@@ -44,6 +44,24 @@ struct Tab {
     __host__ __device__ static constexpr int boff(int l) { int o = 0; for (int i = 0; i < l; ++i) o += n(i); return o; }
     static constexpr int wfloats = woff(NL);     // floats of one forward weight plane (every slab: multiple of 8 rows x 128 B)
     static constexpr int bfloats = boff(NL);
+    // ---- backward.  act[l] = input of layer l (act[0] = the track, act[l] = ELU output of layer l-1); gz[l] = dLoss/d(pre-activation l)
+    // data gradient of layer l:  gh[l] = gz[l] . W_l  (dn(l) columns; the knob columns of layer 4 carry none)
+    __host__ __device__ static constexpr int dn(int l) { constexpr int t[NL] = {KP1_, 64, 32, 16, 16, 16, 16, 32, 64}; return t[l]; }
+    __host__ __device__ static constexpr int tslab(int l) { return (n(l) + 31) / 32 * 32; }      // K extent (layer outputs) of the W^T slabs
+    __host__ __device__ static constexpr int toff(int l) { int o = 0; for (int i = 0; i < l; ++i) o += dn(i) * tslab(i); return o; }
+    static constexpr int tfloats = toff(NL);
+    // weight gradient of layer l on the tensor core: D_w[128 x nf] = Mop^T-tile (live rows at lane `moff`) x Nop, reduction over
+    // the tile's rows.  Mop / Nop = gz[l] / act[l] in the orientation that balances the flush registers (see wg_* below).
+    __host__ __device__ static constexpr int act_w(int l) { constexpr int t[NL] = {KP1_, 64, 32, 16, KP5_, 16, 16, 32, 64}; return t[l]; }   // staged act[l] features
+    __host__ __device__ static constexpr bool wg_m_is_gz(int l) { constexpr bool t[NL] = {true, false, false, true, false, true, true, true, false}; return t[l]; }
+    __host__ __device__ static constexpr int wg_mf(int l) { return wg_m_is_gz(l) ? n(l) : act_w(l); }
+    __host__ __device__ static constexpr int wg_nf(int l) { return wg_m_is_gz(l) ? (act_w(l) + 15) / 16 * 16 : n(l); }
+    __host__ __device__ static constexpr int wg_moff(int l) { constexpr int t[NL] = {0, 0, 64, 0, 32, 16, 96, 64, 64}; return t[l]; }
+    __host__ __device__ static constexpr int wg_reg(int l) { constexpr int t[NL] = {0, 32, 48, 64, 64, 64, 48, 0, 32}; return t[l]; }
+    __host__ __device__ static constexpr bool wg_wide(int l) { return (wg_mf(l) + wg_nf(l)) * 256 > 12288; }     // slice needs two 12 KB sub-buffers
+    // sub-buffer uses (per tile) before layer l's, layers being processed 8, 7, ..., 0: wide layers use every sub-buffer twice
+    __host__ __device__ static constexpr int wg_uses_before(int l) { int c = 0; for (int i = NL - 1; i > l; --i) c += wg_wide(i) ? 2 : 1; return c; }
+    static constexpr int wg_uses_per_tile = wg_uses_before(-1);
 };
 
 __device__ __forceinline__ float elu_f(float z) {
@@ -53,8 +71,24 @@ __device__ __forceinline__ float elu_f(float z) {
 }
 __device__ __forceinline__ float elu_grad(float h) { return h > 0.f ? 1.f : h + 1.f; }   // dELU/dz through the output h
 
-// One copy of the libdevice routines in the instruction stream (they are inlined per call site otherwise: ~25 call sites).
-__device__ __noinline__ float atan2_ni(float y, float x) { return atan2f(y, x); }
+// atan2 for the phase track (nn_proc.py:310), ~25 instructions, inlined: one division by folding the second range reduction
+// into it (|t| <= tan(pi/8) after it), then the 4-term minimax polynomial of Cephes atanf (2 ulp).  atan2(0, 0) = 0 like
+// torch / libdevice; the model never feeds infinities or NaNs here that it does not also produce in the reference.
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const bool mid = mn > 0.41421356237f * mx;                 // atan(a) = pi/4 + atan((a - 1) / (a + 1))
+    const float num = mid ? mn - mx : mn, den = mid ? mn + mx : mx;
+    const float t = den > 0.f ? __fdividef(num, den) : 0.f;
+    const float z = t * t;
+    float p = fmaf(8.05374449538e-2f, z, -1.38776856032e-1f);
+    p = fmaf(p, z, 1.99777106478e-1f);
+    p = fmaf(p, z, -3.33329491539e-1f);
+    float r = fmaf(t * z, p, t) + (mid ? 0.78539816339744831f : 0.f);
+    if (ay > ax) r = 1.5707963267948966f - r;
+    if (x < 0.f) r = 3.14159265358979323846f - r;
+    return copysignf(r, y);
+}
 __device__ __noinline__ float2 sincos_ni(float x) {
     float s, c;
     sincosf(x, &s, &c);
@@ -83,17 +117,21 @@ __device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&r)[N]) 
     else tmem_st32(taddr, r);
 }
 
-// Write NV values of this thread's row as an exact tf32 pair into the (hi, lo) A-operand columns.
+// Two-term tf32 split on the integer / fp32 pipes (cvt.rna.tf32 issues on the quarter-rate conversion pipe, which the ELU's
+// ex2 already loads): hi = x rounded to 10 mantissa bits, nearest with ties away, exactly as cvt.rna does it on the magnitude
+// (add half an ulp to the bit pattern, clear the 13 low bits); lo = x - hi is exact in fp32 and is handed over unrounded --
+// the tensor core reads its upper 19 bits, i.e. truncates it, a 2^-22 relative effect on x.
+__device__ __forceinline__ void split_tf32_alu(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// Write NV values of this thread's row as a tf32 pair into the (hi, lo) A-operand columns.
 template <int NV>
 __device__ __forceinline__ void store_pair(uint32_t t_hi, uint32_t t_lo, const float (&v)[NV]) {
     uint32_t hi[NV], lo[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        float h, l;
-        st_split_tf32(v[i], h, l);
-        hi[i] = __float_as_uint(h);
-        lo[i] = __float_as_uint(l);
-    }
+    for (int i = 0; i < NV; ++i) split_tf32_alu(v[i], hi[i], lo[i]);
     tmem_st<NV>(t_hi, hi);
     tmem_st<NV>(t_lo, lo);
 }
@@ -102,12 +140,16 @@ __device__ __forceinline__ void store_pair(uint32_t t_hi, uint32_t t_lo, const f
 // step by ae_pack_kernel (the weights change every step), copied into each CTA with one-dimensional bulk copies.
 template <class TB>
 __host__ __device__ constexpr int image_floats() { return 2 * TB::wfloats + (TB::bfloats + 255) / 256 * 256; }   // keeps the next image 1024-byte aligned
+// backward image: [W hi][W lo][W^T hi][W^T lo][bias]
+template <class TB>
+__host__ __device__ constexpr int bwd_image_floats() { return 2 * TB::wfloats + 2 * TB::tfloats + (TB::bfloats + 255) / 256 * 256; }
 
 // B operand of the forward layers = W[n = out][k = in], K-major, zero padded to (n(l), 32-float K-blocks), as (hi, lo).
-template <class TB>
+// BWD: the backward image (adds the data-gradient operand W^T[n = in][k = out], K-major over the layer's outputs).
+template <class TB, bool BWD>
 __global__ void ae_pack_kernel(AeGeom g, AeParams pm, AeParams pp, float* __restrict__ image) {
     const AeParams& p = blockIdx.y ? pp : pm;
-    float* img = image + (long)blockIdx.y * image_floats<TB>();
+    float* img = image + (long)blockIdx.y * (BWD ? bwd_image_floats<TB>() : image_floats<TB>());
     const int l = blockIdx.x;
     const int IN = g.in[l], OUT = g.out[l], NP = TB::n(l), KP = TB::kslab(l);
     float* whi = img + TB::woff(l);
@@ -121,8 +163,22 @@ __global__ void ae_pack_kernel(AeGeom g, AeParams pm, AeParams pp, float* __rest
         whi[off] = hi;
         wlo[off] = lo;
     }
-    float* bias = img + 2 * TB::wfloats + TB::boff(l);
+    float* bias = img + 2 * TB::wfloats + (BWD ? 2 * TB::tfloats : 0) + TB::boff(l);
     for (int o = threadIdx.x; o < NP; o += blockDim.x) bias[o] = (o < OUT) ? __ldg(p.b[l] + o) : 0.f;
+    if (BWD) {
+        const int DN = TB::dn(l), KS = TB::tslab(l), BACK = (l == 4) ? 16 : IN;      // knob inputs carry no data gradient
+        float* thi = img + 2 * TB::wfloats + TB::toff(l);
+        float* tlo = thi + TB::tfloats;
+        for (int idx = threadIdx.x; idx < DN * KS; idx += blockDim.x) {
+            const int i = idx / KS, o = idx - i * KS;
+            const float w = (o < OUT && i < BACK) ? __ldg(p.W[l] + o * IN + i) : 0.f;
+            float hi, lo;
+            st_split_tf32(w, hi, lo);
+            const int off = sw128_off(i, o, DN);
+            thi[off] = hi;
+            tlo[off] = lo;
+        }
+    }
 }
 
 // global -> shared bulk copy (bytes: multiple of 16), completion on an mbarrier of this CTA
@@ -172,8 +228,10 @@ __constant__ int c_n[NL] = {64, 32, 16, 16, 16, 16, 32, 64, 16};
 __constant__ int c_boff[NL] = {0, 64, 96, 112, 128, 144, 160, 192, 256};
 
 // Hidden-layer epilogue of one thread: NLOC accumulator columns -> bias + ELU -> (hi, lo) A columns of the next layer.
-template <int NLOC>
-__device__ __forceinline__ void epi_hidden(uint32_t t_d, uint32_t t_hi, uint32_t t_lo, const float* __restrict__ bias, float* dbg, long long* probe = nullptr) {
+// SAVE (backward kernel): the raw layer output is also kept in TMEM at t_save (ELU' and the weight gradients need it).
+template <int NLOC, bool SAVE = false>
+__device__ __forceinline__ void epi_hidden(uint32_t t_d, uint32_t t_hi, uint32_t t_lo, const float* __restrict__ bias, float* dbg,
+                                           uint32_t t_save = 0, long long* probe = nullptr) {
     uint32_t r[NLOC];
     tmem_ld<NLOC>(t_d, r);
     tmem_wait_ld();
@@ -193,6 +251,12 @@ __device__ __forceinline__ void epi_hidden(uint32_t t_d, uint32_t t_hi, uint32_t
         if (dbg) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) dbg[c0 + c] = h[c];
+        }
+        if (SAVE) {
+            uint32_t raw[CH];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) raw[c] = __float_as_uint(h[c]);
+            tmem_st<CH>(t_save + c0, raw);
         }
         store_pair<CH>(t_hi + c0, t_lo + c0, h);
     }
@@ -235,7 +299,11 @@ ae_fwd_tm_kernel(StDims d, const float* __restrict__ image, const float* __restr
     // mag_hat | phs_hat for the output stage
     float* tails = wbase + 2 * IMG;
     float* xch = tails;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tails + 2 * XCH_J * TILE);
+    // [re | im][KP1][TILE]: the NEXT tile's input frames, fetched with cp.async while this tile runs (each thread fetches and
+    // later reads only its own elements, so no barrier is involved); only when it fits beside the weights (T <= 32)
+    constexpr bool PRE = KP1 == 32;
+    float* pre = tails + 2 * XCH_J * TILE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pre + (PRE ? 2 * KP1 * TILE : 0));
     uint64_t* a_ready = bars;                              // [ae] epilogue -> issuer: the layer's A operand is in TMEM
     uint64_t* d_ready = bars + 2;                          // [ae] issuer -> epilogue: the accumulator is complete
     uint64_t* w_ready = bars + 4;                          // weight image landed
@@ -296,6 +364,24 @@ ae_fwd_tm_kernel(StDims d, const float* __restrict__ image, const float* __restr
         const float* mybias = wbase + ae * IMG + 2 * TB::wfloats;
         const int tail0 = d.T - d.OT, rowstride = 2 * d.Fp;
         uint32_t ph = 0;
+        constexpr int NLOC0 = KP1 / 4;
+        const int pc0 = grp * NLOC0;
+        auto prefetch = [&](int tile) {
+            const int R = tile * TILE + row;
+            const bool ok = tile < ntiles && R < BF;
+            const int b = ok ? R / d.F : 0, f = ok ? R - b * d.F : 0;
+            const float* sp = spec + (long)b * d.Tp * rowstride + f;
+#pragma unroll
+            for (int e = 0; e < NLOC0; ++e) {
+                const int t = pc0 + e;
+                const int bytes = (ok && t < d.T) ? 4 : 0;          // src-size 0: zero fill
+                const float* src = sp + (long)(bytes ? t : 0) * rowstride;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(pre + t * TILE + row)), "l"(src), "r"(bytes) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(pre + (KP1 + t) * TILE + row)), "l"(src + d.Fp), "r"(bytes) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (PRE) prefetch(blockIdx.x);
         mbar_wait_spin(w_ready, 0);                          // biases
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int R = tile * TILE + row;
@@ -314,18 +400,28 @@ ae_fwd_tm_kernel(StDims d, const float* __restrict__ image, const float* __restr
                 const int c0 = grp * NLOC;
                 const float* sp = spec + (long)b * d.Tp * rowstride + f;
                 float re[NLOC], im[NLOC], vm[NLOC], vp[NLOC];
+                if (PRE) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-                for (int e = 0; e < NLOC; ++e) {
-                    const bool in = ok && c0 + e < d.T;
-                    re[e] = in ? __ldg(sp + (long)(c0 + e) * rowstride) : 0.f;
-                    im[e] = in ? __ldg(sp + (long)(c0 + e) * rowstride + d.Fp) : 0.f;
+                    for (int e = 0; e < NLOC; ++e) {
+                        re[e] = pre[(c0 + e) * TILE + row];
+                        im[e] = pre[(KP1 + c0 + e) * TILE + row];
+                    }
+                    prefetch(tile + gridDim.x);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < NLOC; ++e) {
+                        const bool in = ok && c0 + e < d.T;
+                        re[e] = in ? __ldg(sp + (long)(c0 + e) * rowstride) : 0.f;
+                        im[e] = in ? __ldg(sp + (long)(c0 + e) * rowstride + d.Fp) : 0.f;
+                    }
                 }
 #pragma unroll
                 for (int e = 0; e < NLOC; ++e) {
                     const int t = c0 + e;
                     const bool in = ok && t < d.T;
                     vm[e] = sqrtf(re[e] * re[e] + im[e] * im[e]);
-                    vp[e] = in ? atan2_ni(im[e], re[e] + 1e-7f) : 0.f;
+                    vp[e] = in ? atan2_fast(im[e], re[e] + 1e-7f) : 0.f;
                     if (in && mag_out) mag_out[((long)b * d.T + t) * d.F + f] = vm[e];
                     if (t >= tail0 && t < d.T) {
                         tails[(t - tail0) * TILE + row] = vm[e];
@@ -354,9 +450,9 @@ ae_fwd_tm_kernel(StDims d, const float* __restrict__ image, const float* __restr
                 float* ld = mydbg ? mydbg + (long)l * TILE * 64 + c0 : nullptr;
                 const float* bl = mybias + c_boff[l] + c0;
                 long long* probe = (tl && ae == 0) ? timing + 192 + 4 * l : nullptr;
-                if (nloc == 32) epi_hidden<32>(t_d + c0, t_hi + c0, t_lo + c0, bl, ld, probe);
-                else if (nloc == 16) epi_hidden<16>(t_d + c0, t_hi + c0, t_lo + c0, bl, ld, probe);
-                else epi_hidden<8>(t_d + c0, t_hi + c0, t_lo + c0, bl, ld, probe);
+                if (nloc == 32) epi_hidden<32>(t_d + c0, t_hi + c0, t_lo + c0, bl, ld, 0u, probe);
+                else if (nloc == 16) epi_hidden<16>(t_d + c0, t_hi + c0, t_lo + c0, bl, ld, 0u, probe);
+                else epi_hidden<8>(t_d + c0, t_hi + c0, t_lo + c0, bl, ld, 0u, probe);
                 if (l == 3 && half == NSPLIT - 1 && TB::KP5 > 16) {
                     // knob concat (torch.cat, nn_proc.py:95-96): columns 16..23 of fnn_addknobs' input, zero padded
                     float kv[8];
@@ -429,9 +525,536 @@ ae_fwd_tm_kernel(StDims d, const float* __restrict__ image, const float* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// backward (one autoencoder per CTA; recomputes the forward chain in tensor memory instead of reading saved activations)
+// ---------------------------------------------------------------------------------------------------------------------
+// Per 128-row tile (thread = (row, column half) in two chain warpgroups):
+//   1. forward chain as above; every layer output h_l is ALSO kept raw in TMEM (256 columns);
+//   2. output side (nn_proc.py:115, 322, 325-326 backwards) gives gz[8];  then for l = 8..0 one MMA group
+//      gh[l] = gz[l] . W_l (A = gz[l] from TMEM, B = W_l^T from shared memory) and an epilogue gz[l-1] = gh[l] * ELU'(h_l);
+//      gh[0] (+ skip / residual gradient) leaves as the track gradient;
+//   3. weight gradients dW_l = gz[l]^T act[l] are a reduction over ROWS, so both operands go through shared memory: every chain
+//      warp writes its 32 rows of (gz[l], act[l]) as (hi, lo) K-major SWIZZLE_128B slices ([feature][32 rows]: conflict-free
+//      4-byte stores, one row per lane); a second issuing warp runs them as SS-mode MMAs (M = 128: the live feature rows sit at a
+//      lane offset chosen per layer, the other lanes read neighbouring shared memory and are never looked at) into a 32-column
+//      accumulator, which a third warpgroup folds into REGISTER accumulators after every layer (lane = feature, 80 registers);
+//      the same warpgroup sums gz over the slice rows for the bias gradients.  Per-CTA partial gradients go to global memory
+//      once, at the end (deterministic: no atomics).
+constexpr int BWD_CHAIN_WARPS = 8;                  // warps 0-7: (half = w >> 2, quadrant = w & 3)
+constexpr int BWD_FLUSH_WARP0 = 8;                  // warps 8-11: weight-gradient flush / bias gradient, quadrant = w & 3
+constexpr int BWD_ISSUER = 12;                      // chain MMAs
+constexpr int BWD_WISSUER = 13;                     // weight-gradient MMAs
+constexpr int BWD_THREADS = 14 * 32;
+constexpr int SUB_BYTES = 12288;                    // staging sub-buffer: 48 feature rows x 128 B x (hi, lo)
+// TMEM columns
+constexpr uint32_t TC_AH = 256, TC_AL = 320, TC_D = 384, TC_DW = 448;
+__host__ __device__ constexpr uint32_t tc_act(int l) { constexpr uint32_t t[NL] = {0, 0, 64, 96, 112, 128, 144, 160, 192}; return t[l]; }   // act[1..8]
+
+template <class TB>
+struct BwdSmem {
+    static constexpr uint32_t W_HI = 0, W_LO = 4u * TB::wfloats, STAGE = 8u * TB::wfloats;
+    static constexpr uint32_t WT_HI = STAGE + 4u * SUB_BYTES, WT_LO = WT_HI + 4u * TB::tfloats, BIAS = WT_LO + 4u * TB::tfloats;
+    static constexpr uint32_t VTAIL = BIAS + 4u * ((TB::bfloats + 255) / 256 * 256);
+    static constexpr uint32_t BARS = VTAIL + 4u * XCH_J * TILE;
+    static constexpr uint32_t TOTAL = BARS + 256;
+    static_assert(STAGE % 1024 == 0 && WT_HI % 1024 == 0 && WT_LO % 1024 == 0, "operand planes must be 1024-byte aligned");
+};
+
+__device__ __forceinline__ void umma_ss_lohi(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 ad, bd;\n\t"
+        "mov.b64 ad, {%1, %3};\n\t"
+        "mov.b64 bd, {%2, %3};\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// forward layer L of the backward kernel's single chain (recompute)
+template <class TB, int L>
+__device__ __forceinline__ void issue_refwd_layer(uint32_t dlo_base) {
+    constexpr int n = TB::n(L), ksteps = TB::kp(L) / 8;
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+    constexpr uint32_t hi16 = (BwdSmem<TB>::W_HI + 4u * TB::woff(L)) >> 4, lo16 = (BwdSmem<TB>::W_LO + 4u * TB::woff(L)) >> 4;
+#pragma unroll
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t bo = (uint32_t)((ks >> 2) * (n * 128) + (ks & 3) * 32) >> 4;
+        umma_ts_lohi(TC_D, TC_AL + 8 * ks, dlo_base + hi16 + bo, DESC_HI_SW128, idesc, ks > 0 ? 1u : 0u);
+        umma_ts_lohi(TC_D, TC_AH + 8 * ks, dlo_base + lo16 + bo, DESC_HI_SW128, idesc, 1u);
+        umma_ts_lohi(TC_D, TC_AH + 8 * ks, dlo_base + hi16 + bo, DESC_HI_SW128, idesc, 1u);
+    }
+}
+// data gradient of layer L:  gh[L] (dn columns) = gz[L] (n columns, TMEM) . W_L   (B = W_L^T [dn rows][n], K-major)
+template <class TB, int L>
+__device__ __forceinline__ void issue_dgrad_layer(uint32_t dlo_base) {
+    constexpr int dn = TB::dn(L), ksteps = TB::n(L) / 8;
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(dn >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+    constexpr uint32_t hi16 = (BwdSmem<TB>::WT_HI + 4u * TB::toff(L)) >> 4, lo16 = (BwdSmem<TB>::WT_LO + 4u * TB::toff(L)) >> 4;
+#pragma unroll
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t bo = (uint32_t)((ks >> 2) * (dn * 128) + (ks & 3) * 32) >> 4;
+        umma_ts_lohi(TC_D, TC_AL + 8 * ks, dlo_base + hi16 + bo, DESC_HI_SW128, idesc, ks > 0 ? 1u : 0u);
+        umma_ts_lohi(TC_D, TC_AH + 8 * ks, dlo_base + lo16 + bo, DESC_HI_SW128, idesc, 1u);
+        umma_ts_lohi(TC_D, TC_AH + 8 * ks, dlo_base + hi16 + bo, DESC_HI_SW128, idesc, 1u);
+    }
+}
+
+// Staging geometry of layer L's weight-gradient slice (one quadrant = 32 rows): byte offsets inside the slice buffer.
+template <class TB, int L>
+struct Stg {
+    static constexpr int MF = TB::wg_mf(L), NF = TB::wg_nf(L);
+    static constexpr uint32_t M_HI = 0, M_LO = MF * 128u, N_HI = 2u * MF * 128u, N_LO = N_HI + NF * 128u;
+    static constexpr bool M_IS_GZ = TB::wg_m_is_gz(L);
+    static constexpr uint32_t GZ_HI = M_IS_GZ ? M_HI : N_HI, GZ_LO = M_IS_GZ ? M_LO : N_LO;
+    static constexpr uint32_t ACT_HI = M_IS_GZ ? N_HI : M_HI, ACT_LO = M_IS_GZ ? N_LO : M_LO;
+    // Quadrants q and q + 2 share the 24 KB buffer (q & 1) and alternate strictly (q first): barriers are per QUADRANT
+    // (full[q]: slice written, free[q]: slice consumed), so every waiter observes every phase of the barrier it waits on
+    // (an mbarrier parity wait cannot tell phase k from phase k + 2).
+    __host__ __device__ static constexpr uint32_t buf(int q) { return BwdSmem<TB>::STAGE + (uint32_t)(q & 1) * 2u * SUB_BYTES; }
+    static_assert((MF + NF) * 256 <= 2 * SUB_BYTES, "slice does not fit its staging buffer");
+};
+
+// weight-gradient MMAs of layer L, slice q (32 rows = 4 k-steps)
+template <class TB, int L, int Q>
+__device__ __forceinline__ void issue_wgrad_slice(uint32_t dlo_base) {
+    using S = Stg<TB, L>;
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::NF >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+    constexpr uint32_t buf = S::buf(Q);
+    constexpr uint32_t moff = (uint32_t)TB::wg_moff(L) * 128u;
+    static_assert(buf + S::M_HI >= moff, "the A tile must start inside shared memory");
+    constexpr uint32_t a_hi = (buf + S::M_HI - moff) >> 4, a_lo = (buf + S::M_LO - moff) >> 4, b_hi = (buf + S::N_HI) >> 4, b_lo = (buf + S::N_LO) >> 4;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        umma_ss_lohi(TC_DW, dlo_base + a_lo + 2 * ks, dlo_base + b_hi + 2 * ks, DESC_HI_SW128, idesc, (Q > 0 || ks > 0) ? 1u : 0u);
+        umma_ss_lohi(TC_DW, dlo_base + a_hi + 2 * ks, dlo_base + b_lo + 2 * ks, DESC_HI_SW128, idesc, 1u);
+        umma_ss_lohi(TC_DW, dlo_base + a_hi + 2 * ks, dlo_base + b_hi + 2 * ks, DESC_HI_SW128, idesc, 1u);
+    }
+}
+
+// One value of this lane's row into a [feature][32 rows] K-major SWIZZLE_128B plane: feature row f is 128 bytes, the lane's
+// 4-byte slot sits in 16-byte chunk (lane >> 2) ^ (f & 7).  lane_off = ((lane >> 2) << 4) | ((lane & 3) << 2).
+__device__ __forceinline__ void stage_put(uint8_t* plane_hi, uint8_t* plane_lo, int f, uint32_t lane_off, uint32_t hi, uint32_t lo) {
+    const uint32_t off = (uint32_t)f * 128u + (lane_off ^ ((uint32_t)(f & 7) << 4));
+    *reinterpret_cast<uint32_t*>(plane_hi + off) = hi;
+    *reinterpret_cast<uint32_t*>(plane_lo + off) = lo;
+}
+
+// gz[L] of this thread (its NLOC = n(L)/2 columns) is ready: (1) A operand of layer L's data-gradient MMAs -> TMEM, signal the
+// chain issuer; (2) this quadrant's slice of layer L's weight gradient -> shared memory: gz[L] and act[L] (its own columns of
+// the saved layer output; the track for layer 0; knobs appended for layer 4), signal the weight-gradient issuer / flush warps.
+template <class TB, int L>
+__device__ __forceinline__ void bwd_handoff(uint8_t* smem_raw, uint32_t t_lane, uint32_t lane_off, int half, int q, int it, int lane,
+                                            const float (&gz)[TB::n(L) / 2], uint64_t* a_ready, uint64_t* full, uint64_t* freeb,
+                                            const float (&vkeep)[16], const float* knobs, long knob_off, int nk) {
+    using S = Stg<TB, L>;
+    constexpr int NLOC = TB::n(L) / 2;
+    const int c0 = half * NLOC;
+    uint32_t ghi[NLOC], glo[NLOC];
+#pragma unroll
+    for (int c = 0; c < NLOC; ++c) split_tf32_alu(gz[c], ghi[c], glo[c]);
+    tmem_st<NLOC>(t_lane + TC_AH + c0, ghi);
+    tmem_st<NLOC>(t_lane + TC_AL + c0, glo);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_ready);
+    // ---- weight-gradient slice
+    // the shared buffer: quadrant q < 2 fills first (after its partner's previous slice was consumed), q >= 2 after q - 2's
+    const int i = it * NL + (NL - 1 - L);                    // this quadrant's fill count = phase index of its barriers
+    if (q >= 2) mbar_wait_spin(&freeb[q ^ 2], (uint32_t)(i & 1));
+    else if (i > 0) mbar_wait_spin(&freeb[q ^ 2], (uint32_t)((i - 1) & 1));
+    uint8_t* buf = smem_raw + BwdSmem<TB>::STAGE + (uint32_t)(q & 1) * 2u * SUB_BYTES;
+#pragma unroll
+    for (int c = 0; c < NLOC; ++c) stage_put(buf + S::GZ_HI, buf + S::GZ_LO, c0 + c, lane_off, ghi[c], glo[c]);
+    if constexpr (L == 0) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            uint32_t hi, lo;
+            split_tf32_alu(vkeep[e], hi, lo);
+            stage_put(buf + S::ACT_HI, buf + S::ACT_LO, 16 * half + e, lane_off, hi, lo);
+        }
+    } else {
+        constexpr int AW = TB::n(L - 1) / 2;                 // this thread's share of act[L] (width n(L-1))
+        const int ac0 = half * AW;
+        uint32_t hv[AW];
+        tmem_ld<AW>(t_lane + tc_act(L) + ac0, hv);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < AW; ++c) {
+            uint32_t hi, lo;
+            split_tf32_alu(__uint_as_float(hv[c]), hi, lo);
+            stage_put(buf + S::ACT_HI, buf + S::ACT_LO, ac0 + c, lane_off, hi, lo);
+        }
+        if (L == 4 && half == 1 && TB::KP5 > 16) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float kv = e < nk ? __ldg(knobs + knob_off + e) : 0.f;
+                uint32_t hi, lo;
+                split_tf32_alu(kv, hi, lo);
+                stage_put(buf + S::ACT_HI, buf + S::ACT_LO, 16 + e, lane_off, hi, lo);
+            }
+        }
+    }
+    fence_async_smem();                                      // generic-proxy writes -> the MMAs' async-proxy reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full[q]);
+}
+
+struct BwdArgs {
+    const float* image;      // [2 autoencoders] backward images
+    const float* spec;
+    const float* knobs;
+    const float* mag_hat;    // forward outputs
+    const float* phs_hat;
+    const float* g_ri;       // dLoss/d(re | im) of the synthesis input, [(b, j)][2 Fp]
+    const float* g_mag_hat;  // nullable: direct gradient on mag_hat (the L1 term of the loss)
+    float* g_track;          // [2][B][T][F] track gradients (magnitude | phase)
+    float* partials;         // [(slot, autoencoder)][flat_total] per-CTA weight / bias gradient sums
+    float* dbg;              // nullable: [18][128][64] layer outputs then gz of tile 0 (tests)
+    int B;
+};
+
+template <class TB>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
+    static_assert(TB::KP1 == 32, "backward kernel: T <= 32");
+    using SM = BwdSmem<TB>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    float* bias = reinterpret_cast<float*>(smem_raw + SM::BIAS);
+    float* vtail = reinterpret_cast<float*>(smem_raw + SM::VTAIL);          // [XCH_J][TILE]: tail of the track, then skip / residual gradient
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + SM::BARS);
+    uint64_t* a_ready = bars;            // chain warps -> chain issuer (count 8)
+    uint64_t* d_ready = bars + 1;        // chain issuer -> chain warps
+    uint64_t* w_ready = bars + 2;        // weight image landed
+    uint64_t* full = bars + 3;           // [4] staging sub-buffer written (count 2: the two column halves of a quadrant)
+    uint64_t* freeb = bars + 7;          // [4] staging sub-buffer consumed (count 2: weight-gradient MMAs + bias-gradient reader)
+    uint64_t* dw_ready = bars + 11;      // weight-gradient issuer -> flush warps: the layer's accumulator is complete
+    uint64_t* dw_free = bars + 12;       // flush warps -> weight-gradient issuer (count 4)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int ae = blockIdx.x & 1, slot = blockIdx.x >> 1, nslot = gridDim.x >> 1;
+    constexpr int IMGF = bwd_image_floats<TB>();
+    if (threadIdx.x == 0) {
+        mbar_init(a_ready, BWD_CHAIN_WARPS); mbar_init(d_ready, 1); mbar_init(w_ready, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 2); mbar_init(&freeb[i], 2); }
+        mbar_init(dw_ready, 1); mbar_init(dw_free, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint8_t* img = reinterpret_cast<const uint8_t*>(a.image + (long)ae * IMGF);
+        constexpr uint32_t WB = 8u * TB::wfloats, TBY = 8u * TB::tfloats + 4u * ((TB::bfloats + 255) / 256 * 256);
+        mbar_expect_tx(w_ready, WB + TBY);
+        constexpr uint32_t CHUNK = 32768;
+        for (uint32_t o = 0; o < WB; o += CHUNK) bulk_g2s(smem_raw + SM::W_HI + o, img + o, (WB - o) < CHUNK ? (WB - o) : CHUNK, w_ready);
+        for (uint32_t o = 0; o < TBY; o += CHUNK) bulk_g2s(smem_raw + SM::WT_HI + o, img + WB + o, (TBY - o) < CHUNK ? (TBY - o) : CHUNK, w_ready);
+    }
+    if (warp == BWD_ISSUER) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (*tmem_slot != 0 || (smem_u32(smem_raw) & 1023u) != 0) __trap();
+
+    const int BF = a.B * d.F;
+    const int ntiles = (BF + TILE - 1) / TILE;
+    const uint32_t dlo_base = desc_lo_sw128(smem_u32(smem_raw));
+
+    if (warp == BWD_ISSUER) {
+        // ======================= chain MMAs: forward layers 0..8, then data gradients of layers 8..0 =======================
+        mbar_wait_spin(w_ready, 0);
+        uint32_t ph = 0;
+        for (int tile = slot; tile < ntiles; tile += nslot) {
+#define ST_CH(CALL) mbar_wait_spin(a_ready, ph); ph ^= 1; tc_fence_after(); CALL; umma_commit_elect(d_ready);
+            ST_CH((issue_refwd_layer<TB, 0>(dlo_base))) ST_CH((issue_refwd_layer<TB, 1>(dlo_base))) ST_CH((issue_refwd_layer<TB, 2>(dlo_base)))
+            ST_CH((issue_refwd_layer<TB, 3>(dlo_base))) ST_CH((issue_refwd_layer<TB, 4>(dlo_base))) ST_CH((issue_refwd_layer<TB, 5>(dlo_base)))
+            ST_CH((issue_refwd_layer<TB, 6>(dlo_base))) ST_CH((issue_refwd_layer<TB, 7>(dlo_base))) ST_CH((issue_refwd_layer<TB, 8>(dlo_base)))
+            ST_CH((issue_dgrad_layer<TB, 8>(dlo_base))) ST_CH((issue_dgrad_layer<TB, 7>(dlo_base))) ST_CH((issue_dgrad_layer<TB, 6>(dlo_base)))
+            ST_CH((issue_dgrad_layer<TB, 5>(dlo_base))) ST_CH((issue_dgrad_layer<TB, 4>(dlo_base))) ST_CH((issue_dgrad_layer<TB, 3>(dlo_base)))
+            ST_CH((issue_dgrad_layer<TB, 2>(dlo_base))) ST_CH((issue_dgrad_layer<TB, 1>(dlo_base))) ST_CH((issue_dgrad_layer<TB, 0>(dlo_base)))
+#undef ST_CH
+        }
+    } else if (warp == BWD_WISSUER) {
+        // ======================= weight-gradient MMAs: per layer 8..0, the four 32-row slices into one accumulator ===========
+        int nl = 0;                                          // layers issued so far = phase index of full[] / free[] / dw_*
+        for (int tile = slot; tile < ntiles; tile += nslot) {
+#define ST_WQ(L, Q)                                                                                         \
+            mbar_wait_spin(&full[Q], (uint32_t)(nl & 1));                                                   \
+            tc_fence_after();                                                                               \
+            issue_wgrad_slice<TB, L, Q>(dlo_base);                                                          \
+            umma_commit_elect(&freeb[Q]);
+#define ST_WL(L)                                                                                            \
+            mbar_wait_spin(dw_free, (uint32_t)(nl & 1) ^ 1u);                                               \
+            tc_fence_after();                                                                               \
+            ST_WQ(L, 0) ST_WQ(L, 1) ST_WQ(L, 2) ST_WQ(L, 3)                                                 \
+            umma_commit_elect(dw_ready);                                                                    \
+            ++nl;
+            ST_WL(8) ST_WL(7) ST_WL(6) ST_WL(5) ST_WL(4) ST_WL(3) ST_WL(2) ST_WL(1) ST_WL(0)
+#undef ST_WL
+#undef ST_WQ
+        }
+    } else if (warp >= BWD_FLUSH_WARP0) {
+        // ======================= flush warps: accumulate D_w into registers, bias gradients from the staged gz ================
+        const int q = warp & 3;
+        const int glane = 32 * q + lane;                     // TMEM lane = feature row of the M operand (+ its lane offset)
+        const uint32_t t_dw = ((uint32_t)(32 * q) << 16) + TC_DW;
+        float acc[80];
+        float dbacc[11];
+#pragma unroll
+        for (int i = 0; i < 80; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 11; ++i) dbacc[i] = 0.f;
+        int nl = 0;
+        for (int tile = slot; tile < ntiles; tile += nslot) {
+#define ST_FL(L, DBSLOT)                                                                                              \
+            {                                                                                                          \
+                using S = Stg<TB, L>;                                                                                  \
+                mbar_wait_spin(&full[q], (uint32_t)(nl & 1));                                                          \
+                const uint8_t* gb = smem_raw + SM::STAGE + (uint32_t)(q & 1) * 2u * SUB_BYTES;                         \
+                _Pragma("unroll")                                                                                      \
+                for (int p = 0; p < (TB::n(L) + 31) / 32; ++p) {                                                       \
+                    const int f = 32 * p + lane;                                                                       \
+                    if (f < TB::n(L)) {                                                                                \
+                        float sum = 0.f;                                                                               \
+                        _Pragma("unroll")                                                                              \
+                        for (int c = 0; c < 8; ++c) {                                                                  \
+                            const uint32_t o = (uint32_t)f * 128u + ((uint32_t)(c ^ (f & 7)) << 4);                    \
+                            const float4 h4 = *reinterpret_cast<const float4*>(gb + S::GZ_HI + o);                     \
+                            const float4 l4 = *reinterpret_cast<const float4*>(gb + S::GZ_LO + o);                     \
+                            sum += ((h4.x + l4.x) + (h4.y + l4.y)) + ((h4.z + l4.z) + (h4.w + l4.w));                  \
+                        }                                                                                              \
+                        dbacc[DBSLOT + p] += sum;                                                                      \
+                    }                                                                                                  \
+                }                                                                                                      \
+                __syncwarp();                                                                                          \
+                if (lane == 0) mbar_arrive(&freeb[q]);                                                                 \
+                mbar_wait_spin(dw_ready, (uint32_t)(nl & 1));                                                          \
+                tc_fence_after();                                                                                      \
+                constexpr int MO = TB::wg_moff(L), MF = S::MF, NF = S::NF, RG = TB::wg_reg(L);                         \
+                if (32 * q < MO + MF && 32 * q + 32 > MO) {                                                            \
+                    uint32_t v[NF];                                                                                    \
+                    tmem_ld<NF>(t_dw, v);                                                                              \
+                    tmem_wait_ld();                                                                                    \
+                    if (glane >= MO && glane < MO + MF) {                                                              \
+                        _Pragma("unroll")                                                                              \
+                        for (int i = 0; i < NF; ++i) acc[RG + i] += __uint_as_float(v[i]);                             \
+                    }                                                                                                  \
+                }                                                                                                      \
+                tc_fence_before();                                                                                     \
+                __syncwarp();                                                                                          \
+                if (lane == 0) mbar_arrive(dw_free);                                                                   \
+                ++nl;                                                                                                  \
+            }
+            ST_FL(8, 10) ST_FL(7, 8) ST_FL(6, 7) ST_FL(5, 6) ST_FL(4, 5) ST_FL(3, 4) ST_FL(2, 3) ST_FL(1, 2) ST_FL(0, 0)
+#undef ST_FL
+        }
+        // ---- per-CTA partial gradients -> global memory (layout: [W_0, b_0, W_1, b_1, ...] like ae_grad_reduce_kernel reads it)
+        float* part = a.partials + ((long)slot * 2 + ae) * g.flat_total;
+#define ST_WR(L)                                                                                                       \
+        {                                                                                                              \
+            constexpr int MO = TB::wg_moff(L), MF = TB::wg_mf(L), NF = TB::wg_nf(L), RG = TB::wg_reg(L);               \
+            const int IN = g.in[L], OUT = g.out[L];                                                                    \
+            float* W = part + g.flat_off[L];                                                                           \
+            if (glane >= MO && glane < MO + MF) {                                                                      \
+                const int m = glane - MO;                                                                              \
+                _Pragma("unroll")                                                                                      \
+                for (int i = 0; i < NF; ++i) {                                                                         \
+                    const int o = TB::wg_m_is_gz(L) ? m : i, k = TB::wg_m_is_gz(L) ? i : m;                            \
+                    if (o < OUT && k < IN) W[o * IN + k] = acc[RG + i];                                                \
+                }                                                                                                      \
+            }                                                                                                          \
+        }
+        ST_WR(0) ST_WR(1) ST_WR(2) ST_WR(3) ST_WR(4) ST_WR(5) ST_WR(6) ST_WR(7) ST_WR(8)
+#undef ST_WR
+        // bias gradients: the four flush warps hold the sums of their own quadrant's rows -> add through shared memory
+        float* dbs = reinterpret_cast<float*>(smem_raw + SM::STAGE);          // staging is idle now: [4][11][32]
+        asm volatile("bar.sync 2, 128;" ::: "memory");                        // every flush warp is past its last slice
+#pragma unroll
+        for (int i = 0; i < 11; ++i) dbs[(q * 11 + i) * 32 + lane] = dbacc[i];
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (q == 0) {
+            constexpr int slot_of[NL] = {0, 2, 3, 4, 5, 6, 7, 8, 10};
+#pragma unroll
+            for (int L = 0; L < NL; ++L) {
+                const int OUT = g.out[L], IN = g.in[L];
+                for (int p = 0; p < (TB::n(L) + 31) / 32; ++p) {
+                    const int f = 32 * p + lane, i = slot_of[L] + p;
+                    if (f < OUT)
+                        part[g.flat_off[L] + OUT * IN + f] = (dbs[(0 * 11 + i) * 32 + lane] + dbs[(1 * 11 + i) * 32 + lane]) +
+                                                             (dbs[(2 * 11 + i) * 32 + lane] + dbs[(3 * 11 + i) * 32 + lane]);
+                }
+            }
+        }
+    } else {
+        // ======================= chain warps: thread = (row, column half) =======================
+        const int half = warp >> 2, q = warp & 3;
+        const int row = 32 * q + lane;
+        const uint32_t t_lane = (uint32_t)(32 * q) << 16;
+        const uint32_t lane_off = ((uint32_t)(lane >> 2) << 4) | ((uint32_t)(lane & 3) << 2);
+        const int tail0 = d.T - d.OT, rowstride = 2 * d.Fp;
+        const long ntrk = (long)a.B * d.T * d.F;
+        uint32_t ph = 0;
+        int it = 0;
+        mbar_wait_spin(w_ready, 0);                          // biases
+        for (int tile = slot; tile < ntiles; tile += nslot, ++it) {
+            const int R = tile * TILE + row;
+            const bool ok = R < BF;
+            const int b = ok ? R / d.F : 0, f = ok ? R - b * d.F : 0;
+            float* mydbg = (a.dbg && tile == 0 && ae == 0) ? a.dbg + (long)row * 64 : nullptr;
+            float vkeep[16];
+            // ---- input track (this thread: frames [16 half, +16)) -> A operand, kept in registers for layer 0's weight gradient
+            {
+                const int c0 = 16 * half;
+                const float* sp = a.spec + (long)b * d.Tp * rowstride + f;
+                float re[16], im[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const bool in = ok && c0 + e < d.T;
+                    re[e] = in ? __ldg(sp + (long)(c0 + e) * rowstride) : 0.f;
+                    im[e] = in ? __ldg(sp + (long)(c0 + e) * rowstride + d.Fp) : 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int t = c0 + e;
+                    const bool in = ok && t < d.T;
+                    vkeep[e] = ae == 0 ? sqrtf(re[e] * re[e] + im[e] * im[e]) : (in ? atan2_fast(im[e], re[e] + 1e-7f) : 0.f);
+                    if (t >= tail0 && t < d.T) vtail[(t - tail0) * TILE + row] = vkeep[e];
+                }
+                store_pair<16>(t_lane + TC_AH + c0, t_lane + TC_AL + c0, vkeep);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // vtail complete (both halves)
+
+            // ---- forward layers 0..7: h = ELU(D + b) -> raw copy (kept for the backward) + (hi, lo) A operand
+#pragma unroll 1
+            for (int l = 0; l < NL - 1; ++l) {
+                mbar_wait_spin(d_ready, ph);
+                ph ^= 1;
+                tc_fence_after();
+                const int nloc = c_n[l] / 2, c0 = half * nloc;
+                const float* bl = bias + c_boff[l] + c0;
+                const uint32_t t_save = t_lane + tc_act(l + 1) + c0;
+                float* ld = mydbg ? mydbg + (long)l * TILE * 64 + c0 : nullptr;
+                if (nloc == 32) epi_hidden<32, true>(t_lane + TC_D + c0, t_lane + TC_AH + c0, t_lane + TC_AL + c0, bl, ld, t_save);
+                else if (nloc == 16) epi_hidden<16, true>(t_lane + TC_D + c0, t_lane + TC_AH + c0, t_lane + TC_AL + c0, bl, ld, t_save);
+                else epi_hidden<8, true>(t_lane + TC_D + c0, t_lane + TC_AH + c0, t_lane + TC_AL + c0, bl, ld, t_save);
+                if (l == 3 && half == 1 && TB::KP5 > 16) {
+                    float kv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) kv[e] = (ok && e < d.K) ? __ldg(a.knobs + (long)b * d.K + e) : 0.f;
+                    store_pair<8>(t_lane + TC_AH + 16, t_lane + TC_AL + 16, kv);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);
+            }
+
+            // ---- fnn_dec + output side backwards: gz[8], and the skip / residual gradient (left in vtail for the end of the tile)
+            {
+                const int j0 = 8 * half;
+                float gre[8], gim[8], phv[8], x3[8];
+                const float* gri = a.g_ri + (long)b * d.OTp * rowstride + f;
+                const long oo0 = (long)b * d.OT * d.F + f;
+                const float* x3p = ae == 1 ? a.mag_hat : a.g_mag_hat;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool in = ok && j0 + j < d.OT;
+                    gre[j] = in ? __ldg(gri + (long)(j0 + j) * rowstride) : 0.f;
+                    gim[j] = in ? __ldg(gri + (long)(j0 + j) * rowstride + d.Fp) : 0.f;
+                    phv[j] = in ? __ldg(a.phs_hat + oo0 + (long)(j0 + j) * d.F) : 0.f;
+                    x3[j] = (in && x3p) ? __ldg(x3p + oo0 + (long)(j0 + j) * d.F) : 0.f;
+                }
+                mbar_wait_spin(d_ready, ph);
+                ph ^= 1;
+                tc_fence_after();
+                uint32_t rr[8];
+                tmem_ld<8>(t_lane + TC_D + j0, rr);
+                tmem_wait_ld();
+                const float* bl = bias + c_boff[NL - 1] + j0;
+                float gz[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float e9 = elu_f(__uint_as_float(rr[j]) + bl[j]);
+                    if (mydbg) mydbg[(long)(NL - 1) * TILE * 64 + j0 + j] = e9;
+                    const float2 sc = sincos_ni(phv[j]);
+                    float tb;
+                    if (ae == 0) {                  // an = mag_hat (cos, sin);  mag_hat = ELU(dec) * track tail
+                        const float gm = gre[j] * sc.y + gim[j] * sc.x + x3[j];
+                        gz[j] = gm * vtail[(j0 + j) * TILE + row] * elu_grad(e9);
+                        tb = gm * e9;
+                    } else {                        // phs_hat = ELU(dec) + track tail
+                        const float gp = x3[j] * (gim[j] * sc.y - gre[j] * sc.x);
+                        gz[j] = gp * elu_grad(e9);
+                        tb = gp;
+                    }
+                    if (j0 + j >= d.OT) { gz[j] = 0.f; tb = 0.f; }
+                    vtail[(j0 + j) * TILE + row] = tb;
+                }
+                if (mydbg) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) mydbg[(long)(NL + 8) * TILE * 64 + j0 + j] = gz[j];
+                }
+                bwd_handoff<TB, 8>(smem_raw, t_lane, lane_off, half, q, it, lane, gz, a_ready, full, freeb, vkeep, nullptr, 0, 0);
+            }
+            // ---- data gradients, layers 8..1: gz[l-1] = gh[l] * ELU'(act[l]); the weight-gradient slice of layer l-1 follows
+#define ST_BW(L)                                                                                                     \
+            {                                                                                                        \
+                constexpr int NLOC = TB::dn(L) / 2;                                                                  \
+                const int c0 = half * NLOC;                                                                          \
+                mbar_wait_spin(d_ready, ph);                                                                         \
+                ph ^= 1;                                                                                             \
+                tc_fence_after();                                                                                    \
+                uint32_t gh[NLOC], hv[NLOC];                                                                         \
+                tmem_ld<NLOC>(t_lane + TC_D + c0, gh);                                                               \
+                tmem_ld<NLOC>(t_lane + tc_act(L) + c0, hv);                                                          \
+                tmem_wait_ld();                                                                                      \
+                float gz[NLOC];                                                                                      \
+                _Pragma("unroll")                                                                                    \
+                for (int c = 0; c < NLOC; ++c) gz[c] = __uint_as_float(gh[c]) * elu_grad(__uint_as_float(hv[c]));    \
+                if (mydbg) {                                                                                         \
+                    _Pragma("unroll")                                                                                \
+                    for (int c = 0; c < NLOC; ++c) mydbg[(long)(NL + (L) - 1) * TILE * 64 + c0 + c] = gz[c];          \
+                }                                                                                                    \
+                bwd_handoff<TB, (L) - 1>(smem_raw, t_lane, lane_off, half, q, it, lane, gz, a_ready, full, freeb, vkeep, a.knobs, (long)b * d.K, ok ? d.K : 0); \
+            }
+            ST_BW(8) ST_BW(7) ST_BW(6) ST_BW(5) ST_BW(4) ST_BW(3) ST_BW(2) ST_BW(1)
+#undef ST_BW
+            // ---- layer 0: gh[0] + skip / residual gradient = dLoss/d(track), stored lane <-> bin (coalesced)
+            {
+                const int c0 = 16 * half;
+                mbar_wait_spin(d_ready, ph);
+                ph ^= 1;
+                tc_fence_after();
+                uint32_t gh[16];
+                tmem_ld<16>(t_lane + TC_D + c0, gh);
+                tmem_wait_ld();
+                tc_fence_before();
+                float* gt = a.g_track + (long)ae * ntrk + ((long)b * d.T) * d.F + f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int t = c0 + e;
+                    if (ok && t < d.T) gt[(long)t * d.F] = __uint_as_float(gh[e]) + (t >= tail0 ? vtail[(t - tail0) * TILE + row] : 0.f);
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // vtail is free for the next tile
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == BWD_ISSUER) {
+        tc_fence_after();
+        tmem_dealloc(0u, 512);
+    }
+}
+
 template <class TB>
 constexpr size_t fwd_smem_bytes() {
-    return sizeof(float) * (2 * (size_t)image_floats<TB>() + 2 * XCH_J * TILE) + 5 * sizeof(uint64_t) + 16;
+    return sizeof(float) * (2 * (size_t)image_floats<TB>() + 2 * XCH_J * TILE + (TB::KP1 == 32 ? 2 * TB::KP1 * TILE : 0)) + 5 * sizeof(uint64_t) + 16;
 }
 
 template <class TB>
@@ -445,13 +1068,68 @@ bool launch_fwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AePa
         if (cudaFuncSetAttribute(ae_fwd_tm_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
         configured = true;
     }
-    if (pack) ae_pack_kernel<TB><<<dim3(NL, 2), 256, 0, s_pack>>>(g, pm, pp, wpack);
+    if (pack) ae_pack_kernel<TB, false><<<dim3(NL, 2), 256, 0, s_pack>>>(g, pm, pp, wpack);
     if (B > 0) {
         const long ntiles = ((long)B * d.F + TILE - 1) / TILE;
         const int grid = (int)std::min<long>(ntiles, sm_count);
         ae_fwd_tm_kernel<TB><<<grid, FWD_THREADS, smem, s>>>(d, wpack, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, dbg, timing);
     }
     return true;
+}
+
+// dL/d(re, im) from the two track gradients (magnitude and phase autoencoder), stored as the (hi, lo) tf32 pair the analysis
+// weight-gradient GEMM consumes.  mag = sqrt(re^2 + im^2) with subgradient 0 at 0 (torch.norm backward, nn_proc.py:309);
+// phs = atan2(im, re + 1e-7) (nn_proc.py:310).  g_mag: optional external gradient of the mag output.
+__global__ void ae_track_to_spec_kernel(StDims d, int B, const float* __restrict__ spec, const float* __restrict__ gt_m,
+                                        const float* __restrict__ gt_p, const float* __restrict__ g_mag, float* __restrict__ g_spec,
+                                        float* __restrict__ g_spec_lo) {
+    const long n = (long)B * d.T * d.F;
+    const int rowstride = 2 * d.Fp;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+        const long bt = idx / d.F;
+        const int f = (int)(idx - bt * d.F);
+        const int b = (int)(bt / d.T), tt = (int)(bt - (long)b * d.T);
+        const long o = ((long)b * d.Tp + tt) * rowstride + f;
+        const float re = __ldg(spec + o), im = __ldg(spec + o + d.Fp);
+        float gm = __ldg(gt_m + idx);
+        if (g_mag) gm += __ldg(g_mag + idx);
+        const float gp = __ldg(gt_p + idx);
+        const float m = sqrtf(re * re + im * im);
+        const float scm = m > 0.f ? gm / m : 0.f;
+        const float u = re + 1e-7f;
+        const float den = u * u + im * im;
+        const float scp = den > 0.f ? gp / den : 0.f;
+        st_split_tf32(scm * re - scp * im, g_spec[o], g_spec_lo[o]);
+        st_split_tf32(scm * im + scp * u, g_spec[o + d.Fp], g_spec_lo[o + d.Fp]);
+    }
+}
+
+template <class TB>
+int launch_bwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, const float* knobs, int B,
+               const float* mag_hat, const float* phs_hat, const float* g_ri, const float* g_mag_hat, const float* g_mag,
+               float* g_track, float* g_spec, float* g_spec_lo, float* partials, float* wpack, float* dbg, int sm_count, bool pack,
+               cudaStream_t s_pack, cudaStream_t s) {
+    constexpr size_t smem = BwdSmem<TB>::TOTAL;
+    static_assert(smem <= 227 * 1024, "backward tile does not fit shared memory");
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(ae_bwd_tm_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+        configured = true;
+    }
+    if (pack) ae_pack_kernel<TB, true><<<dim3(NL, 2), 256, 0, s_pack>>>(g, pm, pp, wpack);
+    if (B <= 0) return 0;
+    const long ntiles = ((long)B * d.F + TILE - 1) / TILE;
+    const int nslot = (int)std::min<long>(ntiles, sm_count / 2);
+    BwdArgs a;
+    a.image = wpack; a.spec = spec; a.knobs = knobs; a.mag_hat = mag_hat; a.phs_hat = phs_hat; a.g_ri = g_ri; a.g_mag_hat = g_mag_hat;
+    a.g_track = g_track; a.partials = partials; a.dbg = dbg; a.B = B;
+    ae_bwd_tm_kernel<TB><<<2 * nslot, BWD_THREADS, smem, s>>>(d, g, a);
+    if (g_spec) {
+        const long ntrk = (long)B * d.T * d.F;
+        ae_track_to_spec_kernel<<<(int)std::min<long>((ntrk + 255) / 256, 8L * sm_count), 256, 0, s>>>(d, B, spec, g_track, g_track + ntrk, g_mag,
+                                                                                                    g_spec, g_spec_lo);
+    }
+    return nslot;
 }
 
 }  // namespace
@@ -473,4 +1151,22 @@ bool st_launch_ae_forward_tm(const StDims& d, const AeGeom& g, const AeParams& p
     if (knob) return ST_FWD(Tab<64, 24>);
     return ST_FWD(Tab<64, 16>);
 #undef ST_FWD
+}
+
+long st_ae_tm_bwd_pack_floats() { return 2L * bwd_image_floats<Tab<32, 24>>(); }
+
+// Backward of both autoencoders with in-kernel recompute (no saved activations): track gradients -> g_track (2 * B * T * F
+// floats) and, when g_spec is non-null, dL/d(re, im) as the (hi, lo) operand of the analysis weight-gradient GEMM; per-CTA
+// partial weight / bias gradients -> partials ([(slot, autoencoder)][flat_total]).  Returns the number of slots written per
+// autoencoder (0: geometry not covered -- T <= 32, OT <= 16, K <= 8).  wpack: st_ae_tm_bwd_pack_floats() floats.
+int st_launch_ae_backward_tm(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
+                             const float* knobs, int B, const float* mag_hat, const float* phs_hat, const float* g_ri,
+                             const float* g_mag_hat, const float* g_mag, float* g_track, float* g_spec, float* g_spec_lo,
+                             float* partials, float* wpack, float* dbg, int sm_count, bool pack, cudaStream_t s_pack, cudaStream_t s) {
+    if (d.T > 32 || d.OT > 16 || d.K > 8) return 0;
+    if (d.K > 0)
+        return launch_bwd<Tab<32, 24>>(d, g, pm, pp, spec, knobs, B, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, g_track, g_spec, g_spec_lo,
+                                       partials, wpack, dbg, sm_count, pack, s_pack, s);
+    return launch_bwd<Tab<32, 16>>(d, g, pm, pp, spec, knobs, B, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, g_track, g_spec, g_spec_lo,
+                                   partials, wpack, dbg, sm_count, pack, s_pack, s);
 }

@@ -180,6 +180,13 @@ bool st_launch_ae_forward_tm(const StDims& d, const AeGeom& g, const AeParams& p
                              float* wpack, float* dbg, long long* timing /*nullable: 256 counters*/, int sm_count,
                              bool pack, cudaStream_t s_pack, cudaStream_t s);
 
+long st_ae_tm_bwd_pack_floats();
+// Backward with in-kernel recompute.  Returns the number of per-CTA partial-gradient vectors per autoencoder (0: not covered).
+int st_launch_ae_backward_tm(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
+                             const float* knobs, int B, const float* mag_hat, const float* phs_hat, const float* g_ri,
+                             const float* g_mag_hat, const float* g_mag, float* g_track, float* g_spec, float* g_spec_lo,
+                             float* partials, float* wpack, float* dbg, int sm_count, bool pack, cudaStream_t s_pack, cudaStream_t s);
+
 // st_data.cu
 void st_launch_compressor_4c(const float* x, const double* knobs_wc, int B, int n, double sr, float* scratch, float* y, cudaStream_t s);
 void st_launch_crop_windows(const float* cx, const float* cy, const long* off, const float* sign, int B, int C, int L, float* ox,

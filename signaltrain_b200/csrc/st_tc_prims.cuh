@@ -142,11 +142,11 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
         ::"r"(smem_u32(bar)) : "memory");
 }
-// Spin on an mbarrier phase without reading the clock (a trap after ~2^26 polls: a protocol bug is a launch failure, not a hang).
+// Spin on an mbarrier phase without reading the clock (a trap after ~2^22 polls: a protocol bug is a launch failure, not a hang).
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if (++spins > (1u << 22)) __trap();
     }
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

@@ -40,6 +40,7 @@ struct HostAe {
 };
 
 static double elu(double z) { return z > 0 ? z : std::expm1(z); }
+#define AE_DBG 0
 
 int main(int argc, char** argv) {
     const int B = argc > 1 ? atoi(argv[1]) : 3;
@@ -152,6 +153,159 @@ int main(int argc, char** argv) {
     const bool fwd_ok = e_mh < 2e-5 && e_ph < 2e-5 && e_ri < 2e-5;
     printf("forward %s\n", fwd_ok ? "OK" : "MISMATCH");
 
+    // ---------------- backward check ----------------
+    bool bwd_ok = true;
+    if (d.T <= 32) {
+        // CPU forward outputs as the kernel's inputs (isolates the backward), random upstream gradients
+        std::vector<float> c_mh((long)B * d.OT * d.F), c_ph((long)B * d.OT * d.F), gri(nri, 0.f), gmh((long)B * d.OT * d.F);
+        for (auto& v : gmh) v = 1e-3f * nd(rng);
+        for (int b = 0; b < B; ++b)
+            for (int j = 0; j < d.OT; ++j)
+                for (int f = 0; f < d.F; ++f) {
+                    const long orr = ((long)b * d.OTp + j) * 2 * d.Fp + f;
+                    gri[orr] = 1e-2f * nd(rng);
+                    gri[orr + d.Fp] = 1e-2f * nd(rng);
+                }
+        std::vector<double> rW[2][9], rb[2][9];
+        std::vector<double> rgt(2L * B * d.T * d.F, 0.0), rgz(18L * 128 * 64, 0.0);
+        for (int a = 0; a < 2; ++a)
+            for (int l = 0; l < 9; ++l) { rW[a][l].assign(g.in[l] * g.out[l], 0.0); rb[a][l].assign(g.out[l], 0.0); }
+        const int tail0 = d.T - d.OT;
+        // pass 1: forward of both autoencoders per row (mag_hat / phs_hat), pass 2: backward
+        std::vector<std::vector<double>> acts(10);
+        for (int pass = 0; pass < 2; ++pass)
+            for (int b = 0; b < B; ++b)
+                for (int f = 0; f < d.F; ++f) {
+                    const long R = (long)b * d.F + f;
+                    for (int a = 0; a < 2; ++a) {
+                        acts[0].assign(d.T, 0.0);
+                        for (int t = 0; t < d.T; ++t) {
+                            const long o = ((long)b * d.Tp + t) * 2 * d.Fp + f;
+                            const double re = spec[o], im = spec[o + d.Fp];
+                            acts[0][t] = a == 0 ? std::sqrt(re * re + im * im) : std::atan2(im, (double)(float)(spec[o] + 1e-7f));
+                        }
+                        for (int l = 0; l < 9; ++l) {
+                            std::vector<double> in(acts[l]);
+                            if (l == 4) for (int k = 0; k < d.K; ++k) in.push_back(knobs[(long)b * d.K + k]);
+                            if (l == 4) acts[4] = in;
+                            acts[l + 1].assign(g.out[l], 0.0);
+                            for (int o = 0; o < g.out[l]; ++o) {
+                                double s2 = ae[a].b[l][o];
+                                for (int i = 0; i < g.in[l]; ++i) s2 += (double)ae[a].W[l][o * g.in[l] + i] * in[i];
+                                acts[l + 1][o] = elu(s2);
+                            }
+                        }
+                        if (pass == 0) {
+                            for (int j = 0; j < d.OT; ++j) {
+                                const long oo = ((long)b * d.OT + j) * d.F + f;
+                                if (a == 0) c_mh[oo] = (float)(acts[9][j] * acts[0][tail0 + j]);
+                                else c_ph[oo] = (float)(acts[9][j] + acts[0][tail0 + j]);
+                            }
+                            continue;
+                        }
+                        std::vector<double> gz(d.OT), tb(d.OT);
+                        for (int j = 0; j < d.OT; ++j) {
+                            const long oo = ((long)b * d.OT + j) * d.F + f, orr = ((long)b * d.OTp + j) * 2 * d.Fp + f;
+                            const double cs = std::cos((double)c_ph[oo]), sn = std::sin((double)c_ph[oo]);
+                            const double e9 = acts[9][j], eg = e9 > 0 ? 1.0 : e9 + 1.0;
+                            if (a == 0) {
+                                const double gm = gri[orr] * cs + gri[orr + d.Fp] * sn + gmh[oo];
+                                gz[j] = gm * acts[0][tail0 + j] * eg; tb[j] = gm * e9;
+                            } else {
+                                const double gp = (double)c_mh[oo] * (gri[orr + d.Fp] * cs - gri[orr] * sn);
+                                gz[j] = gp * eg; tb[j] = gp;
+                            }
+                        }
+                        for (int l = 8; l >= 0; --l) {
+                            if (a == AE_DBG && R < 128) for (int o = 0; o < g.out[l]; ++o) rgz[((long)(9 + l) * 128 + R) * 64 + o] = gz[o];
+                            const std::vector<double>& in = acts[l];
+                            for (int o = 0; o < g.out[l]; ++o) {
+                                rb[a][l][o] += gz[o];
+                                for (int i = 0; i < g.in[l]; ++i) rW[a][l][o * g.in[l] + i] += gz[o] * in[i];
+                            }
+                            const int nin = l == 4 ? 16 : g.in[l];
+                            std::vector<double> gh(nin, 0.0);
+                            for (int i = 0; i < nin; ++i)
+                                for (int o = 0; o < g.out[l]; ++o) gh[i] += gz[o] * ae[a].W[l][o * g.in[l] + i];
+                            if (l > 0) {
+                                gz.assign(nin, 0.0);
+                                for (int i = 0; i < nin; ++i) gz[i] = gh[i] * (acts[l][i] > 0 ? 1.0 : acts[l][i] + 1.0);
+                            } else {
+                                for (int t = 0; t < d.T; ++t)
+                                    rgt[(long)a * B * d.T * d.F + ((long)b * d.T + t) * d.F + f] = gh[t] + (t >= tail0 ? tb[t - tail0] : 0.0);
+                            }
+                        }
+                    }
+                }
+        float *dcmh, *dcph, *dgri, *dgmh, *dgt, *dpart, *dwb, *ddbg2;
+        const long ntrk = (long)B * d.T * d.F;
+        CK(cudaMalloc(&dcmh, c_mh.size() * 4)); CK(cudaMalloc(&dcph, c_ph.size() * 4)); CK(cudaMalloc(&dgri, std::max<long>(nri, 1) * 4));
+        CK(cudaMalloc(&dgmh, (long)Bmax * d.OT * d.F * 4)); CK(cudaMalloc(&dgt, 2L * Bmax * d.T * d.F * 4));
+        CK(cudaMalloc(&dpart, (long)sm * g.flat_total * 4)); CK(cudaMalloc(&dwb, st_ae_tm_bwd_pack_floats() * 4)); CK(cudaMalloc(&ddbg2, 18L * 128 * 64 * 4));
+        CK(cudaMemcpy(dcmh, c_mh.data(), c_mh.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dcph, c_ph.data(), c_ph.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dgri, gri.data(), nri * 4, cudaMemcpyHostToDevice)); CK(cudaMemset(dgmh, 0, (long)Bmax * d.OT * d.F * 4));
+        CK(cudaMemcpy(dgmh, gmh.data(), gmh.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemset(dpart, 0, (long)sm * g.flat_total * 4)); CK(cudaMemset(ddbg2, 0, 18L * 128 * 64 * 4)); CK(cudaMemset(dgt, 0, 2L * Bmax * d.T * d.F * 4));
+        const int nslot = st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, B, dcmh, dcph, dgri, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb,
+                                                   ddbg2, sm, true, 0, 0);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("backward: CUDA error %s\n", cudaGetErrorString(e)); return 2; }
+        printf("backward: %d partial slots per autoencoder\n", nslot);
+        std::vector<float> gt(2 * ntrk), part((long)2 * nslot * g.flat_total), dbg2(18L * 128 * 64);
+        CK(cudaMemcpy(gt.data(), dgt, gt.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(part.data(), dpart, part.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(dbg2.data(), ddbg2, dbg2.size() * 4, cudaMemcpyDeviceToHost));
+        for (int a = 0; a < 2; ++a) {
+            double eg = 0, mg = 0;
+            for (long i = 0; i < ntrk; ++i) { eg = std::max(eg, std::fabs(rgt[a * ntrk + i] - gt[a * ntrk + i])); mg = std::max(mg, std::fabs(rgt[a * ntrk + i])); }
+            printf("  ae%d track gradient: max err %.3g of max %.3g (%.2g rel)\n", a, eg, mg, eg / mg);
+            if (eg > 3e-4 * mg) bwd_ok = false;
+            for (int l = 0; l < 9; ++l) {
+                double ew = 0, mw = 0, eb = 0, mb = 0;
+                for (int i = 0; i < g.in[l] * g.out[l]; ++i) {
+                    double sum = 0;
+                    for (int sidx = 0; sidx < nslot; ++sidx) sum += part[((long)sidx * 2 + a) * g.flat_total + g.flat_off[l] + i];
+                    ew = std::max(ew, std::fabs(sum - rW[a][l][i])); mw = std::max(mw, std::fabs(rW[a][l][i]));
+                }
+                for (int i = 0; i < g.out[l]; ++i) {
+                    double sum = 0;
+                    for (int sidx = 0; sidx < nslot; ++sidx) sum += part[((long)sidx * 2 + a) * g.flat_total + g.flat_off[l] + g.in[l] * g.out[l] + i];
+                    eb = std::max(eb, std::fabs(sum - rb[a][l][i])); mb = std::max(mb, std::fabs(rb[a][l][i]));
+                }
+                printf("    layer %d: dW err %.3g / %.3g (%.2g)   db err %.3g / %.3g (%.2g)\n", l, ew, mw, ew / mw, eb, mb, eb / mb);
+                if (ew > 3e-4 * mw || eb > 3e-4 * mb) bwd_ok = false;
+            }
+        }
+        {
+            printf("  tile-0 chain of ae%d (dbg): fwd layer errs:", AE_DBG);
+            // the dbg buffer holds the chain of whichever autoencoder's CTA 0/1 processed tile 0: both write the same slots, the
+            // kernel lets autoencoder AE_DBG win by launching order being unspecified -> compare against the closer one
+            for (int l = 0; l < 9; ++l) {
+                double em = 0;
+                for (int r = 0; r < 128 && r < B * d.F; ++r) for (int o = 0; o < g.out[l]; ++o) em = std::max(em, std::fabs(rgz[((long)(9 + l) * 128 + r) * 64 + o] - dbg2[((long)(9 + l) * 128 + r) * 64 + o]));
+                printf(" gz%d %.2g", l, em);
+            }
+            printf("\n");
+        }
+        printf("backward %s\n", bwd_ok ? "OK" : "MISMATCH");
+        // timing
+        cudaEvent_t b0, b1;
+        CK(cudaEventCreate(&b0)); CK(cudaEventCreate(&b1));
+        float *dcmh2, *dcph2;
+        CK(cudaMalloc(&dcmh2, nout * 4)); CK(cudaMalloc(&dcph2, nout * 4));
+        CK(cudaMemset(dcmh2, 0, nout * 4)); CK(cudaMemset(dcph2, 0, nout * 4));
+        float* dgri2; CK(cudaMalloc(&dgri2, nri * 4)); CK(cudaMemset(dgri2, 0, nri * 4));
+        for (int i = 0; i < 3; ++i) st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, sm, false, 0, 0);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(b0));
+        for (int i = 0; i < 20; ++i) st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, sm, false, 0, 0);
+        CK(cudaEventRecord(b1));
+        CK(cudaDeviceSynchronize());
+        float bms = 0;
+        CK(cudaEventElapsedTime(&bms, b0, b1));
+        printf("backward timing: B=%d  %.2f us per launch (both autoencoders, without the track->spec kernel)\n", TB, 1000.f * bms / 20);
+    }
+
     // ---------------- timing ----------------
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -196,5 +350,5 @@ int main(int argc, char** argv) {
                    ht[192 + 4 * l + 2] - ht[64 + 2 * l + 1], ht[64 + 2 * l + 2] - ht[64 + 2 * l + 1]);
         printf("\n");
     }
-    return fwd_ok ? 0 : 1;
+    return (fwd_ok && bwd_ok) ? 0 : 1;
 }
