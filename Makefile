@@ -3,7 +3,7 @@ NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(EXTRA) -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
 CSRC := signaltrain_b200/csrc
-OBJ := $(CSRC)/st_api.o $(CSRC)/st_frontend.o $(CSRC)/st_gemm_simt.o $(CSRC)/st_gemm_tc.o $(CSRC)/st_ae.o $(CSRC)/st_ae_mma.o $(CSRC)/st_ae_tc.o $(CSRC)/st_ae_tm.o $(CSRC)/st_ae_f2.o $(CSRC)/st_ae_f2_bwd.o $(CSRC)/st_loss_opt.o $(CSRC)/st_data.o
+OBJ := $(CSRC)/st_api.o $(CSRC)/st_frontend.o $(CSRC)/st_gemm_simt.o $(CSRC)/st_gemm_tc.o $(CSRC)/st_ae.o $(CSRC)/st_ae_mma.o $(CSRC)/st_ae_tm.o $(CSRC)/st_loss_opt.o $(CSRC)/st_data.o
 LIB := signaltrain_b200/lib/libsignaltrain_b200.so
 
 all: $(LIB)

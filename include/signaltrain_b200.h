@@ -195,7 +195,12 @@ const char* st_profile_stage_name(int i);
 int st_profile(st_handle* h, int enable);
 int st_profile_read(st_handle* h, float* ms, long* calls);
 
-/* Diagnostic: cycle counters of the regions of the tensor-core autoencoder backward (16 values; reading resets). */
+/* Number of calls this handle served with a SIMT fallback kernel instead of the tensor-core kernels since creation
+ * (a GEMM shape or autoencoder geometry they do not cover; forwards with return_acts count as well).  The benchmarked
+ * path must read 0: bench.py prints it. */
+long st_debug_fallbacks(const st_handle* h);
+
+/* Diagnostic: cycle counters of the regions of the tensor-core autoencoder backward (64 values; reading resets). */
 int st_debug_ae_timing(st_handle* h, int on, long long* out_host);
 
 /* Test/diagnostic access to workspace buffers by name ("spec", "ri", "frames_out", "g_ri", "g_spec",

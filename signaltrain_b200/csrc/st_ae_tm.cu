@@ -714,6 +714,7 @@ struct BwdArgs {
     float* g_track;          // [2][B][T][F] track gradients (magnitude | phase)
     float* partials;         // [(slot, autoencoder)][flat_total] per-CTA weight / bias gradient sums
     float* dbg;              // nullable: [18][128][64] layer outputs then gz of tile 0 (tests)
+    long long* timing;       // nullable (ST_AE_TM_TIMING builds): clock buckets of the chain warps
     int B;
 };
 
@@ -896,6 +897,14 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
         const long ntrk = (long)a.B * d.T * d.F;
         uint32_t ph = 0;
         int it = 0;
+#ifdef ST_AE_TM_TIMING
+        long long tclk = 0, treg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define BT0() if (a.timing) tclk = clock64();
+#define BT(i) if (a.timing) { const long long n_ = clock64(); treg[i] += n_ - tclk; tclk = n_; }
+#else
+#define BT0()
+#define BT(i)
+#endif
         mbar_wait_spin(w_ready, 0);                          // biases
         for (int tile = slot; tile < ntiles; tile += nslot, ++it) {
             const int R = tile * TILE + row;
@@ -903,6 +912,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
             const int b = ok ? R / d.F : 0, f = ok ? R - b * d.F : 0;
             float* mydbg = (a.dbg && tile == 0 && ae == 0) ? a.dbg + (long)row * 64 : nullptr;
             float vkeep[16];
+            BT0()
             // ---- input track (this thread: frames [16 half, +16)) -> A operand, kept in registers for layer 0's weight gradient
             {
                 const int c0 = 16 * half;
@@ -928,6 +938,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready);
             asm volatile("bar.sync 1, 256;" ::: "memory");   // vtail complete (both halves)
+            BT(0)
 
             // ---- forward layers 0..7: h = ELU(D + b) -> raw copy (kept for the backward) + (hi, lo) A operand
 #pragma unroll 1
@@ -935,6 +946,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 mbar_wait_spin(d_ready, ph);
                 ph ^= 1;
                 tc_fence_after();
+                BT(1)
                 const int nloc = c_n[l] / 2, c0 = half * nloc;
                 const float* bl = bias + c_boff[l] + c0;
                 const uint32_t t_save = t_lane + tc_act(l + 1) + c0;
@@ -952,6 +964,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_ready);
+                BT(2)
             }
 
             // ---- fnn_dec + output side backwards: gz[8], and the skip / residual gradient (left in vtail for the end of the tile)
@@ -972,6 +985,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 mbar_wait_spin(d_ready, ph);
                 ph ^= 1;
                 tc_fence_after();
+                BT(1)
                 uint32_t rr[8];
                 tmem_ld<8>(t_lane + TC_D + j0, rr);
                 tmem_wait_ld();
@@ -999,7 +1013,9 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) mydbg[(long)(NL + 8) * TILE * 64 + j0 + j] = gz[j];
                 }
+                BT(3)
                 bwd_handoff<TB, 8>(smem_raw, t_lane, lane_off, half, q, it, lane, gz, a_ready, full, freeb, vkeep, nullptr, 0, 0);
+                BT(5)
             }
             // ---- data gradients, layers 8..1: gz[l-1] = gh[l] * ELU'(act[l]); the weight-gradient slice of layer l-1 follows
 #define ST_BW(L)                                                                                                     \
@@ -1009,6 +1025,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 mbar_wait_spin(d_ready, ph);                                                                         \
                 ph ^= 1;                                                                                             \
                 tc_fence_after();                                                                                    \
+                BT(1)                                                                                                \
                 uint32_t gh[NLOC], hv[NLOC];                                                                         \
                 tmem_ld<NLOC>(t_lane + TC_D + c0, gh);                                                               \
                 tmem_ld<NLOC>(t_lane + tc_act(L) + c0, hv);                                                          \
@@ -1020,7 +1037,9 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                     _Pragma("unroll")                                                                                \
                     for (int c = 0; c < NLOC; ++c) mydbg[(long)(NL + (L) - 1) * TILE * 64 + c0 + c] = gz[c];          \
                 }                                                                                                    \
+                BT(4)                                                                                                \
                 bwd_handoff<TB, (L) - 1>(smem_raw, t_lane, lane_off, half, q, it, lane, gz, a_ready, full, freeb, vkeep, a.knobs, (long)b * d.K, ok ? d.K : 0); \
+                BT(5)                                                                                                \
             }
             ST_BW(8) ST_BW(7) ST_BW(6) ST_BW(5) ST_BW(4) ST_BW(3) ST_BW(2) ST_BW(1)
 #undef ST_BW
@@ -1030,6 +1049,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 mbar_wait_spin(d_ready, ph);
                 ph ^= 1;
                 tc_fence_after();
+                BT(1)
                 uint32_t gh[16];
                 tmem_ld<16>(t_lane + TC_D + c0, gh);
                 tmem_wait_ld();
@@ -1042,7 +1062,14 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");   // vtail is free for the next tile
+            BT(6)
         }
+#ifdef ST_AE_TM_TIMING
+        if (a.timing && lane == 0)
+            for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.timing) + 8 * warp + i, (unsigned long long)treg[i]);
+#endif
+#undef BT0
+#undef BT
     }
     tc_fence_before();
     __syncthreads();
@@ -1107,7 +1134,7 @@ __global__ void ae_track_to_spec_kernel(StDims d, int B, const float* __restrict
 template <class TB>
 int launch_bwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, const float* knobs, int B,
                const float* mag_hat, const float* phs_hat, const float* g_ri, const float* g_mag_hat, const float* g_mag,
-               float* g_track, float* g_spec, float* g_spec_lo, float* partials, float* wpack, float* dbg, int sm_count, bool pack,
+               float* g_track, float* g_spec, float* g_spec_lo, float* partials, float* wpack, float* dbg, long long* timing, int sm_count, bool pack,
                cudaStream_t s_pack, cudaStream_t s) {
     constexpr size_t smem = BwdSmem<TB>::TOTAL;
     static_assert(smem <= 227 * 1024, "backward tile does not fit shared memory");
@@ -1122,7 +1149,7 @@ int launch_bwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AePar
     const int nslot = (int)std::min<long>(ntiles, sm_count / 2);
     BwdArgs a;
     a.image = wpack; a.spec = spec; a.knobs = knobs; a.mag_hat = mag_hat; a.phs_hat = phs_hat; a.g_ri = g_ri; a.g_mag_hat = g_mag_hat;
-    a.g_track = g_track; a.partials = partials; a.dbg = dbg; a.B = B;
+    a.g_track = g_track; a.partials = partials; a.dbg = dbg; a.timing = timing; a.B = B;
     ae_bwd_tm_kernel<TB><<<2 * nslot, BWD_THREADS, smem, s>>>(d, g, a);
     if (g_spec) {
         const long ntrk = (long)B * d.T * d.F;
@@ -1162,11 +1189,11 @@ long st_ae_tm_bwd_pack_floats() { return 2L * bwd_image_floats<Tab<32, 24>>(); }
 int st_launch_ae_backward_tm(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
                              const float* knobs, int B, const float* mag_hat, const float* phs_hat, const float* g_ri,
                              const float* g_mag_hat, const float* g_mag, float* g_track, float* g_spec, float* g_spec_lo,
-                             float* partials, float* wpack, float* dbg, int sm_count, bool pack, cudaStream_t s_pack, cudaStream_t s) {
+                             float* partials, float* wpack, float* dbg, long long* timing, int sm_count, bool pack, cudaStream_t s_pack, cudaStream_t s) {
     if (d.T > 32 || d.OT > 16 || d.K > 8) return 0;
     if (d.K > 0)
         return launch_bwd<Tab<32, 24>>(d, g, pm, pp, spec, knobs, B, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, g_track, g_spec, g_spec_lo,
-                                       partials, wpack, dbg, sm_count, pack, s_pack, s);
+                                       partials, wpack, dbg, timing, sm_count, pack, s_pack, s);
     return launch_bwd<Tab<32, 16>>(d, g, pm, pp, spec, knobs, B, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, g_track, g_spec, g_spec_lo,
-                                   partials, wpack, dbg, sm_count, pack, s_pack, s);
+                                   partials, wpack, dbg, timing, sm_count, pack, s_pack, s);
 }

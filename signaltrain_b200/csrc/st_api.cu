@@ -31,8 +31,6 @@ struct st_handle {
                                   // 1 = reduced precision (single-pass TF32 products in the GEMMs and the autoencoder chains)
     bool fuse_tail = true;        // st_train_step: fused overlap-add + loss + padded gradient kernel and fused finalize + L1 norm
                                   // (ST_DISABLE_FUSED_TAIL=1 -> the separate kernels the piecewise entry points use)
-    bool tf32_ae_mma = false;     // reduced mode: ST_TF32_AE_MMA=1 moves the autoencoders to the single-pass mma.sync kernels; measured
-                                  // SLOWER than the exact FFMA2 chain (B=512: backward 0.99 vs 0.89 ms, forward 0.51 vs 0.50), so off
     bool use_tc = true;           // tcgen05/TMA GEMMs (falls back to the FFMA GEMM per call when a shape is not covered)
     float *part_a = nullptr, *part_s = nullptr, *ae_part = nullptr;
     float *yhat_ws = nullptr, *gy_ws = nullptr, *gmh_ws = nullptr;   // fused train step only
@@ -49,10 +47,11 @@ struct st_handle {
     bool training = true;         // st_set_training: save activations in st_forward for a following st_backward
     bool have_saves = false;      // the last forward wrote ae_save_*
     bool use_mma_bwd = true;
-    bool use_f2_bwd = true;       // FFMA2 warp-specialised autoencoder backward (ST_DISABLE_FFMA2_AE_BWD=1 -> mma.sync kernel)
-    bool use_f2_fwd = true;       // FFMA2 (packed fp32) autoencoder forward (ST_DISABLE_FFMA2_AE=1 -> mma.sync kernels)
-    bool use_tc_ae = false;       // tcgen05 autoencoder forward (ST_ENABLE_TCGEN05_AE=1): correct, but its CUDA-core epilogue
-                                  // makes it slower than the default chain
+    bool use_tm = true;           // tcgen05 autoencoders with TMEM-resident activations (st_ae_tm.cu); ST_DISABLE_TMEM_AE=1 -> the
+                                  // mma.sync kernels with saved activation records (the path geometries with T > 32 train on)
+    bool tm_fwd = false;          // the last forward ran the TMEM kernel (its backward recomputes: nothing was saved)
+    bool tm_bwd_image = false;    // ae_wpack_bwd holds the backward weight image of the current parameters
+    float *ae_wpack = nullptr, *ae_wpack_bwd = nullptr;   // shared-memory images of the autoencoder weights (st_ae_tm.cu)
     long long* ae_timing = nullptr;   // device: 16 region counters of the tensor-core AE backward (st_debug_ae_timing)
     float* small = nullptr;       // reduction scratch + scalar outputs
     unsigned* counters = nullptr;
@@ -65,6 +64,8 @@ struct st_handle {
     bool prof_on = false;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
     long launches = 0;            // kernels + device copies launched by this handle since creation
+    long simt_fallbacks = 0;      // calls served by a SIMT fallback kernel (GEMM shape or autoencoder geometry not covered by the
+                                  // tensor-core kernels; return_acts forwards count too): st_debug_fallbacks
     char err[1024];
 };
 
@@ -219,11 +220,8 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     }
     if (const char* e = getenv("ST_DISABLE_TCGEN05")) h->use_tc = !(e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_MMA_BACKWARD")) h->use_mma_bwd = !(e[0] == '1');
-    if (const char* e = getenv("ST_ENABLE_TCGEN05_AE")) h->use_tc_ae = (e[0] == '1');
-    if (const char* e = getenv("ST_DISABLE_FFMA2_AE")) h->use_f2_fwd = !(e[0] == '1');
+    if (const char* e = getenv("ST_DISABLE_TMEM_AE")) h->use_tm = !(e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_FUSED_TAIL")) h->fuse_tail = !(e[0] == '1');
-    if (const char* e = getenv("ST_TF32_AE_MMA")) h->tf32_ae_mma = (e[0] == '1');
-    if (const char* e = getenv("ST_DISABLE_FFMA2_AE_BWD")) h->use_f2_bwd = !(e[0] == '1');
     build_geom(d, h->g);
     if (st_ae_configure(h, d, h->g)) {
         snprintf(g_create_err, sizeof(g_create_err), "%s", h->err);
@@ -259,6 +257,8 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     if ((e = cudaMalloc(&h->sfold_lo, 2L * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(sfold_lo)");
     if ((e = cudaMalloc(&h->part_a, (long)kMaxSplits * 2 * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(part_a)");
     if ((e = cudaMalloc(&h->part_s, (long)kMaxSplits * 2 * d.Fp * N * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(part_s)");
+    if ((e = cudaMalloc(&h->ae_wpack, st_ae_tm_pack_floats() * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(ae_wpack)");
+    if ((e = cudaMalloc(&h->ae_wpack_bwd, st_ae_tm_bwd_pack_floats() * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(ae_wpack_bwd)");
     // windows for st_init_frontend: hamming (cls_fe_dft.py:38) and the Griffin-Lim LSEE window (:133-163)
     {
         std::vector<double> w = hamming_sym(N), win(2 * N), env(N, 0.0);
@@ -317,6 +317,8 @@ extern "C" void st_destroy(st_handle* h) {
     if (h->sfold_lo) cudaFree(h->sfold_lo);
     if (h->part_a) cudaFree(h->part_a);
     if (h->part_s) cudaFree(h->part_s);
+    if (h->ae_wpack) cudaFree(h->ae_wpack);
+    if (h->ae_wpack_bwd) cudaFree(h->ae_wpack_bwd);
     if (h->win) cudaFree(h->win);
     if (h->map_live) cudaFree(h->map_live);
     if (h->map_full) cudaFree(h->map_full);
@@ -405,6 +407,7 @@ static int analysis_only(st_handle* h, const float* x, const float* Wr, const fl
     }
     if (r < 0) {
         GemmOperand A{h->xpad, h->xpad_lo, d.H}, W{h->wcat, h->wcat_lo, d.N};
+        ++h->simt_fallbacks;
         st_launch_gemm(true, true, A, W, h->spec, F2, MT, F2, d.N, 1, 0, s);
     }
     st_launch_unpack_spec(d, h->spec, B, re, im, s);
@@ -429,6 +432,7 @@ static int synthesis_only(st_handle* h, const float* re, const float* im, const 
     }
     if (r < 0) {
         GemmOperand R{h->ri, h->ri_lo, F2}, S{h->sfold, h->sfold_lo, d.N};
+        ++h->simt_fallbacks;
         st_launch_gemm(true, false, R, S, h->fo, d.N, MO, d.N, F2, 1, 0, s);
     }
     st_launch_overlap_add(d, h->fo, nullptr, B, wave, nullptr, nullptr, s);
@@ -444,21 +448,38 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
     if (ensure_workspace(h, B)) return 1;
     // packing the weights does not depend on the batch: it runs on the side stream, beside the input padding
     const bool beside = h->side && !h->prof_on;
+    AeParams pm, pp;
+    split_params(params, pm, pp);
+    // Autoencoders: the tcgen05 / TMEM kernels (st_ae_tm.cu) wherever they cover the geometry.  Their backward recomputes
+    // the chain, so nothing is saved; it covers T <= 32, which is why a TRAINING forward with 32 < T <= 64 still takes the
+    // mma.sync kernels with saved records (st_ae_mma.cu).  return_acts is served by the SIMT kernel.
+    const bool tm_geom = h->use_tm && !acts && d.T <= 64 && d.OT <= 16 && d.K <= 8;
+    const bool tm_bwd_geom = tm_geom && d.T <= 32;
+    const bool tm_fwd = tm_geom && (tm_bwd_geom || !h->training);
+    h->tm_bwd_image = false;
     {
         cudaStream_t sp = beside ? h->side : s;
-        StageScope sc(h, SG_PACK_W, 2, s);
+        StageScope sc(h, SG_PACK_W, 2 + tm_fwd + (tm_fwd && tm_bwd_geom && h->training), s);
         if (beside) {
             ST_CUDA_OK(cudaEventRecord(h->ev_fork, s));          // behind whatever wrote the weights (the previous step's Adam)
             ST_CUDA_OK(cudaStreamWaitEvent(sp, h->ev_fork, 0));
         }
         st_launch_pack_analysis(d, params[0], params[1], h->wcat, h->wcat_lo, sp);
         st_launch_fold_synthesis(d, params[2], params[3], h->sfold, h->sfold_lo, sp);
+        if (tm_fwd)       // shared-memory images of the autoencoder weights (B = 0: pack only)
+            st_launch_ae_forward_tm(d, h->g, pm, pp, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, h->ae_wpack, nullptr,
+                                    nullptr, h->sm_count, true, sp, sp);
+        if (tm_fwd && tm_bwd_geom && h->training) {
+            st_launch_ae_backward_tm(d, h->g, pm, pp, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                     nullptr, h->ae_wpack_bwd, nullptr, nullptr, h->sm_count, true, sp, sp);
+            h->tm_bwd_image = true;
+        }
         if (beside) ST_CUDA_OK(cudaEventRecord(h->ev_join, sp));
     }
     {
-        // the knobs are copied only for the SIMT backward, which recomputes the chain; the record-based backward kernels
-        // (every geometry with OT <= 16 when training) read them from the saved activations
-        const bool keep_knobs = d.K > 0 && (acts || !(h->training && h->use_mma_bwd) || d.OT > 16);
+        // the knobs are kept for the backward kernels that recompute the chain (TMEM and SIMT); the record-based mma.sync
+        // backward reads them from the saved activations
+        const bool keep_knobs = d.K > 0;
         StageScope sc(h, SG_PAD_X, 1 + keep_knobs, s);
         // x/2 with the conv padding, as (hi, lo), window stride Sx = Tp*H (frame (b,t) = row b*Tp+t of a stride-H view)
         st_launch_pad_split(x, h->xpad, h->xpad_lo, B, d.C, d.N, d.Sx, 0.5f, s);
@@ -476,35 +497,32 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         }
         if (r < 0) {
             GemmOperand A{h->xpad, h->xpad_lo, d.H}, W{h->wcat, h->wcat_lo, d.N};
+            ++h->simt_fallbacks;
             st_launch_gemm(true, true, A, W, h->spec, F2, MT, F2, d.N, 1, 0, s);
         }
     }
     ST_LAUNCH_OK(h);
     {
-        StageScope sc(h, SG_AE_FWD, (acts ? 1 : 2) + (mag_hat_user != nullptr), s);
-        AeParams pm, pp;
-        split_params(params, pm, pp);
-        // production path: tensor-core (mma.sync TF32x3) register-resident chain; the SIMT kernel serves return_acts
+        StageScope sc(h, SG_AE_FWD, ((acts || tm_fwd) ? 1 : 2) + (mag_hat_user != nullptr), s);
         const bool save = h->training && h->use_mma_bwd;
         h->have_saves = false;
+        h->tm_fwd = false;
         bool done = false;
-        if (!acts && h->use_tc_ae)      // tcgen05 / TMEM chain; falls through to the mma.sync kernel for other geometries
-            done = st_launch_ae_forward_tc(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
-                                           save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->ae_timing ? h->ae_timing + 16 : nullptr,
-                                           h->sm_count, s);
-        // reduced-precision mode: the autoencoders stay on the exact FFMA2 chain unless ST_TF32_AE_MMA=1 (see st_handle)
-        if (!acts && !done && h->use_f2_fwd && !(h->passes == 1 && h->tf32_ae_mma))
-            done = st_launch_ae_forward_f2(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
-                                           save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr,
-                                           h->ae_timing ? h->ae_timing + 16 : nullptr, h->sm_count, s);
-        if (!acts && !done)
+        if (tm_fwd) {
+            done = st_launch_ae_forward_tm(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo, h->ae_wpack,
+                                           nullptr, nullptr, h->sm_count, false, s, s);
+            h->tm_fwd = done;
+        }
+        if (!acts && !done) {
             done = st_launch_ae_forward_mma(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
                                             save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->sm_count, s, h->passes);
-        if (!done)
+            if (done) h->have_saves = save;
+        }
+        if (!done) {
+            ++h->simt_fallbacks;
             st_launch_ae_forward(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo, acts,
                                  h->ae_grid, s);
-        else
-            h->have_saves = save;
+        }
         if (mag_hat_user)
             ST_CUDA_OK(cudaMemcpyAsync(mag_hat_user, h->mag_hat_ws, (long)B * d.OT * d.F * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
@@ -518,6 +536,7 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         }
         if (r < 0) {
             GemmOperand R{h->ri, h->ri_lo, F2}, S{h->sfold, h->sfold_lo, d.N};
+            ++h->simt_fallbacks;
             st_launch_gemm(true, false, R, S, h->fo, d.N, MO, d.N, F2, 1, 0, s);
         }
     }
@@ -619,6 +638,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         }
         if (r < 0) {
             GemmOperand G{h->gwave, h->gwave_lo, d.H}, S{h->sfold, h->sfold_lo, d.N};
+            ++h->simt_fallbacks;
             st_launch_gemm(true, true, G, S, h->g_ri, F2, MO, F2, d.N, 1, 0, s);
         }
     }
@@ -632,6 +652,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         }
         if (ss < 0) {
             GemmOperand R{h->ri, h->ri_lo, F2}, G{h->gwave, h->gwave_lo, d.H};
+            ++h->simt_fallbacks;
             ss = st_launch_gemm(false, false, R, G, h->part_s, d.N, F2, d.N, MO, std::min(kMaxSplits, std::max(1, MO / 256)), plane, s);
         }
     }
@@ -648,21 +669,25 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
     int part_ctas = h->ae_grid;
     {   // both autoencoders: back-propagate, dL/d(re|im) -> g_spec, per-CTA weight-gradient partials.  Tensor-core path
         // from the saved activations when the forward wrote them; otherwise the SIMT kernel recomputes the chain.
-        StageScope sc(h, SG_AE_BWD, (h->have_saves && h->use_f2_bwd) ? 3 : 2, s);   // FFMA2 route: two chain kernels + ae_input_grad
+        StageScope sc(h, SG_AE_BWD, 2 + (h->tm_fwd && !h->tm_bwd_image), s);
         AeParams pm, pp;
         split_params(params, pm, pp);
         int gr = 0;
-        if (h->have_saves && h->use_f2_bwd && !(h->passes == 1 && h->tf32_ae_mma))
-            gr = st_launch_ae_backward_f2(d, h->g, pm, pp, h->spec, B, h->ae_save_m, h->ae_save_p, h->mag_hat_ws, h->phs_hat_ws,
-                                          h->g_ri, g_mag_hat, g_mag, h->gtrack_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_timing, h->sm_count, s);
+        if (h->tm_fwd && h->use_tm)       // recompute in tensor memory; the weight image is packed here when the forward was an eval one
+            gr = st_launch_ae_backward_tm(d, h->g, pm, pp, h->spec, h->knobs_ws, B, h->mag_hat_ws, h->phs_hat_ws, h->g_ri, g_mag_hat, g_mag,
+                                          h->gtrack_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_wpack_bwd, nullptr, h->ae_timing, h->sm_count,
+                                          !h->tm_bwd_image, s, s);
+        if (gr > 0) h->tm_bwd_image = true;
         if (gr == 0 && h->have_saves)
             gr = st_launch_ae_backward_mma(d, h->g, pm, pp, h->spec, B, h->ae_save_m, h->ae_save_p, h->mag_hat_ws, h->phs_hat_ws,
                                            h->g_ri, g_mag_hat, g_mag, h->tail_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_timing, h->sm_count, s, h->passes);
         if (gr > 0)
             part_ctas = gr;
-        else
+        else {
+            ++h->simt_fallbacks;
             st_launch_ae_backward(d, h->g, pm, pp, h->spec, h->knobs_ws, B, h->mag_hat_ws, h->phs_hat_ws, h->g_ri, g_mag_hat,
                                   g_mag, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_grid, s);
+        }
     }
     ST_LAUNCH_OK(h);
     // the per-CTA autoencoder partials are summed on the side stream, beside the analysis weight-gradient GEMM
@@ -692,6 +717,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         }
         if (sa < 0) {
             GemmOperand Gs{h->g_spec, h->g_spec_lo, F2}, X{h->xpad, h->xpad_lo, d.H};
+            ++h->simt_fallbacks;
             sa = st_launch_gemm(false, false, Gs, X, h->part_a, d.N, F2, d.N, MT, std::min(kMaxSplits, std::max(1, MT / 256)), plane, s);
         }
     }
@@ -988,18 +1014,20 @@ extern "C" int st_debug_gemm(st_handle* h, int use_tc /*0 FFMA, 1 tcgen05, 2 tcg
 
 // Diagnostic: enable (on=1) region timing of the tensor-core autoencoder backward and read the 16 cycle counters
 // (backward: 8 regions x {magnitude, phase}; then tcgen05 forward: 4 regions x 2; 24 values).  Reading resets them.  out may be NULL.
+extern "C" long st_debug_fallbacks(const st_handle* h) { return h ? h->simt_fallbacks : -1; }
+
 extern "C" int st_debug_ae_timing(st_handle* h, int on, long long* out_host) {
     if (!h) return 1;
     ST_ON_DEVICE(h);
     ST_CUDA_OK(cudaSetDevice(h->device));
     ST_CUDA_OK(cudaDeviceSynchronize());
     if (on && !h->ae_timing) {
-        ST_CUDA_OK(cudaMalloc(&h->ae_timing, 24 * sizeof(long long)));
-        ST_CUDA_OK(cudaMemset(h->ae_timing, 0, 24 * sizeof(long long)));
+        ST_CUDA_OK(cudaMalloc(&h->ae_timing, 64 * sizeof(long long)));
+        ST_CUDA_OK(cudaMemset(h->ae_timing, 0, 64 * sizeof(long long)));
     }
     if (out_host && h->ae_timing) {
         ST_CUDA_OK(cudaMemcpy(out_host, h->ae_timing, 24 * sizeof(long long), cudaMemcpyDeviceToHost));
-        ST_CUDA_OK(cudaMemset(h->ae_timing, 0, 24 * sizeof(long long)));
+        ST_CUDA_OK(cudaMemset(h->ae_timing, 0, 64 * sizeof(long long)));
     }
     if (!on && h->ae_timing) { cudaFree(h->ae_timing); h->ae_timing = nullptr; }
     return 0;
@@ -1045,6 +1073,7 @@ extern "C" int st_dct_analysis(st_handle* h, const float* x, const float* w, con
     }
     if (r < 0) {
         GemmOperand A{xh, xl, hop}, W{wh, wl, wsz};
+        ++h->simt_fallbacks;
         st_launch_gemm(true, true, A, W, tmp, sz, (int)MT, sz, wsz, 1, 0, s);
     }
     st_launch_dct_bias_unpack(tmp, bias, B, nf, Tp, sz, out, s);
@@ -1076,6 +1105,7 @@ extern "C" int st_dct_synthesis(st_handle* h, const float* x_ft, const float* w,
     }
     if (r < 0) {
         GemmOperand A{ah, al, sz}, S{wh, wl, wsz};
+        ++h->simt_fallbacks;
         st_launch_gemm(true, false, A, S, fo, wsz, (int)M, wsz, sz, 1, 0, s);
     }
     st_launch_dct_overlap_add(fo, B, nf, sz, wsz, hop, C, wave, s);

@@ -148,27 +148,11 @@ bool st_launch_ae_forward_mma(const StDims& d, const AeGeom& g, const AeParams& 
                               const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri_hi, float* ri_lo,
                               float* save_m, float* save_p, int sm_count, cudaStream_t s, int passes = 3);
 
-// st_ae_tc.cu: tcgen05 / TMEM autoencoder forward (same contract and record layout; T <= 32, OT <= 16)
-bool st_launch_ae_forward_tc(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
-                             const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri_hi, float* ri_lo,
-                             float* save_m, float* save_p, long long* timing /*nullable: 8 counters*/, int sm_count, cudaStream_t s);
-// st_ae_f2.cu: packed-fp32 (FFMA2) autoencoders, exact fp32 (production path; same record layout; T <= 32, OT <= 16)
-bool st_launch_ae_forward_f2(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
-                             const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri_hi, float* ri_lo,
-                             float* save_m, float* save_p, long long* timing /*nullable: 8 counters*/, int sm_count, cudaStream_t s);
 int st_launch_ae_backward_mma(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, int B,
                               const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat,
                               const float* g_ri, const float* g_mag_hat, const float* g_mag, float* tail_ws, float* g_spec_hi,
                               float* g_spec_lo, float* partials, long long* timing /*nullable: 16 counters*/, int sm_count, cudaStream_t s,
                               int passes = 3);
-
-// st_ae_f2_bwd.cu: warp-specialised packed-fp32 backward from the same records (production path; T <= 32, OT <= 16).
-// Returns the number of per-CTA partial-gradient vectors written (0: geometry not covered).
-int st_launch_ae_backward_f2(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, int B,
-                             const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat,
-                             const float* g_ri, const float* g_mag_hat, const float* g_mag, float* g_track /*2*B*T*F*/, float* g_spec,
-                             float* g_spec_lo, float* partials, long long* timing /*nullable: 16 counters*/, int sm_count,
-                             cudaStream_t s);
 
 // st_ae_tm.cu: tcgen05 autoencoders with TMEM-resident activations (production path; T <= 64, OT <= 16, K <= 8).
 // Forward: both autoencoders of a 128-row tile in one CTA, no saved activations.  Returns false when the geometry is not covered.
@@ -185,7 +169,8 @@ long st_ae_tm_bwd_pack_floats();
 int st_launch_ae_backward_tm(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
                              const float* knobs, int B, const float* mag_hat, const float* phs_hat, const float* g_ri,
                              const float* g_mag_hat, const float* g_mag, float* g_track, float* g_spec, float* g_spec_lo,
-                             float* partials, float* wpack, float* dbg, int sm_count, bool pack, cudaStream_t s_pack, cudaStream_t s);
+                             float* partials, float* wpack, float* dbg, long long* timing /*nullable: 64 counters*/, int sm_count, bool pack,
+                             cudaStream_t s_pack, cudaStream_t s);
 
 // st_data.cu
 void st_launch_compressor_4c(const float* x, const double* knobs_wc, int B, int n, double sr, float* scratch, float* y, cudaStream_t s);

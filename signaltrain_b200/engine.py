@@ -202,6 +202,10 @@ class Engine:
     def precision(self):
         return {v: k for k, v in self.PRECISIONS.items()}[self.lib.st_get_precision(self.h)]
 
+    def fallback_count(self):
+        """Calls served by a SIMT fallback kernel since the handle was created (0 on the benchmarked path)."""
+        return int(self.lib.st_debug_fallbacks(self.h))
+
     def set_training(self, on):
         self._ok(self.lib.st_set_training(self.h, int(bool(on))), "st_set_training")
 

@@ -247,7 +247,7 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(dgmh, gmh.data(), gmh.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemset(dpart, 0, (long)sm * g.flat_total * 4)); CK(cudaMemset(ddbg2, 0, 18L * 128 * 64 * 4)); CK(cudaMemset(dgt, 0, 2L * Bmax * d.T * d.F * 4));
         const int nslot = st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, B, dcmh, dcph, dgri, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb,
-                                                   ddbg2, sm, true, 0, 0);
+                                                   ddbg2, nullptr, sm, true, 0, 0);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("backward: CUDA error %s\n", cudaGetErrorString(e)); return 2; }
         printf("backward: %d partial slots per autoencoder\n", nslot);
@@ -295,15 +295,31 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&dcmh2, nout * 4)); CK(cudaMalloc(&dcph2, nout * 4));
         CK(cudaMemset(dcmh2, 0, nout * 4)); CK(cudaMemset(dcph2, 0, nout * 4));
         float* dgri2; CK(cudaMalloc(&dgri2, nri * 4)); CK(cudaMemset(dgri2, 0, nri * 4));
-        for (int i = 0; i < 3; ++i) st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, sm, false, 0, 0);
+        for (int i = 0; i < 3; ++i) st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, nullptr, sm, false, 0, 0);
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(b0));
-        for (int i = 0; i < 20; ++i) st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, sm, false, 0, 0);
+        for (int i = 0; i < 20; ++i) st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, nullptr, sm, false, 0, 0);
         CK(cudaEventRecord(b1));
         CK(cudaDeviceSynchronize());
         float bms = 0;
         CK(cudaEventElapsedTime(&bms, b0, b1));
         printf("backward timing: B=%d  %.2f us per launch (both autoencoders, without the track->spec kernel)\n", TB, 1000.f * bms / 20);
+        {
+            long long* dt2;
+            CK(cudaMalloc(&dt2, 64 * sizeof(long long)));
+            CK(cudaMemset(dt2, 0, 64 * sizeof(long long)));
+            const int ns = st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, dt2, sm, false, 0, 0);
+            CK(cudaDeviceSynchronize());
+            long long ht2[64];
+            CK(cudaMemcpy(ht2, dt2, sizeof(ht2), cudaMemcpyDeviceToHost));
+            const char* names[7] = {"prologue", "wait_d", "fwd_epi", "dec", "bwd_epi", "handoff+stage", "final"};
+            printf("backward chain-warp clocks per CTA (%d CTAs):\n", 2 * ns);
+            for (int w = 0; w < 8; w += 3) {
+                printf("  warp %d:", w);
+                for (int i = 0; i < 7; ++i) printf(" %s %.0f", names[i], (double)ht2[8 * w + i] / (2 * ns));
+                printf("\n");
+            }
+        }
     }
 
     // ---------------- timing ----------------

@@ -309,9 +309,9 @@ def test_standalone_analysis_synthesis_roundtrip():
 
 
 def test_autoencoder_backward_implementations_agree(monkeypatch):
-    """The warp-specialised FFMA2 backward (production), the mma.sync backward and the recomputing SIMT backward are three
-    independent implementations of the same gradients: they must agree on a ragged batch (37 windows: the last 32-row
-    chunk of every kernel is partial) and on a large one (512, BASELINE configs[2] shape)."""
+    """The tcgen05 / TMEM backward with in-kernel recompute (production), the mma.sync backward from saved records and the
+    recomputing SIMT backward are three independent implementations of the same gradients: they must agree on a ragged batch
+    (37 windows: the last tile of every kernel is partial) and on a large one (512, BASELINE configs[2] shape)."""
     d = O.model_dims(1, 4, 4)
     P = O.init_params(d, seed=3)
     rng = np.random.RandomState(9)
@@ -321,8 +321,8 @@ def test_autoencoder_backward_implementations_agree(monkeypatch):
         knobs = (rng.beta(0.8, 0.8, (B, d.K)) - 0.5).astype(np.float32)
         y = np.tanh(1.3 * x[:, -d.L:]).astype(np.float32)
         results = []
-        for env in ({}, {"ST_DISABLE_FFMA2_AE_BWD": "1"}, {"ST_DISABLE_FFMA2_AE_BWD": "1", "ST_DISABLE_MMA_BACKWARD": "1"}):
-            for k in ("ST_DISABLE_FFMA2_AE_BWD", "ST_DISABLE_MMA_BACKWARD"):
+        for env in ({}, {"ST_DISABLE_TMEM_AE": "1"}, {"ST_DISABLE_TMEM_AE": "1", "ST_DISABLE_MMA_BACKWARD": "1"}):
+            for k in ("ST_DISABLE_TMEM_AE", "ST_DISABLE_MMA_BACKWARD"):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
