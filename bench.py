@@ -2,7 +2,10 @@
 """bench.py -- audio frames/s per train step (comp_4c), BASELINE.json's metric.
 
   python bench.py --gpus N --steps K --warmup W           # this repo's CUDA path (one process per GPU under torchrun)
-  python bench.py --impl reference --gpus N ...           # the reference's algorithm on the host CPU (oracle port)
+  python bench.py --impl reference --gpus N ...           # the reference's train step on the host CPU: the unmodified reference
+                                                          # when its tree is present (SIGNALTRAIN_REFERENCE, /root/reference), else the
+                                                          # numpy port (oracle/st_oracle.py) + the port/reference time ratio measured
+                                                          # where both could run (profiles/r02_cpu_port_vs_reference.json)
 
 A "step" is one full iteration of the reference's loop body (train.py:112-151): forward, log-cosh/L1 loss,
 backward, L1 clip, Adam, on one batch of synthetic comp_4c windows.  1 audio frame = 1 input PCM sample consumed
@@ -28,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 CHUNK_SCALE, SHRINK, KNOBS, SR = 1, 4, 4, 44100
 METRIC = "audio frames/sec per train step (comp_4c)"
+NCU_SUMMARY = "r02_ae_tm_ncu_full_summary.csv"     # `ncu --set full` of the autoencoder kernels of THIS build (scripts/ncu_summary.py)
 
 # BASELINE.json configs by index.  1 is the bench line (the config the metric is quoted on); 2-4 are the other GPU configs,
 # runnable here as extra, clearly labelled lines (--workload N) at N=1 or under torchrun: per-GPU batch as named, synthetic
@@ -74,24 +78,53 @@ def measured_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback (B200_PROFILING.md)")
 
 
+def measure_tf32_peak(dev):
+    """Dense TF32 GEMM rate of this GPU measured the way MEASURED_PEAKS.json measures bf16: torch.matmul 8192^3 with TF32
+    products allowed, best of 5 after warm-up, CUDA events.  TFLOP/s (2 N^3 flops)."""
+    import torch
+    n = 8192
+    a = torch.randn(n, n, device=dev)
+    b = torch.randn(n, n, device=dev)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for _ in range(2):
+            torch.matmul(a, b)
+        best = float("inf")
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
 def ncu_dram_traffic(stage):
     """dram__bytes_read + dram__bytes_write of the stage's kernels from the committed `ncu --set full` summary (bytes per
     stage = sum over its launches), or (None, why)."""
-    path = os.path.join(ROOT, "profiles", "r01_v7_ae_f2_ncu_full_summary.csv")
-    want = {"ae_backward": "ae_bwd_f2_kernel", "ae_forward": "ae_fwd_f2_kernel"}.get(stage)
+    path = os.path.join(ROOT, "profiles", NCU_SUMMARY)
+    want = {"ae_backward": ("ae_bwd_tm_kernel", "ae_track_to_spec_kernel"), "ae_forward": ("ae_fwd_tm_kernel",)}.get(stage)
     if want is None or not os.path.exists(path):
-        return None, "no ncu --set full capture of this kernel committed"
+        return None, "no ncu --set full capture of this kernel committed for this build"
     import csv
-    rows = list(csv.reader(open(path)))
-    cols = [i for i, n in enumerate(rows[0]) if n.startswith(want)]
-    tot = 0.0
-    for r in rows[1:]:
-        if r[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            tot += sum(float(r[i]) for i in cols) * 1e6
-    n = len(cols)
-    if stage == "ae_forward":          # the capture holds one of the stage's two launches
-        tot, n = 2 * tot / max(n, 1), 2
-    return tot, f"profiles/r01_v7_ae_f2_ncu_full_summary.csv ({n} launches of {want}, B=200)"
+    rows = list(csv.reader(open(path)))            # scripts/ncu_summary.py: one column per captured launch
+    cols = [i for i, n in enumerate(rows[0]) if any(n.startswith(w_) for w_ in want)]
+    if not cols:
+        return None, f"profiles/{NCU_SUMMARY} holds no launch of {want}"
+    seen, tot = set(), 0.0
+    for i in cols:                                  # one launch of each kernel of the stage
+        if rows[0][i] in seen:
+            continue
+        seen.add(rows[0][i])
+        for r in rows[1:]:
+            if r[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(r[i]) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(r[1], 1e6)
+    return tot, f"profiles/{NCU_SUMMARY} (one launch each of {', '.join(sorted(seen))}, B=200, this round's build)"
 
 
 def stage_work(d, B):
@@ -106,7 +139,7 @@ def stage_work(d, B):
         "gemm_synthesis": dict(bound="tensor", flops=4 * d.OT * d.F * d.N * B, bytes=4 * (2 * BOF + W + B * d.OT * d.N)),
         "gemm_synthesis_dgrad": dict(bound="tensor", flops=4 * d.OT * d.F * d.N * B, bytes=4 * (B * d.L + 2 * BOF + W)),
         "gemm_synthesis_wgrad": dict(bound="tensor", flops=4 * d.OT * d.F * d.N * B, bytes=4 * (B * d.L + 2 * BOF + W)),
-        "ae_backward": dict(bound="hbm", flops=12 * d.F * ae_mac * B, bytes=4 * (4 * BOF + 4 * BTF + 2 * p_ae)),
+        "ae_backward": dict(bound="hbm", flops=12 * d.F * ae_mac * B, bytes=4 * (2 * BOF + 4 * BTF + 2 * p_ae)),
         "gemm_analysis_wgrad": dict(bound="tensor", flops=4 * d.T * d.F * d.N * B, bytes=4 * (B * d.C + 2 * BTF + W)),
         "adam": dict(bound="hbm", flops=12 * p_live, bytes=7 * 4 * p_live),
         "pack_weights": dict(bound="hbm", flops=0, bytes=4 * (4 * d.N * d.N * 3 // 4 + 2 * W)),
@@ -155,8 +188,24 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_step_rate(B, steps, warmup, threads, wl=None):
-    """The reference's algorithm (oracle port, float32) on the host cores: frames/s and ms/step."""
+def workload_name(wl, B):
+    """The SAME string in both arms (the GPU count lives in n_gpus / config.gpus)."""
+    return wl["name"].replace(f"batch={wl['batch']} per GPU", f"batch={B} per GPU")
+
+
+def port_over_reference():
+    """Time ratio port / unmodified reference measured where both could run (scripts/measure_port_vs_reference.py)."""
+    path = os.path.join(ROOT, "profiles", "r02_cpu_port_vs_reference.json")
+    if os.path.exists(path):
+        j = json.load(open(path))
+        return float(j["port_over_reference_time"]), f"profiles/r02_cpu_port_vs_reference.json (B={j['batch']}, {j['threads']} threads, {j['where']})"
+    return None, "not measured"
+
+
+def cpu_reference_step_rate(B, steps, warmup, threads, wl=None, batches=None, params=None):
+    """The reference's algorithm (oracle port, float32) on the host cores: frames/s, ms/step and the per-step losses.
+    batches: optional list of (x, y, knobs) numpy batches to step through in order (the oracle replay of bench.py's first
+    steps); params: optional initial parameters (name -> array), default the port's own seeded init."""
     wl = wl or WORKLOADS[1]
     from oracle import st_oracle as O
     from signaltrain_b200 import data
@@ -165,37 +214,65 @@ def cpu_reference_step_rate(B, steps, warmup, threads, wl=None):
     except Exception:
         threadpool_limits = None
     d = O.model_dims(wl["scale"], SHRINK, wl["knobs"])
-    x, y, k = data.make_pool(B, d.C, d.L, getattr(data, wl["effect"])(), SR, seed=218)
+    if batches is None:
+        batches = [data.make_pool(B, d.C, d.L, getattr(data, wl["effect"])(), SR, seed=218)]
     lr_sched, _ = O.get_1cycle_schedule(1e-4, 200000, 1000, 200)
-    tr = O.Trainer(d, O.init_params(d, seed=218), lr_sched, dtype=np.float32)
+    tr = O.Trainer(d, params if params is not None else O.init_params(d, seed=218), lr_sched, dtype=np.float32)
     ctx = threadpool_limits(limits=threads) if threadpool_limits else None
-    for _ in range(warmup):
-        tr.step(x, y, k)
+    losses = []
     t0 = time.perf_counter()
-    for _ in range(steps):
-        tr.step(x, y, k)
+    for i in range(warmup + steps):
+        if i == warmup:
+            t0 = time.perf_counter()
+        x, y, k = batches[i % len(batches)]
+        losses.append(tr.step(x, y, k)[0])
     dt = time.perf_counter() - t0
     if ctx is not None:
         ctx.unregister() if hasattr(ctx, "unregister") else None
-    return B * d.C * steps / dt, 1e3 * dt / steps
+    return B * d.C * steps / dt, 1e3 * dt / steps, losses
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU train step on this box's host cores, all threads, same workload string, metric
+    and unit as the native arm.  Each step is one full train step of the workload's batch (about 1-2 s of CPU work), so the
+    requested --steps/--warmup are honoured up to a budget of ~150 s of CPU time; a clamp is stated in the line."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     wl = WORKLOADS[args.workload]
     B = args.batch or wl["batch"]
-    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    fps, ms = cpu_reference_step_rate(B, steps, warm, threads, wl)
+    from oracle import ref_loader
+    from oracle import st_oracle as O
+    from signaltrain_b200 import data
+    ref = ref_loader.load_reference()
+    d = O.model_dims(wl["scale"], SHRINK, wl["knobs"])
+    x, y, k = data.make_pool(B, d.C, d.L, getattr(data, wl["effect"])(), SR, seed=218)
+    run = (lambda st_, w_: ref_loader.reference_step_rate(ref, x, y, k, st_, w_, threads, scale=wl["scale"], shrink=SHRINK)) if ref is not None \
+        else (lambda st_, w_: cpu_reference_step_rate(B, st_, w_, threads, wl)[:2])
+    _, probe_ms = run(1, 1)                                       # one warm step to size the run
+    budget_steps = max(2, int(150e3 / max(probe_ms, 1.0)))
+    warm = max(0, min(args.warmup, budget_steps // 4))
+    steps = max(1, min(args.steps, budget_steps - warm))
+    fps, ms = run(steps, warm)
+    ratio, ratio_src = port_over_reference()
+    kind = "reference" if ref is not None else "port"
+    cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+           "sample": f"{steps} full train steps of B={B} windows (+{warm + 2} warm-up) by " +
+                     ("the unmodified reference (signaltrain.nn_proc.st_model + calc_loss + clip_grad_norm_ + torch.optim.Adam, torch CPU, "
+                      f"{threads} threads)" if ref is not None else f"oracle/st_oracle.py Trainer (float32 numpy/BLAS, {threads} threads)")}
+    if ref is None:
+        cpu["port_over_reference_time"] = ratio
+        cpu["port_over_reference_source"] = ratio_src
+        cpu["note"] = ("the reference tree does not travel to this box: this is the numpy port; where both ran, the port took "
+                       f"{ratio:.2f}x the unmodified reference's time per step" if ratio else "the reference tree does not travel to this box: numpy port")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": wl["name"].replace(f"batch={wl['batch']} per GPU", f"batch={B}"), "where": "host CPU (float32)"},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": f"{steps} full train steps of B={B} windows (oracle/st_oracle.py Trainer, float32, "
-                                       f"numpy/BLAS on {threads} threads)"},
+            "config": {"workload": workload_name(wl, B), "where": "host CPU (float32)", "gpus": args.gpus,
+                       "steps_requested": args.steps, "warmup_requested": args.warmup,
+                       "steps_clamped": steps != args.steps or warm != args.warmup},
+            "cpu_baseline": cpu,
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -245,11 +322,25 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the first steps are replayed by the oracle in the cpu_baseline leg: keep the initial parameters and the losses
+    replay_n = 3 if (world == 1 and not args.no_cpu_baseline) else 0
+    P0 = {n: p.detach().cpu().numpy().copy() for n, p in zip([n for n, _ in model.named_parameters()], model.parameters())} if replay_n else None
+    first_losses = []
     it = 0
     for _ in range(Wm):
-        trainer.step(*batch_of(it, (xd, yd, kd)))
+        l_ = trainer.step(*batch_of(it, (xd, yd, kd)))
+        if it < replay_n:
+            first_losses.append(l_.clone())
         it += 1
     eng = trainer.eng
+    # data-parallel replicas must hold identical parameters (deterministic update of identically reduced gradients)
+    replicas_equal = None
+    if world > 1:
+        chk = torch.stack([p.detach().double().sum() for p in trainer.params] + [p.detach().double().abs().sum() for p in trainer.params])
+        allchk = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allchk, chk)
+        replicas_equal = all(bool(torch.equal(allchk[0], c)) for c in allchk[1:])
+    tf32_peak = measure_tf32_peak(dev) if rank == 0 else None
     # ---- timed region: K steps, device-resident inputs ------------------------------------------------------
     clocks = ClockSampler(local)
     barrier()
@@ -308,8 +399,8 @@ def run_native(args):
     top = max((k for k in stages if k in work), key=lambda k: stages[k][0])
     w = work[top]
     dur_s = stages[top][0] * 1e-3
-    if w["bound"] == "tensor":
-        achieved, peak, unit = w["flops"] / dur_s / 1e12, peaks["bf16_sustained"], "TFLOP/s"
+    if w["bound"] == "tensor":       # fp32-fidelity GEMMs are 3xTF32: algorithmic FLOPs against the measured TF32 rate
+        achieved, peak, unit = w["flops"] / dur_s / 1e12, tf32_peak, "TFLOP/s"
     else:
         achieved, peak, unit = w["bytes"] / dur_s / 1e9, peaks["hbm"], "GB/s"
     traffic, traffic_src = ncu_dram_traffic(top) if args.workload == 1 and B == 200 else (None, "no ncu --set full capture at this workload")
@@ -318,26 +409,30 @@ def run_native(args):
                 "share_of_step": stages[top][0] / step_sum if step_sum else None,
                 "algorithmic_bytes": w["bytes"], "algorithmic_flops": w["flops"],
                 "stages_ms": {k: round(v[0], 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])}}
-    if top in ("ae_backward", "ae_forward") and wl["precision"] == "fp32" and CHUNK_SCALE == 1:
-        # the autoencoder chains run on the packed-fp32 FMA pipe by design (exact fp32): besides the
-        # HBM figure the contract asks for, state how far they are from the CUDA-core peak (no recompute: 2/3 of the flops)
-        useful = w["flops"] * (2.0 / 3.0 if top == "ae_backward" else 1.0)
-        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-        roofline["fp32_fma"] = {"achieved_tflops": useful / dur_s / 1e12, "peak_tflops": fp32_peak,
-                                "frac": useful / dur_s / 1e12 / fp32_peak,
-                                "note": "148 SMs x 128 FMA lanes x 2 x 1.965 GHz; ncu (both kernels on all SMs): FMA pipe 32 %, shared-memory data "
-                                        "pipe 59 % (profiles/r01_v6_ae_f2_ncu_full_summary.csv)"}
+    roofline["tf32_peak_tflops"] = tf32_peak
+    roofline["tf32_peak_source"] = "measured in this run: torch.matmul 8192^3 with TF32 products, best of 5 (same recipe as MEASURED_PEAKS.json's bf16)"
+    gemm_flops = sum(work[k]["flops"] for k in stages if k.startswith("gemm_") and k in work)
+    gemm_ms = sum(stages[k][0] for k in stages if k.startswith("gemm_") and k in work)
+    if gemm_ms > 0:
+        roofline["gemms"] = {"ms": gemm_ms, "algorithmic_tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12,
+                             "frac_of_tf32_peak": gemm_flops / (gemm_ms * 1e-3) / 1e12 / tf32_peak,
+                             "note": "3xTF32: the tensor pipe issues 3x the algorithmic FLOPs"}
     # CPU baseline: the oracle port on this box's host cores, bounded sample
     cores = os.cpu_count() or 1
-    cpu_fps, cpu_ms = (None, None)
+    cpu_fps, cpu_ms, replay = (None, None, None)
     if world == 1 and not args.no_cpu_baseline:
-        cpu_fps, cpu_ms = cpu_reference_step_rate(B, 3, 1, cores, wl)
+        # the port steps through THE SAME first batches from THE SAME initial parameters: timing sample + oracle replay
+        host_first = [tuple(a_[(i % nbatch) * B:(i % nbatch) * B + B] for a_ in (xh, yh, kh)) for i in range(replay_n)]
+        cpu_fps, cpu_ms, ol = cpu_reference_step_rate(B, replay_n - 1, 1, cores, wl, batches=host_first, params=P0)
+        gl = [float(l_.item()) for l_ in first_losses]
+        replay = {"steps": replay_n, "gpu_losses": gl, "oracle_losses": ol,
+                  "max_abs_diff": max(abs(a_ - b_) for a_, b_ in zip(gl, ol)),
+                  "note": "first train steps of this run replayed by oracle.Trainer (float32) from the same initial parameters on the same batches"}
     frames = world * B * C
     line = {"metric": METRIC, "value": frames * K / (ms_total * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": wl["dtype"], "data": "synthetic",
-            "config": {"workload": wl["name"].replace(f"batch={wl['batch']} per GPU", f"batch={B} per GPU") + f", {world}xB200",
-                       "precision": eng.precision,
+            "config": {"workload": workload_name(wl, B), "gpus": world, "precision": eng.precision,
                        "global_batch": world * B, "windows_per_s": world * B * K / (ms_total * 1e-3),
                        "stft_frames_per_s": world * B * d.T * K / (ms_total * 1e-3),
                        "l2": f"pool: each step reads a different batch of a {P}-window ({P * (C + L + KNOBS) * 4 / 1e6:.0f} MB) pool",
@@ -345,10 +440,18 @@ def run_native(args):
             "e2e": {"value": frames * Ke / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": 1e3 * e2e_s / Ke,
                     "api": "signaltrain_b200.train.FusedTrainer.run_host_batches: pinned host batches, H2D of batch i+1 on a copy stream while step i (st_train_step) runs, every step's loss read back to the host (one step late)"},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
+            "gpu_launches": int(launches), "simt_fallbacks": eng.fallback_count(), "clocks": clk, "roofline": roofline}
+    if replicas_equal is not None:
+        line["replica_parameters_identical"] = replicas_equal
     if cpu_fps is not None:
+        ratio, ratio_src = port_over_reference()
         line["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port", "ms_per_step": cpu_ms,
-                                "sample": f"3 full train steps of B={B} windows by oracle/st_oracle.py (float32 numpy/BLAS, {cores} threads)"}
+                                "sample": f"{replay_n - 1} full train steps of B={B} windows (+1 warm-up) by oracle/st_oracle.py (float32 numpy/BLAS, "
+                                          f"{cores} threads), on this run's first batches",
+                                "port_over_reference_time": ratio, "port_over_reference_source": ratio_src}
+        line["oracle_replay"] = replay
+    if line["simt_fallbacks"] != 0:
+        raise RuntimeError(f"bench.py: {line['simt_fallbacks']} calls of the timed path fell back to SIMT kernels")
     emit(line)
     if world > 1:
         dist.destroy_process_group()

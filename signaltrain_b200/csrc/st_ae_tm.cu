@@ -549,6 +549,10 @@ constexpr int SUB_BYTES = 12288;                    // staging sub-buffer: 48 fe
 // TMEM columns
 constexpr uint32_t TC_AH = 256, TC_AL = 320, TC_D = 384, TC_DW = 448;
 __host__ __device__ constexpr uint32_t tc_act(int l) { constexpr uint32_t t[NL] = {0, 0, 64, 96, 112, 128, 144, 160, 192}; return t[l]; }   // act[1..8]
+// Accumulator columns of layer L's weight gradient: the saved output of layer L (act[L + 1]) is dead once every quadrant has
+// staged layer L + 1 -- which the issuer has waited for before it starts layer L -- so every layer has its own columns and the
+// issuer never waits for a flush inside a tile.  Layer 8 uses the spare columns.
+__host__ __device__ constexpr uint32_t tc_dw(int l) { return l == NL - 1 ? TC_DW : tc_act(l + 1); }
 
 template <class TB>
 struct BwdSmem {
@@ -557,6 +561,8 @@ struct BwdSmem {
     static constexpr uint32_t VTAIL = BIAS + 4u * ((TB::bfloats + 255) / 256 * 256);
     static constexpr uint32_t BARS = VTAIL + 4u * XCH_J * TILE;
     static constexpr uint32_t TOTAL = BARS + 256;
+    static constexpr uint32_t RELOAD_LO = 16384, RELOAD_BYTES = 4u * SUB_BYTES;     // forward-weight bytes clobbered by staging (quadrants 2, 3)
+    static_assert(RELOAD_LO + RELOAD_BYTES <= STAGE, "the aliased staging buffers must lie inside the forward weights");
     static_assert(STAGE % 1024 == 0 && WT_HI % 1024 == 0 && WT_LO % 1024 == 0, "operand planes must be 1024-byte aligned");
 };
 
@@ -613,7 +619,13 @@ struct Stg {
     // Quadrants q and q + 2 share the 24 KB buffer (q & 1) and alternate strictly (q first): barriers are per QUADRANT
     // (full[q]: slice written, free[q]: slice consumed), so every waiter observes every phase of the barrier it waits on
     // (an mbarrier parity wait cannot tell phase k from phase k + 2).
-    __host__ __device__ static constexpr uint32_t buf(int q) { return BwdSmem<TB>::STAGE + (uint32_t)(q & 1) * 2u * SUB_BYTES; }
+    // A private 24 KB buffer per quadrant.  Quadrants 0 and 1 use the staging region; quadrants 2 and 3 use bytes [16 KB, 64 KB)
+    // of the FORWARD weights, which nobody reads during the backward half of a tile -- that part of the image is copied in
+    // again (one bulk copy, issued by the weight-gradient issuer once its last MMAs of the tile are done) while the next
+    // tile's prologue runs.  (Shared memory has no room for four buffers beside both weight images.)
+    __host__ __device__ static constexpr uint32_t buf(int q) {
+        return q < 2 ? BwdSmem<TB>::STAGE + (uint32_t)q * 2u * SUB_BYTES : BwdSmem<TB>::RELOAD_LO + (uint32_t)(q - 2) * 2u * SUB_BYTES;
+    }
     static_assert((MF + NF) * 256 <= 2 * SUB_BYTES, "slice does not fit its staging buffer");
 };
 
@@ -628,9 +640,9 @@ __device__ __forceinline__ void issue_wgrad_slice(uint32_t dlo_base) {
     constexpr uint32_t a_hi = (buf + S::M_HI - moff) >> 4, a_lo = (buf + S::M_LO - moff) >> 4, b_hi = (buf + S::N_HI) >> 4, b_lo = (buf + S::N_LO) >> 4;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-        umma_ss_lohi(TC_DW, dlo_base + a_lo + 2 * ks, dlo_base + b_hi + 2 * ks, DESC_HI_SW128, idesc, (Q > 0 || ks > 0) ? 1u : 0u);
-        umma_ss_lohi(TC_DW, dlo_base + a_hi + 2 * ks, dlo_base + b_lo + 2 * ks, DESC_HI_SW128, idesc, 1u);
-        umma_ss_lohi(TC_DW, dlo_base + a_hi + 2 * ks, dlo_base + b_hi + 2 * ks, DESC_HI_SW128, idesc, 1u);
+        umma_ss_lohi(tc_dw(L), dlo_base + a_lo + 2 * ks, dlo_base + b_hi + 2 * ks, DESC_HI_SW128, idesc, (Q > 0 || ks > 0) ? 1u : 0u);
+        umma_ss_lohi(tc_dw(L), dlo_base + a_hi + 2 * ks, dlo_base + b_lo + 2 * ks, DESC_HI_SW128, idesc, 1u);
+        umma_ss_lohi(tc_dw(L), dlo_base + a_hi + 2 * ks, dlo_base + b_hi + 2 * ks, DESC_HI_SW128, idesc, 1u);
     }
 }
 
@@ -648,8 +660,10 @@ __device__ __forceinline__ void stage_put(uint8_t* plane_hi, uint8_t* plane_lo, 
 template <class TB, int L>
 __device__ __forceinline__ void bwd_handoff(uint8_t* smem_raw, uint32_t t_lane, uint32_t lane_off, int half, int q, int it, int lane,
                                             const float (&gz)[TB::n(L) / 2], uint64_t* a_ready, uint64_t* full, uint64_t* freeb,
-                                            const float (&vkeep)[16], const float* knobs, long knob_off, int nk) {
+                                            const float (&vkeep)[16], const float* knobs, long knob_off, int nk, long long* hb = nullptr) {
     using S = Stg<TB, L>;
+    long long hc = hb ? clock64() : 0;
+#define HB(k) if (hb) { const long long n_ = clock64(); hb[k] += n_ - hc; hc = n_; }
     constexpr int NLOC = TB::n(L) / 2;
     const int c0 = half * NLOC;
     uint32_t ghi[NLOC], glo[NLOC];
@@ -661,14 +675,16 @@ __device__ __forceinline__ void bwd_handoff(uint8_t* smem_raw, uint32_t t_lane, 
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(a_ready);
+    HB(0)
     // ---- weight-gradient slice
-    // the shared buffer: quadrant q < 2 fills first (after its partner's previous slice was consumed), q >= 2 after q - 2's
+    // the quadrant's own buffer: its previous slice must have been consumed (weight-gradient MMAs + bias-gradient pass)
     const int i = it * NL + (NL - 1 - L);                    // this quadrant's fill count = phase index of its barriers
-    if (q >= 2) mbar_wait_spin(&freeb[q ^ 2], (uint32_t)(i & 1));
-    else if (i > 0) mbar_wait_spin(&freeb[q ^ 2], (uint32_t)((i - 1) & 1));
-    uint8_t* buf = smem_raw + BwdSmem<TB>::STAGE + (uint32_t)(q & 1) * 2u * SUB_BYTES;
+    if (i > 0) mbar_wait_spin(&freeb[q], (uint32_t)((i - 1) & 1));
+    HB(1)
+    uint8_t* buf = smem_raw + (q < 2 ? BwdSmem<TB>::STAGE + (uint32_t)q * 2u * SUB_BYTES : BwdSmem<TB>::RELOAD_LO + (uint32_t)(q - 2) * 2u * SUB_BYTES);
 #pragma unroll
     for (int c = 0; c < NLOC; ++c) stage_put(buf + S::GZ_HI, buf + S::GZ_LO, c0 + c, lane_off, ghi[c], glo[c]);
+    HB(2)
     if constexpr (L == 0) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
@@ -698,9 +714,12 @@ __device__ __forceinline__ void bwd_handoff(uint8_t* smem_raw, uint32_t t_lane, 
             }
         }
     }
+    HB(3)
     fence_async_smem();                                      // generic-proxy writes -> the MMAs' async-proxy reads
     __syncwarp();
     if (lane == 0) mbar_arrive(&full[q]);
+    HB(4)
+#undef HB
 }
 
 struct BwdArgs {
@@ -732,9 +751,11 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
     uint64_t* w_ready = bars + 2;        // weight image landed
     uint64_t* full = bars + 3;           // [4] staging sub-buffer written (count 2: the two column halves of a quadrant)
     uint64_t* freeb = bars + 7;          // [4] staging sub-buffer consumed (count 2: weight-gradient MMAs + bias-gradient reader)
-    uint64_t* dw_ready = bars + 11;      // weight-gradient issuer -> flush warps: the layer's accumulator is complete
-    uint64_t* dw_free = bars + 12;       // flush warps -> weight-gradient issuer (count 4)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* flushed = bars + 11;       // flush warps -> chain warps: every accumulator of the tile has been read (count 4), once per tile
+    uint64_t* dw_ready = bars + 16;      // [4] ring: weight-gradient issuer -> flush warps: the layer's accumulator is complete (the
+                                         // issuer may run two layers ahead of a flush warp; a parity wait cannot tell phase k from k + 2)
+    uint64_t* w_reload = bars + 13;      // the forward-weight bytes the staging of quadrants 2, 3 overwrote are back (once per tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -743,7 +764,8 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
     if (threadIdx.x == 0) {
         mbar_init(a_ready, BWD_CHAIN_WARPS); mbar_init(d_ready, 1); mbar_init(w_ready, 1);
         for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 2); mbar_init(&freeb[i], 2); }
-        mbar_init(dw_ready, 1); mbar_init(dw_free, 4);
+        for (int i = 0; i < 4; ++i) mbar_init(&dw_ready[i], 1);
+        mbar_init(flushed, 4); mbar_init(w_reload, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint8_t* img = reinterpret_cast<const uint8_t*>(a.image + (long)ae * IMGF);
         constexpr uint32_t WB = 8u * TB::wfloats, TBY = 8u * TB::tfloats + 4u * ((TB::bfloats + 255) / 256 * 256);
@@ -766,7 +788,9 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
         // ======================= chain MMAs: forward layers 0..8, then data gradients of layers 8..0 =======================
         mbar_wait_spin(w_ready, 0);
         uint32_t ph = 0;
-        for (int tile = slot; tile < ntiles; tile += nslot) {
+        int it = 0;
+        for (int tile = slot; tile < ntiles; tile += nslot, ++it) {
+            if (it > 0) mbar_wait_spin(w_reload, (uint32_t)((it - 1) & 1));
 #define ST_CH(CALL) mbar_wait_spin(a_ready, ph); ph ^= 1; tc_fence_after(); CALL; umma_commit_elect(d_ready);
             ST_CH((issue_refwd_layer<TB, 0>(dlo_base))) ST_CH((issue_refwd_layer<TB, 1>(dlo_base))) ST_CH((issue_refwd_layer<TB, 2>(dlo_base)))
             ST_CH((issue_refwd_layer<TB, 3>(dlo_base))) ST_CH((issue_refwd_layer<TB, 4>(dlo_base))) ST_CH((issue_refwd_layer<TB, 5>(dlo_base)))
@@ -786,12 +810,23 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
             issue_wgrad_slice<TB, L, Q>(dlo_base);                                                          \
             umma_commit_elect(&freeb[Q]);
 #define ST_WL(L)                                                                                            \
-            mbar_wait_spin(dw_free, (uint32_t)(nl & 1) ^ 1u);                                               \
-            tc_fence_after();                                                                               \
             ST_WQ(L, 0) ST_WQ(L, 1) ST_WQ(L, 2) ST_WQ(L, 3)                                                 \
-            umma_commit_elect(dw_ready);                                                                    \
+            umma_commit_elect(&dw_ready[nl & 3]);                                                           \
             ++nl;
             ST_WL(8) ST_WL(7) ST_WL(6) ST_WL(5) ST_WL(4) ST_WL(3) ST_WL(2) ST_WL(1) ST_WL(0)
+            if (tile + nslot < ntiles) {
+                // the last slices of quadrants 2 and 3 have been consumed: put the forward weights they overwrote back
+                mbar_wait_spin(&freeb[2], (uint32_t)((nl - 1) & 1));
+                mbar_wait_spin(&freeb[3], (uint32_t)((nl - 1) & 1));
+                fence_async_smem();
+                if (lane == 0) {
+                    const uint8_t* img = reinterpret_cast<const uint8_t*>(a.image + (long)ae * IMGF);
+                    mbar_expect_tx(w_reload, SM::RELOAD_BYTES);
+                    bulk_g2s(smem_raw + SM::RELOAD_LO, img + SM::RELOAD_LO, SM::RELOAD_BYTES / 2, w_reload);
+                    bulk_g2s(smem_raw + SM::RELOAD_LO + SM::RELOAD_BYTES / 2, img + SM::RELOAD_LO + SM::RELOAD_BYTES / 2, SM::RELOAD_BYTES / 2, w_reload);
+                }
+                __syncwarp();
+            }
 #undef ST_WL
 #undef ST_WQ
         }
@@ -799,7 +834,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
         // ======================= flush warps: accumulate D_w into registers, bias gradients from the staged gz ================
         const int q = warp & 3;
         const int glane = 32 * q + lane;                     // TMEM lane = feature row of the M operand (+ its lane offset)
-        const uint32_t t_dw = ((uint32_t)(32 * q) << 16) + TC_DW;
+        const uint32_t t_lq = (uint32_t)(32 * q) << 16;
         float acc[80];
         float dbacc[11];
 #pragma unroll
@@ -812,7 +847,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
             {                                                                                                          \
                 using S = Stg<TB, L>;                                                                                  \
                 mbar_wait_spin(&full[q], (uint32_t)(nl & 1));                                                          \
-                const uint8_t* gb = smem_raw + SM::STAGE + (uint32_t)(q & 1) * 2u * SUB_BYTES;                         \
+                const uint8_t* gb = smem_raw + (q < 2 ? SM::STAGE + (uint32_t)q * 2u * SUB_BYTES : SM::RELOAD_LO + (uint32_t)(q - 2) * 2u * SUB_BYTES); \
                 _Pragma("unroll")                                                                                      \
                 for (int p = 0; p < (TB::n(L) + 31) / 32; ++p) {                                                       \
                     const int f = 32 * p + lane;                                                                       \
@@ -830,12 +865,12 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 }                                                                                                      \
                 __syncwarp();                                                                                          \
                 if (lane == 0) mbar_arrive(&freeb[q]);                                                                 \
-                mbar_wait_spin(dw_ready, (uint32_t)(nl & 1));                                                          \
+                mbar_wait_spin(&dw_ready[nl & 3], (uint32_t)(nl >> 2) & 1u);                                           \
                 tc_fence_after();                                                                                      \
                 constexpr int MO = TB::wg_moff(L), MF = S::MF, NF = S::NF, RG = TB::wg_reg(L);                         \
                 if (32 * q < MO + MF && 32 * q + 32 > MO) {                                                            \
                     uint32_t v[NF];                                                                                    \
-                    tmem_ld<NF>(t_dw, v);                                                                              \
+                    tmem_ld<NF>(t_lq + tc_dw(L), v);                                                                   \
                     tmem_wait_ld();                                                                                    \
                     if (glane >= MO && glane < MO + MF) {                                                              \
                         _Pragma("unroll")                                                                              \
@@ -843,12 +878,12 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                     }                                                                                                  \
                 }                                                                                                      \
                 tc_fence_before();                                                                                     \
-                __syncwarp();                                                                                          \
-                if (lane == 0) mbar_arrive(dw_free);                                                                   \
                 ++nl;                                                                                                  \
             }
             ST_FL(8, 10) ST_FL(7, 8) ST_FL(6, 7) ST_FL(5, 6) ST_FL(4, 5) ST_FL(3, 4) ST_FL(2, 3) ST_FL(1, 2) ST_FL(0, 0)
 #undef ST_FL
+            __syncwarp();
+            if (lane == 0) mbar_arrive(flushed);             // the next tile's forward may overwrite the accumulator columns
         }
         // ---- per-CTA partial gradients -> global memory (layout: [W_0, b_0, W_1, b_1, ...] like ae_grad_reduce_kernel reads it)
         float* part = a.partials + ((long)slot * 2 + ae) * g.flat_total;
@@ -899,11 +934,14 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
         int it = 0;
 #ifdef ST_AE_TM_TIMING
         long long tclk = 0, treg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long hbuf[5] = {0, 0, 0, 0, 0};
+        long long* hb = a.timing ? hbuf : nullptr;
 #define BT0() if (a.timing) tclk = clock64();
 #define BT(i) if (a.timing) { const long long n_ = clock64(); treg[i] += n_ - tclk; tclk = n_; }
 #else
 #define BT0()
 #define BT(i)
+        long long* hb = nullptr;
 #endif
         mbar_wait_spin(w_ready, 0);                          // biases
         for (int tile = slot; tile < ntiles; tile += nslot, ++it) {
@@ -938,6 +976,10 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready);
             asm volatile("bar.sync 1, 256;" ::: "memory");   // vtail complete (both halves)
+            if (it > 0) {                                    // the weight-gradient accumulators live in the saved-output columns
+                mbar_wait_spin(flushed, (uint32_t)((it - 1) & 1));
+                tc_fence_after();
+            }
             BT(0)
 
             // ---- forward layers 0..7: h = ELU(D + b) -> raw copy (kept for the backward) + (hi, lo) A operand
@@ -1014,7 +1056,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                     for (int j = 0; j < 8; ++j) mydbg[(long)(NL + 8) * TILE * 64 + j0 + j] = gz[j];
                 }
                 BT(3)
-                bwd_handoff<TB, 8>(smem_raw, t_lane, lane_off, half, q, it, lane, gz, a_ready, full, freeb, vkeep, nullptr, 0, 0);
+                bwd_handoff<TB, 8>(smem_raw, t_lane, lane_off, half, q, it, lane, gz, a_ready, full, freeb, vkeep, nullptr, 0, 0, hb);
                 BT(5)
             }
             // ---- data gradients, layers 8..1: gz[l-1] = gh[l] * ELU'(act[l]); the weight-gradient slice of layer l-1 follows
@@ -1038,7 +1080,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                     for (int c = 0; c < NLOC; ++c) mydbg[(long)(NL + (L) - 1) * TILE * 64 + c0 + c] = gz[c];          \
                 }                                                                                                    \
                 BT(4)                                                                                                \
-                bwd_handoff<TB, (L) - 1>(smem_raw, t_lane, lane_off, half, q, it, lane, gz, a_ready, full, freeb, vkeep, a.knobs, (long)b * d.K, ok ? d.K : 0); \
+                bwd_handoff<TB, (L) - 1>(smem_raw, t_lane, lane_off, half, q, it, lane, gz, a_ready, full, freeb, vkeep, a.knobs, (long)b * d.K, ok ? d.K : 0, hb); \
                 BT(5)                                                                                                \
             }
             ST_BW(8) ST_BW(7) ST_BW(6) ST_BW(5) ST_BW(4) ST_BW(3) ST_BW(2) ST_BW(1)
@@ -1066,7 +1108,10 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
         }
 #ifdef ST_AE_TM_TIMING
         if (a.timing && lane == 0)
+        {
             for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.timing) + 8 * warp + i, (unsigned long long)treg[i]);
+            for (int i = 0; i < 5; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.timing) + 64 + 8 * warp + i, (unsigned long long)hbuf[i]);
+        }
 #endif
 #undef BT0
 #undef BT

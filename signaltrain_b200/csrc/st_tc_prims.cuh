@@ -142,7 +142,20 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
         ::"r"(smem_u32(bar)) : "memory");
 }
-// Spin on an mbarrier phase without reading the clock (a trap after ~2^22 polls: a protocol bug is a launch failure, not a hang).
+// try_wait with a suspend-time hint: the thread may be parked in hardware for up to `ns` nanoseconds (it is woken when the
+// phase completes), so a waiting warp does not burn issue slots of the warps it shares a scheduler with.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok;
+}
+// Wait on an mbarrier phase without reading the clock (a trap after ~2^22 polls: a protocol bug is a launch failure, not a hang).
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {

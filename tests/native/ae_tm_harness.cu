@@ -306,18 +306,20 @@ int main(int argc, char** argv) {
         printf("backward timing: B=%d  %.2f us per launch (both autoencoders, without the track->spec kernel)\n", TB, 1000.f * bms / 20);
         {
             long long* dt2;
-            CK(cudaMalloc(&dt2, 64 * sizeof(long long)));
-            CK(cudaMemset(dt2, 0, 64 * sizeof(long long)));
+            CK(cudaMalloc(&dt2, 128 * sizeof(long long)));
+            CK(cudaMemset(dt2, 0, 128 * sizeof(long long)));
             const int ns = st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, dt2, sm, false, 0, 0);
             CK(cudaDeviceSynchronize());
-            long long ht2[64];
+            long long ht2[128];
             CK(cudaMemcpy(ht2, dt2, sizeof(ht2), cudaMemcpyDeviceToHost));
             const char* names[7] = {"prologue", "wait_d", "fwd_epi", "dec", "bwd_epi", "handoff+stage", "final"};
             printf("backward chain-warp clocks per CTA (%d CTAs):\n", 2 * ns);
             for (int w = 0; w < 8; w += 3) {
                 printf("  warp %d:", w);
                 for (int i = 0; i < 7; ++i) printf(" %s %.0f", names[i], (double)ht2[8 * w + i] / (2 * ns));
-                printf("\n");
+                printf("\n           handoff: tmem %.0f wait_free %.0f gz_sts %.0f act %.0f fence+full %.0f\n", (double)ht2[64 + 8 * w] / (2 * ns),
+                       (double)ht2[64 + 8 * w + 1] / (2 * ns), (double)ht2[64 + 8 * w + 2] / (2 * ns), (double)ht2[64 + 8 * w + 3] / (2 * ns),
+                       (double)ht2[64 + 8 * w + 4] / (2 * ns));
             }
         }
     }

@@ -420,11 +420,12 @@ def test_fused_step_tail_matches_the_piecewise_entry_points(case):
         assert (a - b).abs().max().item() <= (8e-9 if i < 4 else 0.0), (i, (a - b).abs().max().item())   # DFT: <= 2 ulp of 0.034
 
 
-@pytest.mark.parametrize("B", [12, 37])
+@pytest.mark.parametrize("B", [12, 37, 200])
 def test_whole_step_vs_oracle_at_batches_that_use_pair_tiles(B):
     """The golden cases hold 2-3 windows (one 128-row tile: the 1-CTA GEMM kernel serves the forward there).  At B = 12 / 37 the
     forward GEMMs run on cta_group::2 tiles (324 / 999 frame rows = 3 / 8 tiles, i.e. a half-empty last pair / exact pairs), and
-    the fused step tail sees a ragged batch.  Forward, loss and all 40 gradients (st_grad_step) against the float64 oracle."""
+    the fused step tail sees a ragged batch; B = 200 is the bench size (BASELINE configs[1]: every SM busy, 5-6 autoencoder tiles per
+    CTA in the forward and 10-11 in the backward).  Forward, loss and all 40 gradients (st_grad_step) against the float64 oracle."""
     d = O.model_dims(1, 4, 4)
     P = O.init_params(d, seed=218)
     rng = np.random.RandomState(B)

@@ -113,3 +113,99 @@ def test_lrfind_runs_the_train_step_through_the_module_api():
     lrs, losses = lrfind(model, batches, opt, st.loss_functions.calc_loss, start=1e-6, stop=1e-3, num_lrs=3)
     assert len(lrs) == len(losses) == 9 and lrs[0] == lrs[2] and lrs[3] > lrs[2] and np.isclose(lrs[-1], 1e-3)
     assert np.isfinite(losses).all() and len(set(losses)) > 1
+
+
+def test_resume_restores_the_adam_step_count():
+    """N + M steps in one run == N steps, checkpoint (model + optimizer state_dict), fresh objects, load, M more steps:
+    bias correction continues from step N (optim.Adam.load_state_dict), so parameters agree bit for bit."""
+    import signaltrain_b200 as st
+    from signaltrain_b200.train import FusedTrainer
+    lr, _ = st.learningrate.get_1cycle_schedule(1e-4, 200000, 1000, 200)
+    pool = st.data.make_pool(6 * 5, 8192, 2048, st.data.Compressor_4c(), 44100, seed=21)
+    batches = [tuple(torch.from_numpy(a[i * 5:(i + 1) * 5]).cuda() for a in pool) for i in range(6)]
+    N, M = 4, 2
+
+    def fresh():
+        torch.manual_seed(218)
+        model = st.nn_proc.st_model(1, 4, 4).cuda()
+        return model, st.optim.Adam(model, lr=float(lr[0]))
+
+    model_a, opt_a = fresh()
+    tr_a = FusedTrainer(model_a, lr, optimizer=opt_a)
+    for b in batches[:N + M]:
+        tr_a.step(*b)
+    model_b, opt_b = fresh()
+    tr_b = FusedTrainer(model_b, lr, optimizer=opt_b)
+    for b in batches[:N]:
+        tr_b.step(*b)
+    tr_b.sync_optimizer_state()
+    sd_model = {k: v.clone() for k, v in model_b.state_dict().items()}
+    sd_opt = opt_b.state_dict()
+    assert int(sd_opt["state"][0]["step"]) == N
+    model_c, opt_c = fresh()
+    model_c.load_state_dict(sd_model)
+    opt_c.load_state_dict(sd_opt)
+    assert opt_c._step == N
+    tr_c = FusedTrainer(model_c, lr, optimizer=opt_c)
+    tr_c.iter_count, tr_c.lr = tr_b.iter_count, tr_b.lr            # the schedule position is the caller's to restore
+    opt_c.param_groups[0]["lr"] = tr_b.lr
+    for b in batches[N:N + M]:
+        tr_c.step(*b)
+    torch.cuda.synchronize()
+    for pa, pc in zip(model_a.parameters(), model_c.parameters()):
+        assert torch.equal(pa, pc)
+
+
+def test_eval_forward_between_steps_keeps_the_fast_path():
+    """A no_grad validation forward (eval_status_save, predict_long) flips the engine to inference mode; the next train
+    step must still run the tensor-core autoencoder kernels (no SIMT fallback) with the same number of launches."""
+    import signaltrain_b200 as st
+    from signaltrain_b200.train import FusedTrainer
+    lr, _ = st.learningrate.get_1cycle_schedule(1e-4, 200000, 1000, 200)
+    torch.manual_seed(218)
+    model = st.nn_proc.st_model(1, 4, 4).cuda()
+    tr = FusedTrainer(model, lr)
+    pool = st.data.make_pool(8, 8192, 2048, st.data.Compressor_4c(), 44100, seed=5)
+    x, y, k = (torch.from_numpy(a).cuda() for a in pool)
+    tr.step(x, y, k)
+    eng = tr.eng
+    n0 = eng.launch_count()
+    tr.step(x, y, k)
+    per_step = eng.launch_count() - n0
+    with torch.no_grad():
+        model.eval()
+        model.forward(x, k)
+        model.train()
+    n1, f1 = eng.launch_count(), eng.fallback_count()
+    tr.step(x, y, k)
+    assert eng.launch_count() - n1 == per_step and eng.fallback_count() == f1 == 0
+
+
+def test_lrfind_at_scale_factor_2():
+    """utils/lr_finder.py:38 passes the INPUT magnitude (B, T, F) as mag_hat; at chunk 16384 (T = 46) that is not a geometry a
+    handle could be built from -- calc_loss takes its sizes from the tensors (st_loss_shaped)."""
+    import signaltrain_b200 as st
+    from signaltrain_b200.lr_finder import lrfind
+    torch.manual_seed(218)
+    model = st.nn_proc.st_model(2, 4, 2).cuda()
+    opt = st.optim.Adam(model, lr=1e-6)
+    pool = st.data.make_pool(2 * 6, model.in_chunk_size, model.out_chunk_size, st.data.Compressor_2knob(), 44100, seed=13)
+    batches = [tuple(torch.from_numpy(a[i * 2:(i + 1) * 2]) for a in pool) for i in range(6)]
+    lrs, losses = lrfind(model, batches, opt, st.loss_functions.calc_loss, start=1e-6, stop=1e-4, num_lrs=2)
+    assert len(losses) == 6 and np.isfinite(losses).all()
+
+
+def test_library_calls_leave_the_current_device_alone():
+    """Every C-ABI entry point runs on the handle's device and restores the caller's current device (DeviceGuard)."""
+    import signaltrain_b200 as st
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.manual_seed(218)
+    model = st.nn_proc.st_model(1, 4, 4).to("cuda:1")
+    torch.cuda.set_device(0)
+    x = torch.randn(2, model.in_chunk_size, device="cuda:1") * 0.1
+    k = torch.zeros(2, 4, device="cuda:1")
+    with torch.no_grad():
+        model.forward(x, k)
+    assert torch.cuda.current_device() == 0
+    assert float(st.loss_functions.mae(x, x)) == 0.0 and torch.cuda.current_device() == 0
