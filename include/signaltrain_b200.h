@@ -186,6 +186,16 @@ int st_grad_step(st_handle* h, const float* x, const float* y, const float* knob
                  float* const* params, float* const* grads, const float* scale_by_freq, float l1_coef,
                  float* loss, void* stream);
 
+/* Data-parallel exchange payload.  Of the 16.8 MB of gradients only 8.5 MB carry information: analysis rows >= F never
+ * receive gradient (cls_fe_dft.py:55-56) and the synthesis gradients are Hermitian (cls_fe_dft.py:109-110).
+ * st_pack_grads gathers [Wr rows < F | Wi rows < F | Sr rows < F | Si rows < F | the 36 autoencoder tensors] into one
+ * contiguous buffer of st_packed_grad_floats() floats (ONE collective covers it); st_unpack_grads scatters the reduced
+ * buffer back and restores the mirrored synthesis rows, so all 40 gradient tensors are exactly what reducing them in
+ * full would have given. */
+long st_packed_grad_floats(const st_handle* h);
+int st_pack_grads(st_handle* h, float* const* grads, float* packed, void* stream);
+int st_unpack_grads(st_handle* h, const float* packed, float* const* grads, void* stream);
+
 /* Measurement support (bench.py): number of kernels / device copies this handle has launched, and per-stage
  * device time bracketed with CUDA events on the launching stream.  st_profile_read synchronises the device,
  * fills ms[i] / calls[i] for i < st_profile_stage_count() with the totals since the previous read, and resets. */

@@ -73,6 +73,9 @@ _SIGNATURES = {
     "st_profile_stage_name": (ctypes.c_char_p, [ctypes.c_int]),
     "st_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "st_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_long)]),
+    "st_packed_grad_floats": (ctypes.c_long, [ctypes.c_void_p]),
+    "st_pack_grads": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_float_p, ctypes.c_void_p]),
+    "st_unpack_grads": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
     "st_debug_fallbacks": (ctypes.c_long, [ctypes.c_void_p]),
     "st_debug_ae_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]),
     "st_debug_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, c_float_p, ctypes.c_long,

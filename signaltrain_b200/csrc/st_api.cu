@@ -863,6 +863,46 @@ extern "C" int st_grad_step(st_handle* h, const float* x, const float* y, const 
     return grad_step_impl(h, x, y, knobs, batch, params, grads, sbf, l1_coef, loss, (cudaStream_t)stream, nullptr);
 }
 
+static long packed_grad_floats(const st_handle* h, int* ae_off) {
+    long n = 4L * h->d.F * h->d.N;
+    long o = 0;
+    for (int t = 4; t < ST_NUM_PARAMS; ++t) {
+        if (ae_off) ae_off[t - 4] = (int)o;
+        o += (h->numel[t] + 3) / 4 * 4;
+    }
+    return n + o;
+}
+
+extern "C" long st_packed_grad_floats(const st_handle* h) { return h ? packed_grad_floats(h, nullptr) : -1; }
+
+static int pack_impl(st_handle* h, float* const* grads, float* packed, int dir, cudaStream_t s) {
+    if (check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_pack_grads(grads)")) return 1;
+    if (!packed) return st_fail_msg(h, "st_pack_grads: null packed buffer");
+    GradPack gp;
+    for (int t = 0; t < ST_NUM_PARAMS; ++t) gp.g[t] = grads[t];
+    gp.packed = packed;
+    gp.live = (long)h->d.F * h->d.N;
+    gp.N = h->d.N;
+    packed_grad_floats(h, gp.ae_off);
+    for (int t = 4; t < ST_NUM_PARAMS; ++t) gp.ae_n[t - 4] = (int)h->numel[t];
+    st_launch_pack_grads(gp, dir, s);
+    h->launches += 1;
+    ST_LAUNCH_OK(h);
+    return 0;
+}
+
+extern "C" int st_pack_grads(st_handle* h, float* const* grads, float* packed, void* stream) {
+    if (!h) return 1;
+    ST_ON_DEVICE(h);
+    return pack_impl(h, grads, packed, 0, (cudaStream_t)stream);
+}
+
+extern "C" int st_unpack_grads(st_handle* h, const float* packed, float* const* grads, void* stream) {
+    if (!h) return 1;
+    ST_ON_DEVICE(h);
+    return pack_impl(h, grads, const_cast<float*>(packed), 1, (cudaStream_t)stream);
+}
+
 extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch,
                              float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                              const float* sbf, float l1_coef, const st_adam* hp, float* loss, void* stream) {

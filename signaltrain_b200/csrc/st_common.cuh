@@ -194,6 +194,17 @@ void st_launch_l1_norm4(const float* const g[4], long n_each, long live_rows_a, 
                         float max_norm, float* norm_out, float* coef_out, float* scratch, unsigned* counter, cudaStream_t s);
 void st_launch_scale4(float* const g[4], long n_each, const float* coef, cudaStream_t s);
 
+// data-parallel exchange payload (st_pack_grads / st_unpack_grads)
+struct GradPack {
+    float* g[ST_NUM_PARAMS];
+    float* packed;
+    long live;                   // F * N
+    int N;
+    int ae_off[ST_NUM_PARAMS - 4];
+    int ae_n[ST_NUM_PARAMS - 4];
+};
+void st_launch_pack_grads(const GradPack& gp, int dir, cudaStream_t s);
+
 struct AdamTensors {
     float* p[ST_NUM_PARAMS];
     const float* g[ST_NUM_PARAMS];

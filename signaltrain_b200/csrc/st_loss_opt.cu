@@ -383,6 +383,46 @@ void st_launch_scale4(float* const g[4], long n_each, const float* coef, cudaStr
     dim3 grid(148 * 2, 4);
     scale4_kernel<<<grid, 256, 0, s>>>(p, n_each, coef);
 }
+// Data-parallel exchange payload: only what carries information travels.  Packed layout:
+//   [Wr rows 0..F-1 | Wi rows 0..F-1 | Sr rows 0..F-1 | Si rows 0..F-1 | the 36 autoencoder tensors, 4-float aligned]
+// Analysis rows >= F never receive gradient (cls_fe_dft.py:55-56) and the synthesis gradients are Hermitian
+// (g_r[N-k] = g_r[k], g_i[N-k] = -g_i[k], cls_fe_dft.py:109-110), so unpacking restores all four full tensors exactly.
+__global__ void __launch_bounds__(256)
+pack_grads_kernel(GradPack gp, int dir /*0: pack, 1: unpack*/) {
+    const long live4 = gp.live / 4;                          // float4 items of one live block (F * N)
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < 4 * live4; i += stride) {
+        const int t = (int)(i / live4);
+        const long e = i - t * live4;
+        float4* full = reinterpret_cast<float4*>(gp.g[t]) + e;
+        float4* pk = reinterpret_cast<float4*>(gp.packed + t * gp.live) + e;
+        if (dir == 0) {
+            *pk = *full;
+        } else {
+            const float4 v = *pk;
+            *full = v;
+            if (t >= 2) {                                    // synthesis: mirror rows 1..N/2-1 onto rows N-1..N/2+1
+                const long row = (e * 4) / gp.N, col4 = e - row * (gp.N / 4);
+                if (row >= 1 && row < gp.N / 2) {
+                    float4* m = reinterpret_cast<float4*>(gp.g[t]) + (gp.N - row) * (gp.N / 4) + col4;
+                    *m = t == 2 ? v : make_float4(-v.x, -v.y, -v.z, -v.w);
+                }
+            }
+        }
+    }
+    // autoencoder tensors: one block per tensor slice
+    for (int t = 4 + blockIdx.x; t < ST_NUM_PARAMS; t += gridDim.x) {
+        float* full = gp.g[t];
+        float* pk = gp.packed + 4 * gp.live + gp.ae_off[t - 4];
+        for (int e = threadIdx.x; e < gp.ae_n[t - 4]; e += blockDim.x) {
+            if (dir == 0) pk[e] = full[e];
+            else full[e] = pk[e];
+        }
+    }
+}
+
+void st_launch_pack_grads(const GradPack& gp, int dir, cudaStream_t s) { pack_grads_kernel<<<148 * 4, 256, 0, s>>>(gp, dir); }
+
 void st_launch_adam(const AdamTensors& t, const int2* chunk_map, int nchunks, const AdamScalars& sc, const float* clip_coef,
                     cudaStream_t s) {
     adam_kernel<<<nchunks, 256, 0, s>>>(t, chunk_map, sc, clip_coef);

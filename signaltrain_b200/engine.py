@@ -328,6 +328,19 @@ class Engine:
                  "st_grad_step")
         return loss
 
+    def packed_grad_floats(self):
+        return int(self.lib.st_packed_grad_floats(self.h))
+
+    def pack_grads(self, grads, packed):
+        """The data-parallel exchange payload (8.5 of 16.8 MB: live analysis rows, Hermitian half of the synthesis pair, the
+        autoencoders) gathered into one contiguous buffer -- one collective reduces it."""
+        _check(packed, "packed", (self.packed_grad_floats(),), self.device)
+        self._ok(self.lib.st_pack_grads(self.h, self.table(grads, "grads"), _ptr(packed), self._stream()), "st_pack_grads")
+
+    def unpack_grads(self, packed, grads):
+        _check(packed, "packed", (self.packed_grad_floats(),), self.device)
+        self._ok(self.lib.st_unpack_grads(self.h, _ptr(packed), self.table(grads, "grads"), self._stream()), "st_unpack_grads")
+
     def launch_count(self):
         return int(self.lib.st_launch_count(self.h))
 

@@ -80,6 +80,31 @@ class GradReducer:
         return 1.0 / w
 
 
+def pack_payload(views, F):
+    """Host-side statement of the packed exchange payload (the CUDA path builds it with st_pack_grads): the first F rows of the
+    four DFT tensors -- analysis rows >= F never receive gradient, the synthesis pair is Hermitian -- and the autoencoder
+    tensors, concatenated.  Works on any device; used by the CPU tests of the exchange logic."""
+    parts = [v.reshape(v.shape[0], -1)[:F].reshape(-1) for v in views[:4]] + [v.reshape(-1) for v in views[4:]]
+    return torch.cat(parts)
+
+
+def unpack_payload(packed, views, F):
+    """Inverse of pack_payload: scatters the (reduced) payload back and restores the mirrored synthesis rows
+    (g_r[N-k] = g_r[k], g_i[N-k] = -g_i[k], cls_fe_dft.py:109-110).  Analysis rows >= F are left untouched (they are zero)."""
+    o = 0
+    for t, v in enumerate(views[:4]):
+        m = v.reshape(v.shape[0], -1)
+        N = m.shape[0]
+        m[:F].copy_(packed[o:o + F * m.shape[1]].view(F, -1))
+        o += F * m.shape[1]
+        if t >= 2:
+            mirror = m[1:N // 2].flip(0)
+            m[N // 2 + 1:].copy_(mirror if t == 2 else -mirror)
+    for v in views[4:]:
+        v.reshape(-1).copy_(packed[o:o + v.numel()])
+        o += v.numel()
+
+
 def shard_range(n_items, rank, world):
     """Contiguous shard [lo, hi) of n_items windows for `rank` (earlier ranks take the remainder)."""
     base, rem = divmod(n_items, world)

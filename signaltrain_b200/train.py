@@ -67,7 +67,7 @@ class FusedTrainer:
             eng.train_step(x, y, knobs, self.params, self.grads, self.m, self.v, self.sbf, self.l1_lambda / 10, hp,
                            loss_out=self.loss_buf)
         else:
-            mode = os.environ.get("ST_DP_EXCHANGE", "whole")
+            mode = os.environ.get("ST_DP_EXCHANGE", "packed")
             if mode in ("overlap", "sliced"):
                 y_hat, _, mag_hat, _ = eng.forward(x, knobs, self.params)
                 loss, g_y, g_m = eng.loss(y_hat, y, mag_hat, self.sbf, self.l1_lambda / 10)
@@ -82,7 +82,15 @@ class FusedTrainer:
                 eng.backward(g_y, None, g_m, self.params, self.grads)
                 self.reducer.start_synthesis()
                 scale = self.reducer.finish()
-            else:                                 # default: st_grad_step (forward + fused loss tail + backward in one call),
+            elif mode == "packed":                # default: st_grad_step, then ONE allreduce of the packed payload (8.5 MB: analysis
+                # rows >= F are zero and the synthesis pair is Hermitian), scattered back by st_unpack_grads
+                loss = eng.grad_step(x, y, knobs, self.params, self.grads, self.sbf, self.l1_lambda / 10, loss_out=self.loss_buf)
+                if getattr(self, "_packed", None) is None:
+                    self._packed = torch.empty(eng.packed_grad_floats(), device=self.device, dtype=torch.float32)
+                eng.pack_grads(self.grads, self._packed)
+                scale = parallel.allreduce_sum_(self._packed, self.pg)
+                eng.unpack_grads(self._packed, self.grads)
+            else:                                 # "whole": st_grad_step (forward + fused loss tail + backward in one call),
                 # then ONE allreduce of the whole flat buffer (16.8 MB).  Measured on 2 B200s (ms/step, v7): whole 1.011,
                 # sliced 1.056, overlap 1.060 -- at this size NCCL is launch / latency bound, so four smaller collectives
                 # cost more than the 25 % of payload they save, and the overlapped one cannot get SMs while the

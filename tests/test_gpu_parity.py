@@ -448,3 +448,39 @@ def test_whole_step_vs_oracle_at_batches_that_use_pair_tiles(B):
         got, ref = gt.cpu().numpy(), ref_grads[name]
         assert np.isfinite(got).all(), name
         assert np.abs(got - ref).max() <= GRAD_RTOL * np.abs(ref).max() + 1e-12, (name, np.abs(got - ref).max() / np.abs(ref).max())
+
+
+def test_packed_exchange_payload_roundtrip():
+    """st_pack_grads / st_unpack_grads (the data-parallel exchange payload: 8.5 of 16.8 MB): the packed buffer equals the
+    host-side statement of the layout (parallel.pack_payload), and unpacking restores all 40 gradient tensors BIT-exactly --
+    analysis rows >= F are exactly zero and the synthesis gradients exactly Hermitian after a real backward."""
+    from signaltrain_b200 import parallel
+    d = O.model_dims(1, 4, 4)
+    eng = _engine(d)
+    P = O.init_params(d, seed=5)
+    rng = np.random.RandomState(3)
+    B = 7
+    x = (0.3 * rng.standard_normal((B, d.C))).astype(np.float32)
+    knobs = (rng.beta(0.8, 0.8, (B, d.K)) - 0.5).astype(np.float32)
+    y = np.tanh(x[:, -d.L:]).astype(np.float32)
+    params = _dev_params(P, d)
+    grads = [torch.full_like(p, float("nan")) for p in params]
+    eng.grad_step(_t(x), _t(y), _t(knobs), params, grads, _t(O.scale_by_freq(d.F)), 2e-6)
+    packed = torch.empty(eng.packed_grad_floats(), device="cuda")
+    eng.pack_grads(grads, packed)
+    ref = parallel.pack_payload(grads, d.F)
+    n_dft = 4 * d.F * d.N
+    assert torch.equal(packed[:n_dft], ref[:n_dft])
+    o_lib, o_ref = n_dft, n_dft                                   # the library aligns every autoencoder tensor to 4 floats
+    for g_ in grads[4:]:
+        assert torch.equal(packed[o_lib:o_lib + g_.numel()], ref[o_ref:o_ref + g_.numel()])
+        o_lib += (g_.numel() + 3) // 4 * 4
+        o_ref += g_.numel()
+    assert o_lib == packed.numel()
+    restored = [torch.full_like(g_, float("nan")) for g_ in grads]
+    for r_, g_ in zip(restored[:2], grads[:2]):
+        r_.view(d.N, -1)[d.F:] = 0.0                              # dead analysis rows are not part of the payload: left untouched
+    eng.unpack_grads(packed, restored)
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(grads, restored)):
+        assert torch.equal(a, b), i

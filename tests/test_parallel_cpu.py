@@ -43,8 +43,18 @@ def _worker(rank, world, port, q):
     red = parallel.GradReducer(fb2, shapes, d.F)
     red.start_synthesis()
     scale2 = red.finish()
+    # the packed exchange (default on the GPU path): one collective over 8.5 MB instead of 16.8 MB
+    fb3 = parallel.FlatBuffer(shapes, "cpu")
+    fb3.flat.copy_(fb.flat)
+    packed = parallel.pack_payload(fb3.views, d.F)
+    assert packed.numel() == 4 * d.F * d.N + sum(int(np.prod(s)) for s in shapes[4:])
+    scale3 = parallel.allreduce_sum_(packed)
+    parallel.unpack_payload(packed, fb3.views, d.F)
     scale = parallel.allreduce_sum_(fb.flat)
     assert scale2 == scale and torch.equal(fb.flat, fb2.flat), "sliced allreduce differs from the whole-buffer allreduce"
+    assert scale3 == scale
+    for a_, b_ in zip(fb.views, fb3.views):   # Hermitian symmetry of the oracle's float64 gradients holds to rounding
+        assert (a_ - b_).abs().max().item() <= 1e-6 * max(a_.abs().max().item(), 1e-30), "packed exchange differs from the whole-buffer one"
     avg = {name: v.numpy().astype(np.float64) * scale for v, (name, _) in zip(fb.views, O.param_order(d))}
     total = O.clip_grad_norm_(avg)
     Pn = O.adam_step({n: a.astype(np.float64) for n, a in P.items()}, avg, {}, 1e-4 / 15)
