@@ -56,12 +56,15 @@ struct Tab {
     __host__ __device__ static constexpr bool wg_m_is_gz(int l) { constexpr bool t[NL] = {true, false, false, true, false, true, true, true, false}; return t[l]; }
     __host__ __device__ static constexpr int wg_mf(int l) { return wg_m_is_gz(l) ? n(l) : act_w(l); }
     __host__ __device__ static constexpr int wg_nf(int l) { return wg_m_is_gz(l) ? (act_w(l) + 15) / 16 * 16 : n(l); }
-    __host__ __device__ static constexpr int wg_moff(int l) { constexpr int t[NL] = {0, 0, 64, 0, 32, 16, 96, 64, 64}; return t[l]; }
-    __host__ __device__ static constexpr int wg_reg(int l) { constexpr int t[NL] = {0, 32, 48, 64, 64, 64, 48, 0, 32}; return t[l]; }
-    __host__ __device__ static constexpr bool wg_wide(int l) { return (wg_mf(l) + wg_nf(l)) * 256 > 12288; }     // slice needs two 12 KB sub-buffers
-    // sub-buffer uses (per tile) before layer l's, layers being processed 8, 7, ..., 0: wide layers use every sub-buffer twice
-    __host__ __device__ static constexpr int wg_uses_before(int l) { int c = 0; for (int i = NL - 1; i > l; --i) c += wg_wide(i) ? 2 : 1; return c; }
-    static constexpr int wg_uses_per_tile = wg_uses_before(-1);
+    // One MMA per 8-row k-step covers every product the split needs, because an SS-mode MMA of this size is bound by the 128-row
+    // A tile it reads, not by N: the N operand is the stacked [N_hi ; N_lo] planes (2 NF columns: D[:, 0:NF] = m . n_hi,
+    // D[:, NF:2NF] = m . n_lo), and where 2 MF <= 64 the A tile is the stacked [M_hi ; M_lo] planes as well (wg_one: the lo
+    // feature rows come out MF lanes below the hi rows and are folded in when the kernel ends); the wide layers run a second
+    // MMA (A = M_lo, B = N_hi) into the first NF columns instead.
+    __host__ __device__ static constexpr bool wg_one(int l) { constexpr bool t[NL] = {false, false, true, true, true, true, true, false, false}; return t[l]; }
+    __host__ __device__ static constexpr int wg_moff(int l) { constexpr int t[NL] = {0, 0, 64, 0, 0, 32, 64, 64, 64}; return t[l]; }   // first live TMEM lane
+    __host__ __device__ static constexpr int wg_reg(int l) { constexpr int t[NL] = {0, 32, 48, 64, 80, 64, 64, 0, 32}; return t[l]; }  // first flush register
+    static constexpr int wg_regs = 96;
 };
 
 __device__ __forceinline__ float elu_f(float z) {
@@ -89,6 +92,7 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
     if (x < 0.f) r = 3.14159265358979323846f - r;
     return copysignf(r, y);
 }
+__device__ __noinline__ float atan2_ni(float y, float x) { return atan2_fast(y, x); }
 __device__ __noinline__ float2 sincos_ni(float x) {
     float s, c;
     sincosf(x, &s, &c);
@@ -549,10 +553,11 @@ constexpr int SUB_BYTES = 12288;                    // staging sub-buffer: 48 fe
 // TMEM columns
 constexpr uint32_t TC_AH = 256, TC_AL = 320, TC_D = 384, TC_DW = 448;
 __host__ __device__ constexpr uint32_t tc_act(int l) { constexpr uint32_t t[NL] = {0, 0, 64, 96, 112, 128, 144, 160, 192}; return t[l]; }   // act[1..8]
-// Accumulator columns of layer L's weight gradient: the saved output of layer L (act[L + 1]) is dead once every quadrant has
-// staged layer L + 1 -- which the issuer has waited for before it starts layer L -- so every layer has its own columns and the
-// issuer never waits for a flush inside a tile.  Layer 8 uses the spare columns.
-__host__ __device__ constexpr uint32_t tc_dw(int l) { return l == NL - 1 ? TC_DW : tc_act(l + 1); }
+// Accumulator columns of layer L's weight gradient (2 NF columns).  A layer may only use columns that are dead in EVERY quadrant
+// when its first MMA (which overwrites all 128 lanes) is issued, i.e. after the issuer has seen all of layer L + 1 staged: the
+// saved outputs act[j], j >= L + 1 (their last readers ran before the layer-(L + 1) slices were signalled), the spare columns, and
+// accumulators of layers >= L + 3 (a flush warp lags the issuer by at most two layers).
+__host__ __device__ constexpr uint32_t tc_dw(int l) { constexpr uint32_t t[NL] = {128, 192, 96, 448, 128, 480, 160, 192, 448}; return t[l]; }
 
 template <class TB>
 struct BwdSmem {
@@ -561,6 +566,7 @@ struct BwdSmem {
     static constexpr uint32_t VTAIL = BIAS + 4u * ((TB::bfloats + 255) / 256 * 256);
     static constexpr uint32_t BARS = VTAIL + 4u * XCH_J * TILE;
     static constexpr uint32_t TOTAL = BARS + 256;
+    static_assert(TOTAL <= 227u * 1024u, "backward tile does not fit shared memory");
     static constexpr uint32_t RELOAD_LO = 16384, RELOAD_BYTES = 4u * SUB_BYTES;     // forward-weight bytes clobbered by staging (quadrants 2, 3)
     static_assert(RELOAD_LO + RELOAD_BYTES <= STAGE, "the aliased staging buffers must lie inside the forward weights");
     static_assert(STAGE % 1024 == 0 && WT_HI % 1024 == 0 && WT_LO % 1024 == 0, "operand planes must be 1024-byte aligned");
@@ -579,33 +585,40 @@ __device__ __forceinline__ void umma_ss_lohi(uint32_t tmem_d, uint32_t adesc_lo,
         : "memory");
 }
 
-// forward layer L of the backward kernel's single chain (recompute)
+// One layer's MMAs of the backward kernel's single chain: D[128 x n] = A (hi | lo columns of TMEM, `ksteps` 8-wide k-steps) x B
+// (K-major SWIZZLE_128B slabs of 32 k, `n` rows each, hi plane at b_hi16, lo plane at b_lo16, in descriptor units of 16 bytes).
+// The k-step loop is rolled (the kernel is bound by instruction fetch); its trip count and every stride are
+// compile-time constants, the running addresses live in uniform registers.
+template <int N, int KSTEPS>
+__device__ __forceinline__ void issue_chain_layer(uint32_t b_hi16, uint32_t b_lo16) {
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+    constexpr uint32_t slab16 = (uint32_t)(N * 128) >> 4;            // next 32-wide K slab
+    uint32_t acc = 0u;
+#pragma unroll 1
+    for (int k0 = 0; k0 < KSTEPS; k0 += (KSTEPS < 4 ? KSTEPS : 4)) {
+#pragma unroll
+        for (int ks = 0; ks < (KSTEPS < 4 ? KSTEPS : 4); ++ks) {
+            const uint32_t ta = (uint32_t)(8 * (k0 + ks));
+            umma_ts_lohi(TC_D, TC_AL + ta, b_hi16 + 2 * ks, DESC_HI_SW128, idesc, ks > 0 ? 1u : acc);
+            umma_ts_lohi(TC_D, TC_AH + ta, b_lo16 + 2 * ks, DESC_HI_SW128, idesc, 1u);
+            umma_ts_lohi(TC_D, TC_AH + ta, b_hi16 + 2 * ks, DESC_HI_SW128, idesc, 1u);
+        }
+        b_hi16 += slab16;
+        b_lo16 += slab16;
+        acc = 1u;
+    }
+}
+// forward layer L (recompute)
 template <class TB, int L>
 __device__ __forceinline__ void issue_refwd_layer(uint32_t dlo_base) {
-    constexpr int n = TB::n(L), ksteps = TB::kp(L) / 8;
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-    constexpr uint32_t hi16 = (BwdSmem<TB>::W_HI + 4u * TB::woff(L)) >> 4, lo16 = (BwdSmem<TB>::W_LO + 4u * TB::woff(L)) >> 4;
-#pragma unroll
-    for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t bo = (uint32_t)((ks >> 2) * (n * 128) + (ks & 3) * 32) >> 4;
-        umma_ts_lohi(TC_D, TC_AL + 8 * ks, dlo_base + hi16 + bo, DESC_HI_SW128, idesc, ks > 0 ? 1u : 0u);
-        umma_ts_lohi(TC_D, TC_AH + 8 * ks, dlo_base + lo16 + bo, DESC_HI_SW128, idesc, 1u);
-        umma_ts_lohi(TC_D, TC_AH + 8 * ks, dlo_base + hi16 + bo, DESC_HI_SW128, idesc, 1u);
-    }
+    issue_chain_layer<TB::n(L), TB::kp(L) / 8>(dlo_base + ((BwdSmem<TB>::W_HI + 4u * TB::woff(L)) >> 4),
+                                                dlo_base + ((BwdSmem<TB>::W_LO + 4u * TB::woff(L)) >> 4));
 }
 // data gradient of layer L:  gh[L] (dn columns) = gz[L] (n columns, TMEM) . W_L   (B = W_L^T [dn rows][n], K-major)
 template <class TB, int L>
 __device__ __forceinline__ void issue_dgrad_layer(uint32_t dlo_base) {
-    constexpr int dn = TB::dn(L), ksteps = TB::n(L) / 8;
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(dn >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-    constexpr uint32_t hi16 = (BwdSmem<TB>::WT_HI + 4u * TB::toff(L)) >> 4, lo16 = (BwdSmem<TB>::WT_LO + 4u * TB::toff(L)) >> 4;
-#pragma unroll
-    for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t bo = (uint32_t)((ks >> 2) * (dn * 128) + (ks & 3) * 32) >> 4;
-        umma_ts_lohi(TC_D, TC_AL + 8 * ks, dlo_base + hi16 + bo, DESC_HI_SW128, idesc, ks > 0 ? 1u : 0u);
-        umma_ts_lohi(TC_D, TC_AH + 8 * ks, dlo_base + lo16 + bo, DESC_HI_SW128, idesc, 1u);
-        umma_ts_lohi(TC_D, TC_AH + 8 * ks, dlo_base + hi16 + bo, DESC_HI_SW128, idesc, 1u);
-    }
+    issue_chain_layer<TB::dn(L), TB::n(L) / 8>(dlo_base + ((BwdSmem<TB>::WT_HI + 4u * TB::toff(L)) >> 4),
+                                                dlo_base + ((BwdSmem<TB>::WT_LO + 4u * TB::toff(L)) >> 4));
 }
 
 // Staging geometry of layer L's weight-gradient slice (one quadrant = 32 rows): byte offsets inside the slice buffer.
@@ -629,20 +642,25 @@ struct Stg {
     static_assert((MF + NF) * 256 <= 2 * SUB_BYTES, "slice does not fit its staging buffer");
 };
 
-// weight-gradient MMAs of layer L, slice q (32 rows = 4 k-steps)
-template <class TB, int L, int Q>
-__device__ __forceinline__ void issue_wgrad_slice(uint32_t dlo_base) {
+// weight-gradient MMAs of layer L for one 32-row slice (4 k-steps); `dlo_buf` = descriptor low word of the quadrant's buffer.
+// The quadrant is a run-time value (the loop over quadrants stays rolled: the kernel's code must stay small, its instruction
+// fetch is what bounds it), everything else is an immediate.
+template <class TB, int L>
+__device__ __forceinline__ void issue_wgrad_slice(uint32_t dlo_buf, uint32_t first) {
     using S = Stg<TB, L>;
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::NF >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-    constexpr uint32_t buf = S::buf(Q);
+    constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * S::NF >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+    constexpr uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::NF >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
     constexpr uint32_t moff = (uint32_t)TB::wg_moff(L) * 128u;
-    static_assert(buf + S::M_HI >= moff, "the A tile must start inside shared memory");
-    constexpr uint32_t a_hi = (buf + S::M_HI - moff) >> 4, a_lo = (buf + S::M_LO - moff) >> 4, b_hi = (buf + S::N_HI) >> 4, b_lo = (buf + S::N_LO) >> 4;
+    static_assert(S::buf(0) + S::M_HI >= moff && S::buf(2) + S::M_HI >= moff, "the A tile must start inside shared memory");
+    static_assert(S::M_LO == S::M_HI + S::MF * 128u && S::N_LO == S::N_HI + S::NF * 128u, "the (hi, lo) planes must be stacked");
+    static_assert(S::MF % 8 == 0 && S::NF % 8 == 0, "planes must start on a swizzle period");
+    const uint32_t a_hi = dlo_buf + (S::M_HI >> 4) - (moff >> 4), a_lo = dlo_buf + (S::M_LO >> 4) - (moff >> 4), b_hi = dlo_buf + (S::N_HI >> 4);
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-        umma_ss_lohi(tc_dw(L), dlo_base + a_lo + 2 * ks, dlo_base + b_hi + 2 * ks, DESC_HI_SW128, idesc, (Q > 0 || ks > 0) ? 1u : 0u);
-        umma_ss_lohi(tc_dw(L), dlo_base + a_hi + 2 * ks, dlo_base + b_lo + 2 * ks, DESC_HI_SW128, idesc, 1u);
-        umma_ss_lohi(tc_dw(L), dlo_base + a_hi + 2 * ks, dlo_base + b_hi + 2 * ks, DESC_HI_SW128, idesc, 1u);
+        // A = [M_hi ; M_lo ; ...] (the lo rows count only for wg_one layers), B = [N_hi ; N_lo]
+        umma_ss_lohi(tc_dw(L), a_hi + 2 * ks, b_hi + 2 * ks, DESC_HI_SW128, idesc2, ks > 0 ? 1u : first);
+        if constexpr (!TB::wg_one(L))
+            umma_ss_lohi(tc_dw(L), a_lo + 2 * ks, b_hi + 2 * ks, DESC_HI_SW128, idesc1, 1u);
     }
 }
 
@@ -655,13 +673,11 @@ __device__ __forceinline__ void stage_put(uint8_t* plane_hi, uint8_t* plane_lo, 
 }
 
 // gz[L] of this thread (its NLOC = n(L)/2 columns) is ready: (1) A operand of layer L's data-gradient MMAs -> TMEM, signal the
-// chain issuer; (2) this quadrant's slice of layer L's weight gradient -> shared memory: gz[L] and act[L] (its own columns of
-// the saved layer output; the track for layer 0; knobs appended for layer 4), signal the weight-gradient issuer / flush warps.
+// chain issuer; (2) ELU'(act[L]) of the thread's own columns for the NEXT epilogue (gz[L-1] = gh[L] * ELU'), read here so
+// that nobody touches act[L] once the layer-L slices have been signalled.
 template <class TB, int L>
-__device__ __forceinline__ void bwd_handoff(uint8_t* smem_raw, uint32_t t_lane, uint32_t lane_off, int half, int q, int it, int lane,
-                                            const float (&gz)[TB::n(L) / 2], uint64_t* a_ready, uint64_t* full, uint64_t* freeb,
-                                            const float (&vkeep)[16], const float* knobs, long knob_off, int nk, long long* hb = nullptr) {
-    using S = Stg<TB, L>;
+__device__ __forceinline__ void bwd_handoff(uint32_t t_lane, int half, int lane, const float (&gz)[TB::n(L) / 2], uint64_t* a_ready,
+                                            float (&eg)[L > 0 ? TB::n(L > 0 ? L - 1 : 0) / 2 : 1], long long* hb = nullptr) {
     long long hc = hb ? clock64() : 0;
 #define HB(k) if (hb) { const long long n_ = clock64(); hb[k] += n_ - hc; hc = n_; }
     constexpr int NLOC = TB::n(L) / 2;
@@ -676,15 +692,42 @@ __device__ __forceinline__ void bwd_handoff(uint8_t* smem_raw, uint32_t t_lane, 
     __syncwarp();
     if (lane == 0) mbar_arrive(a_ready);
     HB(0)
-    // ---- weight-gradient slice
+    if constexpr (L > 0) {
+        constexpr int AW = TB::n(L - 1) / 2;                 // this thread's share of act[L] (width n(L-1))
+        uint32_t hv[AW];
+        tmem_ld<AW>(t_lane + tc_act(L) + half * AW, hv);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < AW; ++c) eg[c] = elu_grad(__uint_as_float(hv[c]));
+    }
+    HB(3)
+#undef HB
+}
+
+// gz[L] of this thread -> this quadrant's slice of layer L's weight gradient in shared memory, signal the weight-gradient issuer.
+// Runs one chain stage AFTER the hand-over above (the data-gradient MMAs of layer L are already in flight), so that the
+// buffer's previous slice has had a whole stage to be consumed.  act[L] is staged by the quadrant's flush warp, except the
+// track (act[0]), which the chain warps hold in registers.
+template <class TB, int L>
+__device__ __forceinline__ void bwd_stage_gz(uint8_t* smem_raw, uint32_t lane_off, int half, int q, int it, int lane,
+                                             const float (&gz)[TB::n(L) / 2], uint64_t* full, uint64_t* freeb, const float (&vkeep)[16],
+                                             long long* hb = nullptr) {
+    using S = Stg<TB, L>;
+    long long hc = hb ? clock64() : 0;
+#define HB(k) if (hb) { const long long n_ = clock64(); hb[k] += n_ - hc; hc = n_; }
+    constexpr int NLOC = TB::n(L) / 2;
+    const int c0 = half * NLOC;
     // the quadrant's own buffer: its previous slice must have been consumed (weight-gradient MMAs + bias-gradient pass)
     const int i = it * NL + (NL - 1 - L);                    // this quadrant's fill count = phase index of its barriers
     if (i > 0) mbar_wait_spin(&freeb[q], (uint32_t)((i - 1) & 1));
     HB(1)
     uint8_t* buf = smem_raw + (q < 2 ? BwdSmem<TB>::STAGE + (uint32_t)q * 2u * SUB_BYTES : BwdSmem<TB>::RELOAD_LO + (uint32_t)(q - 2) * 2u * SUB_BYTES);
 #pragma unroll
-    for (int c = 0; c < NLOC; ++c) stage_put(buf + S::GZ_HI, buf + S::GZ_LO, c0 + c, lane_off, ghi[c], glo[c]);
-    HB(2)
+    for (int c = 0; c < NLOC; ++c) {
+        uint32_t hi, lo;
+        split_tf32_alu(gz[c], hi, lo);
+        stage_put(buf + S::GZ_HI, buf + S::GZ_LO, c0 + c, lane_off, hi, lo);
+    }
     if constexpr (L == 0) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
@@ -692,34 +735,60 @@ __device__ __forceinline__ void bwd_handoff(uint8_t* smem_raw, uint32_t t_lane, 
             split_tf32_alu(vkeep[e], hi, lo);
             stage_put(buf + S::ACT_HI, buf + S::ACT_LO, 16 * half + e, lane_off, hi, lo);
         }
-    } else {
-        constexpr int AW = TB::n(L - 1) / 2;                 // this thread's share of act[L] (width n(L-1))
-        const int ac0 = half * AW;
-        uint32_t hv[AW];
-        tmem_ld<AW>(t_lane + tc_act(L) + ac0, hv);
-        tmem_wait_ld();
-#pragma unroll
-        for (int c = 0; c < AW; ++c) {
-            uint32_t hi, lo;
-            split_tf32_alu(__uint_as_float(hv[c]), hi, lo);
-            stage_put(buf + S::ACT_HI, buf + S::ACT_LO, ac0 + c, lane_off, hi, lo);
-        }
-        if (L == 4 && half == 1 && TB::KP5 > 16) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float kv = e < nk ? __ldg(knobs + knob_off + e) : 0.f;
-                uint32_t hi, lo;
-                split_tf32_alu(kv, hi, lo);
-                stage_put(buf + S::ACT_HI, buf + S::ACT_LO, 16 + e, lane_off, hi, lo);
-            }
-        }
     }
-    HB(3)
+    HB(2)
     fence_async_smem();                                      // generic-proxy writes -> the MMAs' async-proxy reads
     __syncwarp();
     if (lane == 0) mbar_arrive(&full[q]);
     HB(4)
 #undef HB
+}
+
+// Sum over the 32 rows of a slice of feature f of a staged (hi, lo) plane pair (bias gradient; not inlined: code size).
+__device__ __noinline__ float slice_row_sum(const uint8_t* plane_hi, const uint8_t* plane_lo, int f) {
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint32_t o = (uint32_t)f * 128u + ((uint32_t)(c ^ (f & 7)) << 4);
+        const float4 h4 = *reinterpret_cast<const float4*>(plane_hi + o);
+        const float4 l4 = *reinterpret_cast<const float4*>(plane_lo + o);
+        sum += ((h4.x + l4.x) + (h4.y + l4.y)) + ((h4.z + l4.z) + (h4.w + l4.w));
+    }
+    return sum;
+}
+// Flush warp: this quadrant's 32 rows (lane = row) of `width` saved activations starting at TMEM address t_src -> (hi, lo)
+// planes of a slice.  One rolled loop shared by every layer (not inlined: code size).
+__device__ __noinline__ void stage_act_rows(uint8_t* plane_hi, uint8_t* plane_lo, uint32_t t_src, int width, uint32_t lane_off) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < width; c0 += 16) {
+        uint32_t hv[16];
+        tmem_ld<16>(t_src + c0, hv);
+        tmem_wait_ld();
+        uint8_t* ph = plane_hi + c0 * 128;
+        uint8_t* pl = plane_lo + c0 * 128;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {                       // (c0 + c) & 7 == c & 7: the swizzle term is an immediate
+            uint32_t hi, lo;
+            split_tf32_alu(__uint_as_float(hv[c]), hi, lo);
+            stage_put(ph, pl, c, lane_off, hi, lo);
+        }
+    }
+}
+// act[L] (the saved output of layer L - 1; knobs appended for layer 4) -> layer L's slice
+template <class TB, int L>
+__device__ __forceinline__ void stage_act(uint8_t* buf, uint32_t t_lq, uint32_t lane_off, const float* knobs, long knob_off, int nk) {
+    using S = Stg<TB, L>;
+    static_assert(L > 0, "the track is staged by the chain warps");
+    stage_act_rows(buf + S::ACT_HI, buf + S::ACT_LO, t_lq + tc_act(L), TB::n(L - 1), lane_off);
+    if constexpr (L == 4 && TB::KP5 > 16) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float kv = e < nk ? __ldg(knobs + knob_off + e) : 0.f;
+            uint32_t hi, lo;
+            split_tf32_alu(kv, hi, lo);
+            stage_put(buf + S::ACT_HI, buf + S::ACT_LO, 16 + e, lane_off, hi, lo);
+        }
+    }
 }
 
 struct BwdArgs {
@@ -749,12 +818,13 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
     uint64_t* a_ready = bars;            // chain warps -> chain issuer (count 8)
     uint64_t* d_ready = bars + 1;        // chain issuer -> chain warps
     uint64_t* w_ready = bars + 2;        // weight image landed
-    uint64_t* full = bars + 3;           // [4] staging sub-buffer written (count 2: the two column halves of a quadrant)
+    uint64_t* full = bars + 3;           // [4] slice written (count 3: the two column halves of the quadrant + its flush warp)
     uint64_t* freeb = bars + 7;          // [4] staging sub-buffer consumed (count 2: weight-gradient MMAs + bias-gradient reader)
     uint64_t* flushed = bars + 11;       // flush warps -> chain warps: every accumulator of the tile has been read (count 4), once per tile
     uint64_t* dw_ready = bars + 16;      // [4] ring: weight-gradient issuer -> flush warps: the layer's accumulator is complete (the
                                          // issuer may run two layers ahead of a flush warp; a parity wait cannot tell phase k from k + 2)
     uint64_t* w_reload = bars + 13;      // the forward-weight bytes the staging of quadrants 2, 3 overwrote are back (once per tile)
+    uint64_t* fwd_done = bars + 12;      // chain warps -> flush warps: the tile's forward chain is complete (count 8), once per tile
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -763,9 +833,9 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
     constexpr int IMGF = bwd_image_floats<TB>();
     if (threadIdx.x == 0) {
         mbar_init(a_ready, BWD_CHAIN_WARPS); mbar_init(d_ready, 1); mbar_init(w_ready, 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 2); mbar_init(&freeb[i], 2); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 3); mbar_init(&freeb[i], 2); }
         for (int i = 0; i < 4; ++i) mbar_init(&dw_ready[i], 1);
-        mbar_init(flushed, 4); mbar_init(w_reload, 1);
+        mbar_init(flushed, 4); mbar_init(w_reload, 1); mbar_init(fwd_done, BWD_CHAIN_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint8_t* img = reinterpret_cast<const uint8_t*>(a.image + (long)ae * IMGF);
         constexpr uint32_t WB = 8u * TB::wfloats, TBY = 8u * TB::tfloats + 4u * ((TB::bfloats + 255) / 256 * 256);
@@ -804,13 +874,15 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
         // ======================= weight-gradient MMAs: per layer 8..0, the four 32-row slices into one accumulator ===========
         int nl = 0;                                          // layers issued so far = phase index of full[] / free[] / dw_*
         for (int tile = slot; tile < ntiles; tile += nslot) {
-#define ST_WQ(L, Q)                                                                                         \
-            mbar_wait_spin(&full[Q], (uint32_t)(nl & 1));                                                   \
-            tc_fence_after();                                                                               \
-            issue_wgrad_slice<TB, L, Q>(dlo_base);                                                          \
-            umma_commit_elect(&freeb[Q]);
 #define ST_WL(L)                                                                                            \
-            ST_WQ(L, 0) ST_WQ(L, 1) ST_WQ(L, 2) ST_WQ(L, 3)                                                 \
+            _Pragma("unroll 1")                                                                             \
+            for (int qq = 0; qq < 4; ++qq) {                                                                \
+                mbar_wait_spin(&full[qq], (uint32_t)(nl & 1));                                              \
+                tc_fence_after();                                                                           \
+                const uint32_t boff = qq < 2 ? SM::STAGE + (uint32_t)qq * 2u * SUB_BYTES : SM::RELOAD_LO + (uint32_t)(qq - 2) * 2u * SUB_BYTES; \
+                issue_wgrad_slice<TB, L>(dlo_base + (boff >> 4), qq > 0 ? 1u : 0u);                          \
+                umma_commit_elect(&freeb[qq]);                                                              \
+            }                                                                                               \
             umma_commit_elect(&dw_ready[nl & 3]);                                                           \
             ++nl;
             ST_WL(8) ST_WL(7) ST_WL(6) ST_WL(5) ST_WL(4) ST_WL(3) ST_WL(2) ST_WL(1) ST_WL(0)
@@ -828,53 +900,74 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 __syncwarp();
             }
 #undef ST_WL
-#undef ST_WQ
         }
     } else if (warp >= BWD_FLUSH_WARP0) {
-        // ======================= flush warps: accumulate D_w into registers, bias gradients from the staged gz ================
+        // ======================= flush warps: stage act[L], bias gradients from the staged gz, accumulate D_w into registers ====
         const int q = warp & 3;
         const int glane = 32 * q + lane;                     // TMEM lane = feature row of the M operand (+ its lane offset)
         const uint32_t t_lq = (uint32_t)(32 * q) << 16;
-        float acc[80];
-        float dbacc[11];
+        const uint32_t lane_off = ((uint32_t)(lane >> 2) << 4) | ((uint32_t)(lane & 3) << 2);
+        uint8_t* const qbuf = smem_raw + (q < 2 ? SM::STAGE + (uint32_t)q * 2u * SUB_BYTES : SM::RELOAD_LO + (uint32_t)(q - 2) * 2u * SUB_BYTES);
+        float acc[TB::wg_regs];
+        float dbacc[11];                                     // bias-gradient sums: lane = feature, one register per 32 features of a layer
 #pragma unroll
-        for (int i = 0; i < 80; ++i) acc[i] = 0.f;
+        for (int i = 0; i < TB::wg_regs; ++i) acc[i] = 0.f;
 #pragma unroll
         for (int i = 0; i < 11; ++i) dbacc[i] = 0.f;
-        int nl = 0;
-        for (int tile = slot; tile < ntiles; tile += nslot) {
+        int nl = 0, it = 0;
+        for (int tile = slot; tile < ntiles; tile += nslot, ++it) {
+            const int R = tile * TILE + glane;
+            const bool ok = R < BF;
+            const long knob_off = (long)(ok ? R / d.F : 0) * d.K;
+            const int nk = ok ? d.K : 0;
+            // act[8] of this tile: the forward chain must be complete (which also means the forward weights that quadrants 2, 3
+            // stage over are no longer being read), and the buffer's last slice of the previous tile consumed
+            mbar_wait_spin(fwd_done, (uint32_t)(it & 1));
+            tc_fence_after();
+            if (nl > 0) mbar_wait_spin(&freeb[q], (uint32_t)((nl - 1) & 1));
+            stage_act<TB, NL - 1>(qbuf, t_lq, lane_off, a.knobs, knob_off, nk);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[q]);
 #define ST_FL(L, DBSLOT)                                                                                              \
             {                                                                                                          \
                 using S = Stg<TB, L>;                                                                                  \
                 mbar_wait_spin(&full[q], (uint32_t)(nl & 1));                                                          \
-                const uint8_t* gb = smem_raw + (q < 2 ? SM::STAGE + (uint32_t)q * 2u * SUB_BYTES : SM::RELOAD_LO + (uint32_t)(q - 2) * 2u * SUB_BYTES); \
                 _Pragma("unroll")                                                                                      \
                 for (int p = 0; p < (TB::n(L) + 31) / 32; ++p) {                                                       \
                     const int f = 32 * p + lane;                                                                       \
-                    if (f < TB::n(L)) {                                                                                \
-                        float sum = 0.f;                                                                               \
-                        _Pragma("unroll")                                                                              \
-                        for (int c = 0; c < 8; ++c) {                                                                  \
-                            const uint32_t o = (uint32_t)f * 128u + ((uint32_t)(c ^ (f & 7)) << 4);                    \
-                            const float4 h4 = *reinterpret_cast<const float4*>(gb + S::GZ_HI + o);                     \
-                            const float4 l4 = *reinterpret_cast<const float4*>(gb + S::GZ_LO + o);                     \
-                            sum += ((h4.x + l4.x) + (h4.y + l4.y)) + ((h4.z + l4.z) + (h4.w + l4.w));                  \
-                        }                                                                                              \
-                        dbacc[DBSLOT + p] += sum;                                                                      \
-                    }                                                                                                  \
+                    if (f < TB::n(L)) dbacc[DBSLOT + p] += slice_row_sum(qbuf + S::GZ_HI, qbuf + S::GZ_LO, f);         \
                 }                                                                                                      \
                 __syncwarp();                                                                                          \
                 if (lane == 0) mbar_arrive(&freeb[q]);                                                                 \
+                /* next layer's act into the same buffer as soon as this layer's MMAs have read it */                  \
+                if constexpr ((L) > 1) {                                                                               \
+                    mbar_wait_spin(&freeb[q], (uint32_t)(nl & 1));                                                     \
+                    stage_act<TB, ((L) > 1 ? (L) - 1 : 1)>(qbuf, t_lq, lane_off, a.knobs, knob_off, nk);               \
+                    fence_async_smem();                                                                                \
+                    __syncwarp();                                                                                      \
+                }                                                                                                      \
+                if constexpr ((L) > 0) { if (lane == 0) mbar_arrive(&full[q]); }                                       \
                 mbar_wait_spin(&dw_ready[nl & 3], (uint32_t)(nl >> 2) & 1u);                                           \
                 tc_fence_after();                                                                                      \
                 constexpr int MO = TB::wg_moff(L), MF = S::MF, NF = S::NF, RG = TB::wg_reg(L);                         \
-                if (32 * q < MO + MF && 32 * q + 32 > MO) {                                                            \
-                    uint32_t v[NF];                                                                                    \
-                    tmem_ld<NF>(t_lq + tc_dw(L), v);                                                                   \
-                    tmem_wait_ld();                                                                                    \
-                    if (glane >= MO && glane < MO + MF) {                                                              \
-                        _Pragma("unroll")                                                                              \
-                        for (int i = 0; i < NF; ++i) acc[RG + i] += __uint_as_float(v[i]);                             \
+                constexpr int LIVE = TB::wg_one(L) ? 2 * MF : MF;                                                      \
+                if (32 * q < MO + LIVE && 32 * q + 32 > MO) {                                                          \
+                    const bool hi_row = glane >= MO && glane < MO + MF;                                                \
+                    const bool lo_row = TB::wg_one(L) && glane >= MO + MF && glane < MO + 2 * MF;                      \
+                    _Pragma("unroll")                                                                                  \
+                    for (int c0 = 0; c0 < NF; c0 += 8) {                                                               \
+                        uint32_t v[8], w[8];                                                                           \
+                        tmem_ld<8>(t_lq + tc_dw(L) + c0, v);                                                           \
+                        tmem_ld<8>(t_lq + tc_dw(L) + NF + c0, w);                                                      \
+                        tmem_wait_ld();                                                                                \
+                        if (hi_row) {                                                                                  \
+                            _Pragma("unroll")                                                                          \
+                            for (int i = 0; i < 8; ++i) acc[RG + c0 + i] += __uint_as_float(v[i]) + __uint_as_float(w[i]); \
+                        } else if (lo_row) {                                                                           \
+                            _Pragma("unroll")                                                                          \
+                            for (int i = 0; i < 8; ++i) acc[RG + c0 + i] += __uint_as_float(v[i]);                     \
+                        }                                                                                              \
                     }                                                                                                  \
                 }                                                                                                      \
                 tc_fence_before();                                                                                     \
@@ -887,9 +980,10 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
         }
         // ---- per-CTA partial gradients -> global memory (layout: [W_0, b_0, W_1, b_1, ...] like ae_grad_reduce_kernel reads it)
         float* part = a.partials + ((long)slot * 2 + ae) * g.flat_total;
-#define ST_WR(L)                                                                                                       \
-        {                                                                                                              \
-            constexpr int MO = TB::wg_moff(L), MF = TB::wg_mf(L), NF = TB::wg_nf(L), RG = TB::wg_reg(L);               \
+#define ST_WR(L, LO)                                                                                                   \
+        if (!(LO) || TB::wg_one(L)) {                                                                                  \
+            constexpr int MF = TB::wg_mf(L), NF = TB::wg_nf(L), RG = TB::wg_reg(L);                                    \
+            constexpr int MO = TB::wg_moff(L) + ((LO) ? MF : 0);                                                       \
             const int IN = g.in[L], OUT = g.out[L];                                                                    \
             float* W = part + g.flat_off[L];                                                                           \
             if (glane >= MO && glane < MO + MF) {                                                                      \
@@ -897,15 +991,18 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 _Pragma("unroll")                                                                                      \
                 for (int i = 0; i < NF; ++i) {                                                                         \
                     const int o = TB::wg_m_is_gz(L) ? m : i, k = TB::wg_m_is_gz(L) ? i : m;                            \
-                    if (o < OUT && k < IN) W[o * IN + k] = acc[RG + i];                                                \
+                    if (o < OUT && k < IN) { if (LO) W[o * IN + k] += acc[RG + i]; else W[o * IN + k] = acc[RG + i]; } \
                 }                                                                                                      \
             }                                                                                                          \
         }
-        ST_WR(0) ST_WR(1) ST_WR(2) ST_WR(3) ST_WR(4) ST_WR(5) ST_WR(6) ST_WR(7) ST_WR(8)
+        ST_WR(0, false) ST_WR(1, false) ST_WR(2, false) ST_WR(3, false) ST_WR(4, false) ST_WR(5, false) ST_WR(6, false) ST_WR(7, false) ST_WR(8, false)
+        __threadfence_block();
+        asm volatile("bar.sync 2, 128;" ::: "memory");                        // hi rows written; every flush warp is past its last slice
+        // the (m_lo . n_hi) sums of the single-MMA layers sit MF lanes below their hi rows: fold them in
+        ST_WR(2, true) ST_WR(3, true) ST_WR(4, true) ST_WR(5, true) ST_WR(6, true)
 #undef ST_WR
         // bias gradients: the four flush warps hold the sums of their own quadrant's rows -> add through shared memory
         float* dbs = reinterpret_cast<float*>(smem_raw + SM::STAGE);          // staging is idle now: [4][11][32]
-        asm volatile("bar.sync 2, 128;" ::: "memory");                        // every flush warp is past its last slice
 #pragma unroll
         for (int i = 0; i < 11; ++i) dbs[(q * 11 + i) * 32 + lane] = dbacc[i];
         asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -966,7 +1063,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 for (int e = 0; e < 16; ++e) {
                     const int t = c0 + e;
                     const bool in = ok && t < d.T;
-                    vkeep[e] = ae == 0 ? sqrtf(re[e] * re[e] + im[e] * im[e]) : (in ? atan2_fast(im[e], re[e] + 1e-7f) : 0.f);
+                    vkeep[e] = ae == 0 ? sqrtf(re[e] * re[e] + im[e] * im[e]) : (in ? atan2_ni(im[e], re[e] + 1e-7f) : 0.f);
                     if (t >= tail0 && t < d.T) vtail[(t - tail0) * TILE + row] = vkeep[e];
                 }
                 store_pair<16>(t_lane + TC_AH + c0, t_lane + TC_AL + c0, vkeep);
@@ -1010,6 +1107,8 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
             }
 
             // ---- fnn_dec + output side backwards: gz[8], and the skip / residual gradient (left in vtail for the end of the tile)
+            float eg8[TB::n(7) / 2];                         // ELU'(act[8]), this thread's columns (from the layer-8 hand-over)
+            float gz8[8];
             {
                 const int j0 = 8 * half;
                 float gre[8], gim[8], phv[8], x3[8];
@@ -1027,12 +1126,14 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 mbar_wait_spin(d_ready, ph);
                 ph ^= 1;
                 tc_fence_after();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(fwd_done);        // the flush warps may stage act[8] (and overwrite forward weights)
                 BT(1)
                 uint32_t rr[8];
                 tmem_ld<8>(t_lane + TC_D + j0, rr);
                 tmem_wait_ld();
                 const float* bl = bias + c_boff[NL - 1] + j0;
-                float gz[8];
+                float (&gz)[8] = gz8;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float e9 = elu_f(__uint_as_float(rr[j]) + bl[j]);
@@ -1056,11 +1157,13 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                     for (int j = 0; j < 8; ++j) mydbg[(long)(NL + 8) * TILE * 64 + j0 + j] = gz[j];
                 }
                 BT(3)
-                bwd_handoff<TB, 8>(smem_raw, t_lane, lane_off, half, q, it, lane, gz, a_ready, full, freeb, vkeep, nullptr, 0, 0, hb);
+                bwd_handoff<TB, 8>(t_lane, half, lane, gz, a_ready, eg8, hb);
                 BT(5)
             }
             // ---- data gradients, layers 8..1: gz[l-1] = gh[l] * ELU'(act[l]); the weight-gradient slice of layer l-1 follows
-#define ST_BW(L)                                                                                                     \
+#define ST_BW(L, EG_IN, EG_OUT, GZ_IN, GZ_OUT)                                                                       \
+            float EG_OUT[(L) > 1 ? TB::n((L) > 1 ? (L) - 2 : 0) / 2 : 1];                                            \
+            float GZ_OUT[TB::dn(L) / 2];                                                                             \
             {                                                                                                        \
                 constexpr int NLOC = TB::dn(L) / 2;                                                                  \
                 const int c0 = half * NLOC;                                                                          \
@@ -1068,24 +1171,27 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 ph ^= 1;                                                                                             \
                 tc_fence_after();                                                                                    \
                 BT(1)                                                                                                \
-                uint32_t gh[NLOC], hv[NLOC];                                                                         \
+                uint32_t gh[NLOC];                                                                                   \
                 tmem_ld<NLOC>(t_lane + TC_D + c0, gh);                                                               \
-                tmem_ld<NLOC>(t_lane + tc_act(L) + c0, hv);                                                          \
                 tmem_wait_ld();                                                                                      \
-                float gz[NLOC];                                                                                      \
                 _Pragma("unroll")                                                                                    \
-                for (int c = 0; c < NLOC; ++c) gz[c] = __uint_as_float(gh[c]) * elu_grad(__uint_as_float(hv[c]));    \
+                for (int c = 0; c < NLOC; ++c) GZ_OUT[c] = __uint_as_float(gh[c]) * EG_IN[c];                        \
                 if (mydbg) {                                                                                         \
                     _Pragma("unroll")                                                                                \
-                    for (int c = 0; c < NLOC; ++c) mydbg[(long)(NL + (L) - 1) * TILE * 64 + c0 + c] = gz[c];          \
+                    for (int c = 0; c < NLOC; ++c) mydbg[(long)(NL + (L) - 1) * TILE * 64 + c0 + c] = GZ_OUT[c];      \
                 }                                                                                                    \
                 BT(4)                                                                                                \
-                bwd_handoff<TB, (L) - 1>(smem_raw, t_lane, lane_off, half, q, it, lane, gz, a_ready, full, freeb, vkeep, a.knobs, (long)b * d.K, ok ? d.K : 0, hb); \
+                bwd_handoff<TB, (L) - 1>(t_lane, half, lane, GZ_OUT, a_ready, EG_OUT, hb);                           \
+                /* the previous layer's slice, one stage late */                                                    \
+                bwd_stage_gz<TB, (L)>(smem_raw, lane_off, half, q, it, lane, GZ_IN, full, freeb, vkeep, hb);         \
                 BT(5)                                                                                                \
             }
-            ST_BW(8) ST_BW(7) ST_BW(6) ST_BW(5) ST_BW(4) ST_BW(3) ST_BW(2) ST_BW(1)
+            ST_BW(8, eg8, eg7, gz8, gz7) ST_BW(7, eg7, eg6, gz7, gz6) ST_BW(6, eg6, eg5, gz6, gz5) ST_BW(5, eg5, eg4, gz5, gz4)
+            ST_BW(4, eg4, eg3, gz4, gz3) ST_BW(3, eg3, eg2, gz3, gz2) ST_BW(2, eg2, eg1, gz2, gz1) ST_BW(1, eg1, eg0, gz1, gz0)
 #undef ST_BW
             // ---- layer 0: gh[0] + skip / residual gradient = dLoss/d(track), stored lane <-> bin (coalesced)
+            bwd_stage_gz<TB, 0>(smem_raw, lane_off, half, q, it, lane, gz0, full, freeb, vkeep, hb);
+            BT(5)
             {
                 const int c0 = 16 * half;
                 mbar_wait_spin(d_ready, ph);
