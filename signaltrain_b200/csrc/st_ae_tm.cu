@@ -677,12 +677,12 @@ __device__ __forceinline__ void stage_put(uint8_t* plane_hi, uint8_t* plane_lo, 
 // that nobody touches act[L] once the layer-L slices have been signalled.
 template <class TB, int L>
 __device__ __forceinline__ void bwd_handoff(uint32_t t_lane, int half, int lane, const float (&gz)[TB::n(L) / 2], uint64_t* a_ready,
-                                            float (&eg)[L > 0 ? TB::n(L > 0 ? L - 1 : 0) / 2 : 1], long long* hb = nullptr) {
+                                            float (&eg)[L > 0 ? TB::n(L > 0 ? L - 1 : 0) / 2 : 1], uint32_t (&ghi)[TB::n(L) / 2],
+                                            uint32_t (&glo)[TB::n(L) / 2], long long* hb = nullptr) {
     long long hc = hb ? clock64() : 0;
 #define HB(k) if (hb) { const long long n_ = clock64(); hb[k] += n_ - hc; hc = n_; }
     constexpr int NLOC = TB::n(L) / 2;
     const int c0 = half * NLOC;
-    uint32_t ghi[NLOC], glo[NLOC];
 #pragma unroll
     for (int c = 0; c < NLOC; ++c) split_tf32_alu(gz[c], ghi[c], glo[c]);
     tmem_st<NLOC>(t_lane + TC_AH + c0, ghi);
@@ -704,14 +704,14 @@ __device__ __forceinline__ void bwd_handoff(uint32_t t_lane, int half, int lane,
 #undef HB
 }
 
-// gz[L] of this thread -> this quadrant's slice of layer L's weight gradient in shared memory, signal the weight-gradient issuer.
-// Runs one chain stage AFTER the hand-over above (the data-gradient MMAs of layer L are already in flight), so that the
-// buffer's previous slice has had a whole stage to be consumed.  act[L] is staged by the quadrant's flush warp, except the
-// track (act[0]), which the chain warps hold in registers.
+// gz[L] of this thread (already split) -> this quadrant's slice of layer L's weight gradient in shared memory, signal the
+// weight-gradient issuer.  Follows the hand-over above (the data-gradient MMAs of layer L are in flight meanwhile).  act[L] is
+// staged by the quadrant's flush warp, except the track (act[0]), which the chain warps hold in registers.
+// (Staging one chain stage late, to give the buffer longer to drain, was measured slower: 372 vs 354 us.)
 template <class TB, int L>
 __device__ __forceinline__ void bwd_stage_gz(uint8_t* smem_raw, uint32_t lane_off, int half, int q, int it, int lane,
-                                             const float (&gz)[TB::n(L) / 2], uint64_t* full, uint64_t* freeb, const float (&vkeep)[16],
-                                             long long* hb = nullptr) {
+                                             const uint32_t (&ghi)[TB::n(L) / 2], const uint32_t (&glo)[TB::n(L) / 2], uint64_t* full,
+                                             uint64_t* freeb, const float (&vkeep)[16], long long* hb = nullptr) {
     using S = Stg<TB, L>;
     long long hc = hb ? clock64() : 0;
 #define HB(k) if (hb) { const long long n_ = clock64(); hb[k] += n_ - hc; hc = n_; }
@@ -723,11 +723,7 @@ __device__ __forceinline__ void bwd_stage_gz(uint8_t* smem_raw, uint32_t lane_of
     HB(1)
     uint8_t* buf = smem_raw + (q < 2 ? BwdSmem<TB>::STAGE + (uint32_t)q * 2u * SUB_BYTES : BwdSmem<TB>::RELOAD_LO + (uint32_t)(q - 2) * 2u * SUB_BYTES);
 #pragma unroll
-    for (int c = 0; c < NLOC; ++c) {
-        uint32_t hi, lo;
-        split_tf32_alu(gz[c], hi, lo);
-        stage_put(buf + S::GZ_HI, buf + S::GZ_LO, c0 + c, lane_off, hi, lo);
-    }
+    for (int c = 0; c < NLOC; ++c) stage_put(buf + S::GZ_HI, buf + S::GZ_LO, c0 + c, lane_off, ghi[c], glo[c]);
     if constexpr (L == 0) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
@@ -806,7 +802,8 @@ struct BwdArgs {
     int B;
 };
 
-template <class TB>
+// DBG: the instantiation the tests use to dump tile 0's chain (kept out of the production kernel: code size)
+template <class TB, bool DBG>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
     static_assert(TB::KP1 == 32, "backward kernel: T <= 32");
@@ -1045,7 +1042,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
             const int R = tile * TILE + row;
             const bool ok = R < BF;
             const int b = ok ? R / d.F : 0, f = ok ? R - b * d.F : 0;
-            float* mydbg = (a.dbg && tile == 0 && ae == 0) ? a.dbg + (long)row * 64 : nullptr;
+            float* mydbg = (DBG && a.dbg && tile == 0 && ae == 0) ? a.dbg + (long)row * 64 : nullptr;
             float vkeep[16];
             BT0()
             // ---- input track (this thread: frames [16 half, +16)) -> A operand, kept in registers for layer 0's weight gradient
@@ -1108,7 +1105,6 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
 
             // ---- fnn_dec + output side backwards: gz[8], and the skip / residual gradient (left in vtail for the end of the tile)
             float eg8[TB::n(7) / 2];                         // ELU'(act[8]), this thread's columns (from the layer-8 hand-over)
-            float gz8[8];
             {
                 const int j0 = 8 * half;
                 float gre[8], gim[8], phv[8], x3[8];
@@ -1133,7 +1129,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 tmem_ld<8>(t_lane + TC_D + j0, rr);
                 tmem_wait_ld();
                 const float* bl = bias + c_boff[NL - 1] + j0;
-                float (&gz)[8] = gz8;
+                float gz[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float e9 = elu_f(__uint_as_float(rr[j]) + bl[j]);
@@ -1157,13 +1153,14 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                     for (int j = 0; j < 8; ++j) mydbg[(long)(NL + 8) * TILE * 64 + j0 + j] = gz[j];
                 }
                 BT(3)
-                bwd_handoff<TB, 8>(t_lane, half, lane, gz, a_ready, eg8, hb);
+                uint32_t ghi[8], glo[8];
+                bwd_handoff<TB, 8>(t_lane, half, lane, gz, a_ready, eg8, ghi, glo, hb);
+                bwd_stage_gz<TB, 8>(smem_raw, lane_off, half, q, it, lane, ghi, glo, full, freeb, vkeep, hb);
                 BT(5)
             }
             // ---- data gradients, layers 8..1: gz[l-1] = gh[l] * ELU'(act[l]); the weight-gradient slice of layer l-1 follows
-#define ST_BW(L, EG_IN, EG_OUT, GZ_IN, GZ_OUT)                                                                       \
+#define ST_BW(L, EG_IN, EG_OUT)                                                                                      \
             float EG_OUT[(L) > 1 ? TB::n((L) > 1 ? (L) - 2 : 0) / 2 : 1];                                            \
-            float GZ_OUT[TB::dn(L) / 2];                                                                             \
             {                                                                                                        \
                 constexpr int NLOC = TB::dn(L) / 2;                                                                  \
                 const int c0 = half * NLOC;                                                                          \
@@ -1174,24 +1171,23 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 uint32_t gh[NLOC];                                                                                   \
                 tmem_ld<NLOC>(t_lane + TC_D + c0, gh);                                                               \
                 tmem_wait_ld();                                                                                      \
+                float gz[NLOC];                                                                                      \
                 _Pragma("unroll")                                                                                    \
-                for (int c = 0; c < NLOC; ++c) GZ_OUT[c] = __uint_as_float(gh[c]) * EG_IN[c];                        \
+                for (int c = 0; c < NLOC; ++c) gz[c] = __uint_as_float(gh[c]) * EG_IN[c];                            \
                 if (mydbg) {                                                                                         \
                     _Pragma("unroll")                                                                                \
-                    for (int c = 0; c < NLOC; ++c) mydbg[(long)(NL + (L) - 1) * TILE * 64 + c0 + c] = GZ_OUT[c];      \
+                    for (int c = 0; c < NLOC; ++c) mydbg[(long)(NL + (L) - 1) * TILE * 64 + c0 + c] = gz[c];          \
                 }                                                                                                    \
                 BT(4)                                                                                                \
-                bwd_handoff<TB, (L) - 1>(t_lane, half, lane, GZ_OUT, a_ready, EG_OUT, hb);                           \
-                /* the previous layer's slice, one stage late */                                                    \
-                bwd_stage_gz<TB, (L)>(smem_raw, lane_off, half, q, it, lane, GZ_IN, full, freeb, vkeep, hb);         \
+                uint32_t ghi[NLOC], glo[NLOC];                                                                       \
+                bwd_handoff<TB, (L) - 1>(t_lane, half, lane, gz, a_ready, EG_OUT, ghi, glo, hb);                     \
+                bwd_stage_gz<TB, (L) - 1>(smem_raw, lane_off, half, q, it, lane, ghi, glo, full, freeb, vkeep, hb);  \
                 BT(5)                                                                                                \
             }
-            ST_BW(8, eg8, eg7, gz8, gz7) ST_BW(7, eg7, eg6, gz7, gz6) ST_BW(6, eg6, eg5, gz6, gz5) ST_BW(5, eg5, eg4, gz5, gz4)
-            ST_BW(4, eg4, eg3, gz4, gz3) ST_BW(3, eg3, eg2, gz3, gz2) ST_BW(2, eg2, eg1, gz2, gz1) ST_BW(1, eg1, eg0, gz1, gz0)
+            ST_BW(8, eg8, eg7) ST_BW(7, eg7, eg6) ST_BW(6, eg6, eg5) ST_BW(5, eg5, eg4) ST_BW(4, eg4, eg3) ST_BW(3, eg3, eg2) ST_BW(2, eg2, eg1)
+            ST_BW(1, eg1, eg0)
 #undef ST_BW
             // ---- layer 0: gh[0] + skip / residual gradient = dLoss/d(track), stored lane <-> bin (coalesced)
-            bwd_stage_gz<TB, 0>(smem_raw, lane_off, half, q, it, lane, gz0, full, freeb, vkeep, hb);
-            BT(5)
             {
                 const int c0 = 16 * half;
                 mbar_wait_spin(d_ready, ph);
@@ -1291,7 +1287,8 @@ int launch_bwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AePar
     static_assert(smem <= 227 * 1024, "backward tile does not fit shared memory");
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(ae_bwd_tm_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+        if (cudaFuncSetAttribute(ae_bwd_tm_kernel<TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+        if (cudaFuncSetAttribute(ae_bwd_tm_kernel<TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
         configured = true;
     }
     if (pack) ae_pack_kernel<TB, true><<<dim3(NL, 2), 256, 0, s_pack>>>(g, pm, pp, wpack);
@@ -1301,7 +1298,8 @@ int launch_bwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AePar
     BwdArgs a;
     a.image = wpack; a.spec = spec; a.knobs = knobs; a.mag_hat = mag_hat; a.phs_hat = phs_hat; a.g_ri = g_ri; a.g_mag_hat = g_mag_hat;
     a.g_track = g_track; a.partials = partials; a.dbg = dbg; a.timing = timing; a.B = B;
-    ae_bwd_tm_kernel<TB><<<2 * nslot, BWD_THREADS, smem, s>>>(d, g, a);
+    if (dbg) ae_bwd_tm_kernel<TB, true><<<2 * nslot, BWD_THREADS, smem, s>>>(d, g, a);
+    else ae_bwd_tm_kernel<TB, false><<<2 * nslot, BWD_THREADS, smem, s>>>(d, g, a);
     if (g_spec) {
         const long ntrk = (long)B * d.T * d.F;
         ae_track_to_spec_kernel<<<(int)std::min<long>((ntrk + 255) / 256, 8L * sm_count), 256, 0, s>>>(d, B, spec, g_track, g_track + ntrk, g_mag,
