@@ -113,7 +113,7 @@ def ncu_dram_traffic(stage):
         return None, "no ncu --set full capture of this kernel committed for this build"
     import csv
     rows = list(csv.reader(open(path)))            # scripts/ncu_summary.py: one column per captured launch
-    cols = [i for i, n in enumerate(rows[0]) if any(n.startswith(w_) for w_ in want)]
+    cols = [i for i, n in enumerate(rows[0]) if any(w_ in n for w_ in want)]
     if not cols:
         return None, f"profiles/{NCU_SUMMARY} holds no launch of {want}"
     seen, tot = set(), 0.0

@@ -16,6 +16,10 @@ def main():
         if r.get("Metric Name") == "gpu__time_duration.sum":
             ns = float(r["Metric Value"]) * (1000.0 if r["Metric Unit"] in ("us", "usecond") else 1.0)
             rows.append((r["Kernel Name"], ns))
+    # torch's own kernels (pool generation, fills, the TF32-peak matmul bench.py times for its GEMM fraction) are not the step
+    own = [(n, ns) for n, ns in rows if not re.search(r"cutlass|at::|cublas|elementwise|distribution", n)]
+    foreign = sum(ns for _, ns in rows) - sum(ns for _, ns in own)
+    rows = own
     tot = sum(ns for _, ns in rows)
     agg = defaultdict(lambda: [0, 0.0])
     for name, ns in rows:
@@ -27,6 +31,7 @@ def main():
     print("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 3 "
           "--no-cpu-baseline`  \n(cold-cache, serialised per-launch times: compare SHARES, not absolutes; first 400 launches, "
           "including torch's setup fills)\n")
+    print(f"Kernels of torch itself (synthetic pool, fills, the TF32-peak matmul of the bench) are left out: {foreign / 1000:.0f} us.\n")
     print("| kernel | launches | total us | share |\n|---|---|---|---|")
     for name, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         if ns / tot < 0.001:
