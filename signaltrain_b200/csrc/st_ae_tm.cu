@@ -549,7 +549,6 @@ constexpr int BWD_FLUSH_WARP0 = 8;                  // warps 8-11: weight-gradie
 constexpr int BWD_ISSUER = 12;                      // chain MMAs
 constexpr int BWD_WISSUER = 13;                     // weight-gradient MMAs
 constexpr int BWD_THREADS = 14 * 32;
-constexpr int SUB_BYTES = 12288;                    // staging sub-buffer: 48 feature rows x 128 B x (hi, lo)
 // TMEM columns
 constexpr uint32_t TC_AH = 256, TC_AL = 320, TC_D = 384, TC_DW = 448;
 __host__ __device__ constexpr uint32_t tc_act(int l) { constexpr uint32_t t[NL] = {0, 0, 64, 96, 112, 128, 144, 160, 192}; return t[l]; }   // act[1..8]
@@ -559,17 +558,23 @@ __host__ __device__ constexpr uint32_t tc_act(int l) { constexpr uint32_t t[NL] 
 // accumulators of layers >= L + 3 (a flush warp lags the issuer by at most two layers).
 __host__ __device__ constexpr uint32_t tc_dw(int l) { constexpr uint32_t t[NL] = {128, 192, 96, 448, 128, 480, 160, 192, 448}; return t[l]; }
 
+// Shared-memory map of the backward kernel.  The staging area of the weight gradients is four 32 KB regions (one per quadrant
+// of rows) laid over the forward weights AND the dedicated staging bytes behind them: nobody reads the forward weights during
+// the backward half of a tile, so they are copied in again (one 80 KB bulk copy per tile, issued by the weight-gradient issuer
+// once the tile's last slices are consumed) while the next tile's prologue runs.  The small arrays sit in front so that an A
+// tile whose live rows start at a TMEM lane offset (its descriptor starts up to 8 KB before the plane) stays inside the window.
 template <class TB>
 struct BwdSmem {
-    static constexpr uint32_t W_HI = 0, W_LO = 4u * TB::wfloats, STAGE = 8u * TB::wfloats;
-    static constexpr uint32_t WT_HI = STAGE + 4u * SUB_BYTES, WT_LO = WT_HI + 4u * TB::tfloats, BIAS = WT_LO + 4u * TB::tfloats;
-    static constexpr uint32_t VTAIL = BIAS + 4u * ((TB::bfloats + 255) / 256 * 256);
-    static constexpr uint32_t BARS = VTAIL + 4u * XCH_J * TILE;
+    static constexpr uint32_t BIAS = 0, VTAIL = 4u * ((TB::bfloats + 255) / 256 * 256);
+    static constexpr uint32_t W_HI = VTAIL + 4u * XCH_J * TILE, W_LO = W_HI + 4u * TB::wfloats, STAGE = W_LO + 4u * TB::wfloats;
+    static constexpr uint32_t REGION0 = W_HI, REGION_BYTES = 32768;                 // quadrant q stages into [REGION0 + q * 32 KB, + 32 KB)
+    static constexpr uint32_t WT_HI = REGION0 + 4u * REGION_BYTES, WT_LO = WT_HI + 4u * TB::tfloats;
+    static constexpr uint32_t BARS = WT_LO + 4u * TB::tfloats;
     static constexpr uint32_t TOTAL = BARS + 256;
+    static constexpr uint32_t RELOAD_BYTES = 8u * TB::wfloats;                      // the whole forward image
     static_assert(TOTAL <= 227u * 1024u, "backward tile does not fit shared memory");
-    static constexpr uint32_t RELOAD_LO = 16384, RELOAD_BYTES = 4u * SUB_BYTES;     // forward-weight bytes clobbered by staging (quadrants 2, 3)
-    static_assert(RELOAD_LO + RELOAD_BYTES <= STAGE, "the aliased staging buffers must lie inside the forward weights");
-    static_assert(STAGE % 1024 == 0 && WT_HI % 1024 == 0 && WT_LO % 1024 == 0, "operand planes must be 1024-byte aligned");
+    static_assert(STAGE <= WT_HI && REGION0 >= 64u * 128u, "staging regions must cover the forward weights and leave room below");
+    static_assert(W_HI % 1024 == 0 && W_LO % 1024 == 0 && WT_HI % 1024 == 0 && WT_LO % 1024 == 0, "operand planes must be 1024-byte aligned");
 };
 
 __device__ __forceinline__ void umma_ss_lohi(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t desc_hi, uint32_t idesc,
@@ -621,26 +626,41 @@ __device__ __forceinline__ void issue_dgrad_layer(uint32_t dlo_base) {
                                                 dlo_base + ((BwdSmem<TB>::WT_LO + 4u * TB::toff(L)) >> 4));
 }
 
-// Staging geometry of layer L's weight-gradient slice (one quadrant = 32 rows): byte offsets inside the slice buffer.
+// Staging geometry of layer L's weight-gradient slice (one quadrant = 32 rows) inside the quadrant's 32 KB region, in units of
+// one feature = 256 bytes (a 128-byte K-major row of the hi plane + one of the lo plane; the two planes of an operand are
+// stacked [hi ; lo], which is what the single-MMA formulation reads).  act[L] is staged ONE LAYER AHEAD (while layer L + 1's
+// MMAs run), so its block must not touch layer L + 1's blocks: even layers keep act at the bottom of the region, odd layers at
+// the top; gz[L] (written once layer L + 1 is consumed) only has to avoid act[L] and act[L - 1].
+__host__ __device__ constexpr int stg_act_row(int l) { constexpr int t[NL] = {0, 64, 0, 112, 0, 112, 0, 96, 0}; return t[l]; }
+__host__ __device__ constexpr int stg_gz_row(int l) { constexpr int t[NL] = {32, 32, 32, 32, 32, 32, 16, 32, 64}; return t[l]; }
 template <class TB, int L>
 struct Stg {
     static constexpr int MF = TB::wg_mf(L), NF = TB::wg_nf(L);
-    static constexpr uint32_t M_HI = 0, M_LO = MF * 128u, N_HI = 2u * MF * 128u, N_LO = N_HI + NF * 128u;
     static constexpr bool M_IS_GZ = TB::wg_m_is_gz(L);
-    static constexpr uint32_t GZ_HI = M_IS_GZ ? M_HI : N_HI, GZ_LO = M_IS_GZ ? M_LO : N_LO;
-    static constexpr uint32_t ACT_HI = M_IS_GZ ? N_HI : M_HI, ACT_LO = M_IS_GZ ? N_LO : M_LO;
-    // Quadrants q and q + 2 share the 24 KB buffer (q & 1) and alternate strictly (q first): barriers are per QUADRANT
-    // (full[q]: slice written, free[q]: slice consumed), so every waiter observes every phase of the barrier it waits on
-    // (an mbarrier parity wait cannot tell phase k from phase k + 2).
-    // A private 24 KB buffer per quadrant.  Quadrants 0 and 1 use the staging region; quadrants 2 and 3 use bytes [16 KB, 64 KB)
-    // of the FORWARD weights, which nobody reads during the backward half of a tile -- that part of the image is copied in
-    // again (one bulk copy, issued by the weight-gradient issuer once its last MMAs of the tile are done) while the next
-    // tile's prologue runs.  (Shared memory has no room for four buffers beside both weight images.)
-    __host__ __device__ static constexpr uint32_t buf(int q) {
-        return q < 2 ? BwdSmem<TB>::STAGE + (uint32_t)q * 2u * SUB_BYTES : BwdSmem<TB>::RELOAD_LO + (uint32_t)(q - 2) * 2u * SUB_BYTES;
-    }
-    static_assert((MF + NF) * 256 <= 2 * SUB_BYTES, "slice does not fit its staging buffer");
+    static constexpr int GZ_W = TB::n(L), ACT_W = M_IS_GZ ? NF : MF;
+    static constexpr uint32_t GZ_HI = stg_gz_row(L) * 256u, GZ_LO = GZ_HI + GZ_W * 128u;
+    static constexpr uint32_t ACT_HI = stg_act_row(L) * 256u, ACT_LO = ACT_HI + ACT_W * 128u;
+    static constexpr uint32_t M_HI = M_IS_GZ ? GZ_HI : ACT_HI, M_LO = M_IS_GZ ? GZ_LO : ACT_LO;
+    static constexpr uint32_t N_HI = M_IS_GZ ? ACT_HI : GZ_HI, N_LO = M_IS_GZ ? ACT_LO : GZ_LO;
+    __host__ __device__ static constexpr uint32_t buf(int q) { return BwdSmem<TB>::REGION0 + (uint32_t)q * BwdSmem<TB>::REGION_BYTES; }
+    static_assert(stg_act_row(L) + ACT_W <= 128 && stg_gz_row(L) + GZ_W <= 128, "block outside the region");
+    static_assert(stg_act_row(L) + ACT_W <= stg_gz_row(L) || stg_gz_row(L) + GZ_W <= stg_act_row(L), "act[L] and gz[L] overlap");
+    static_assert((M_IS_GZ ? MF : NF) == GZ_W, "gz width");
 };
+// act[L - 1] (staged ahead) must not touch layer L's blocks, and gz[L - 1] must not touch act[L - 2]
+template <class TB, int L>
+__host__ __device__ constexpr bool stg_ahead_ok() {
+    if constexpr (L == 0) return true;
+    else {
+        using A = Stg<TB, L>;
+        using P = Stg<TB, L - 1>;
+        constexpr int a0 = stg_act_row(L - 1), a1 = a0 + P::ACT_W;
+        constexpr bool vs_act = a1 <= stg_act_row(L) || stg_act_row(L) + A::ACT_W <= a0;
+        constexpr bool vs_gz = a1 <= stg_gz_row(L) || stg_gz_row(L) + A::GZ_W <= a0;
+        constexpr bool gz_vs_next_act = stg_gz_row(L) + A::GZ_W <= a0 || a1 <= stg_gz_row(L);
+        return vs_act && vs_gz && gz_vs_next_act && stg_ahead_ok<TB, L - 1>();
+    }
+}
 
 // weight-gradient MMAs of layer L for one 32-row slice (4 k-steps); `dlo_buf` = descriptor low word of the quadrant's buffer.
 // The quadrant is a run-time value (the loop over quadrants stays rolled: the kernel's code must stay small, its instruction
@@ -651,7 +671,7 @@ __device__ __forceinline__ void issue_wgrad_slice(uint32_t dlo_buf, uint32_t fir
     constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * S::NF >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
     constexpr uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::NF >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
     constexpr uint32_t moff = (uint32_t)TB::wg_moff(L) * 128u;
-    static_assert(S::buf(0) + S::M_HI >= moff && S::buf(2) + S::M_HI >= moff, "the A tile must start inside shared memory");
+    static_assert(S::buf(0) + S::M_HI + 0u >= moff + 0u, "the A tile must start inside shared memory");
     static_assert(S::M_LO == S::M_HI + S::MF * 128u && S::N_LO == S::N_HI + S::NF * 128u, "the (hi, lo) planes must be stacked");
     static_assert(S::MF % 8 == 0 && S::NF % 8 == 0, "planes must start on a swizzle period");
     const uint32_t a_hi = dlo_buf + (S::M_HI >> 4) - (moff >> 4), a_lo = dlo_buf + (S::M_LO >> 4) - (moff >> 4), b_hi = dlo_buf + (S::N_HI >> 4);
@@ -721,7 +741,7 @@ __device__ __forceinline__ void bwd_stage_gz(uint8_t* smem_raw, uint32_t lane_of
     const int i = it * NL + (NL - 1 - L);                    // this quadrant's fill count = phase index of its barriers
     if (i > 0) mbar_wait_spin(&freeb[q], (uint32_t)((i - 1) & 1));
     HB(1)
-    uint8_t* buf = smem_raw + (q < 2 ? BwdSmem<TB>::STAGE + (uint32_t)q * 2u * SUB_BYTES : BwdSmem<TB>::RELOAD_LO + (uint32_t)(q - 2) * 2u * SUB_BYTES);
+    uint8_t* buf = smem_raw + BwdSmem<TB>::REGION0 + (uint32_t)q * BwdSmem<TB>::REGION_BYTES;
 #pragma unroll
     for (int c = 0; c < NLOC; ++c) stage_put(buf + S::GZ_HI, buf + S::GZ_LO, c0 + c, lane_off, ghi[c], glo[c]);
     if constexpr (L == 0) {
@@ -807,6 +827,7 @@ template <class TB, bool DBG>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
     static_assert(TB::KP1 == 32, "backward kernel: T <= 32");
+    static_assert(stg_ahead_ok<TB, NL - 1>(), "act[L - 1] is staged while layer L's slice is live: the blocks must be disjoint");
     using SM = BwdSmem<TB>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     float* bias = reinterpret_cast<float*>(smem_raw + SM::BIAS);
@@ -815,14 +836,16 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
     uint64_t* a_ready = bars;            // chain warps -> chain issuer (count 8)
     uint64_t* d_ready = bars + 1;        // chain issuer -> chain warps
     uint64_t* w_ready = bars + 2;        // weight image landed
-    uint64_t* full = bars + 3;           // [4] slice written (count 3: the two column halves of the quadrant + its flush warp)
-    uint64_t* freeb = bars + 7;          // [4] staging sub-buffer consumed (count 2: weight-gradient MMAs + bias-gradient reader)
+    uint64_t* full = bars + 3;           // [4] gz[L] of the quadrant's slice written (count 2: the two column halves)
+    uint64_t* freeb = bars + 7;          // [4] slice consumed (count 2: weight-gradient MMAs + bias-gradient reader)
     uint64_t* flushed = bars + 11;       // flush warps -> chain warps: every accumulator of the tile has been read (count 4), once per tile
+    uint64_t* fwd_done = bars + 12;      // chain warps -> flush warps: the tile's forward chain is complete (count 8), once per tile
+    uint64_t* w_reload = bars + 13;      // the forward weights the staging regions overwrote are back (once per tile)
     uint64_t* dw_ready = bars + 16;      // [4] ring: weight-gradient issuer -> flush warps: the layer's accumulator is complete (the
                                          // issuer may run two layers ahead of a flush warp; a parity wait cannot tell phase k from k + 2)
-    uint64_t* w_reload = bars + 13;      // the forward-weight bytes the staging of quadrants 2, 3 overwrote are back (once per tile)
-    uint64_t* fwd_done = bars + 12;      // chain warps -> flush warps: the tile's forward chain is complete (count 8), once per tile
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* afull = bars + 20;         // [4][2] act[L] of the quadrant's slice written by its flush warp (count 1), ring over the
+                                         // parity of L: the flush warp stages one layer ahead of the issuer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -830,16 +853,19 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
     constexpr int IMGF = bwd_image_floats<TB>();
     if (threadIdx.x == 0) {
         mbar_init(a_ready, BWD_CHAIN_WARPS); mbar_init(d_ready, 1); mbar_init(w_ready, 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 3); mbar_init(&freeb[i], 2); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 2); mbar_init(&freeb[i], 2); }
+        for (int i = 0; i < 8; ++i) mbar_init(&afull[i], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&dw_ready[i], 1);
         mbar_init(flushed, 4); mbar_init(w_reload, 1); mbar_init(fwd_done, BWD_CHAIN_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint8_t* img = reinterpret_cast<const uint8_t*>(a.image + (long)ae * IMGF);
-        constexpr uint32_t WB = 8u * TB::wfloats, TBY = 8u * TB::tfloats + 4u * ((TB::bfloats + 255) / 256 * 256);
-        mbar_expect_tx(w_ready, WB + TBY);
+        constexpr uint32_t WB = 8u * TB::wfloats, TBY = 8u * TB::tfloats, BB = 4u * TB::bfloats;
+        static_assert(BB % 16 == 0, "bulk copies move multiples of 16 bytes");
+        mbar_expect_tx(w_ready, WB + TBY + BB);
         constexpr uint32_t CHUNK = 32768;
         for (uint32_t o = 0; o < WB; o += CHUNK) bulk_g2s(smem_raw + SM::W_HI + o, img + o, (WB - o) < CHUNK ? (WB - o) : CHUNK, w_ready);
         for (uint32_t o = 0; o < TBY; o += CHUNK) bulk_g2s(smem_raw + SM::WT_HI + o, img + WB + o, (TBY - o) < CHUNK ? (TBY - o) : CHUNK, w_ready);
+        bulk_g2s(smem_raw + SM::BIAS, img + WB + TBY, BB, w_ready);
     }
     if (warp == BWD_ISSUER) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -869,33 +895,36 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
         }
     } else if (warp == BWD_WISSUER) {
         // ======================= weight-gradient MMAs: per layer 8..0, the four 32-row slices into one accumulator ===========
-        int nl = 0;                                          // layers issued so far = phase index of full[] / free[] / dw_*
+        int nl = 0, it = 0;                                  // layers issued so far = phase index of full[] / free[] / dw_*
         for (int tile = slot; tile < ntiles; tile += nslot) {
 #define ST_WL(L)                                                                                            \
             _Pragma("unroll 1")                                                                             \
             for (int qq = 0; qq < 4; ++qq) {                                                                \
+                mbar_wait_spin(&afull[2 * qq + ((L) & 1)], (uint32_t)(((L) & 1 ? 4 * it + (7 - (L)) / 2 : 5 * it + (8 - (L)) / 2) & 1)); \
                 mbar_wait_spin(&full[qq], (uint32_t)(nl & 1));                                              \
                 tc_fence_after();                                                                           \
-                const uint32_t boff = qq < 2 ? SM::STAGE + (uint32_t)qq * 2u * SUB_BYTES : SM::RELOAD_LO + (uint32_t)(qq - 2) * 2u * SUB_BYTES; \
-                issue_wgrad_slice<TB, L>(dlo_base + (boff >> 4), qq > 0 ? 1u : 0u);                          \
+                issue_wgrad_slice<TB, L>(dlo_base + ((SM::REGION0 + (uint32_t)qq * SM::REGION_BYTES) >> 4), qq > 0 ? 1u : 0u); \
                 umma_commit_elect(&freeb[qq]);                                                              \
             }                                                                                               \
             umma_commit_elect(&dw_ready[nl & 3]);                                                           \
             ++nl;
             ST_WL(8) ST_WL(7) ST_WL(6) ST_WL(5) ST_WL(4) ST_WL(3) ST_WL(2) ST_WL(1) ST_WL(0)
             if (tile + nslot < ntiles) {
-                // the last slices of quadrants 2 and 3 have been consumed: put the forward weights they overwrote back
+                // the tile's last slices have been consumed: put the forward weights the staging regions overwrote back
+                mbar_wait_spin(&freeb[0], (uint32_t)((nl - 1) & 1));
+                mbar_wait_spin(&freeb[1], (uint32_t)((nl - 1) & 1));
                 mbar_wait_spin(&freeb[2], (uint32_t)((nl - 1) & 1));
-                mbar_wait_spin(&freeb[3], (uint32_t)((nl - 1) & 1));
                 fence_async_smem();
                 if (lane == 0) {
                     const uint8_t* img = reinterpret_cast<const uint8_t*>(a.image + (long)ae * IMGF);
                     mbar_expect_tx(w_reload, SM::RELOAD_BYTES);
-                    bulk_g2s(smem_raw + SM::RELOAD_LO, img + SM::RELOAD_LO, SM::RELOAD_BYTES / 2, w_reload);
-                    bulk_g2s(smem_raw + SM::RELOAD_LO + SM::RELOAD_BYTES / 2, img + SM::RELOAD_LO + SM::RELOAD_BYTES / 2, SM::RELOAD_BYTES / 2, w_reload);
+                    constexpr uint32_t CHUNK = 32768;
+                    for (uint32_t o = 0; o < SM::RELOAD_BYTES; o += CHUNK)
+                        bulk_g2s(smem_raw + SM::W_HI + o, img + o, (SM::RELOAD_BYTES - o) < CHUNK ? (SM::RELOAD_BYTES - o) : CHUNK, w_reload);
                 }
                 __syncwarp();
             }
+            ++it;
 #undef ST_WL
         }
     } else if (warp >= BWD_FLUSH_WARP0) {
@@ -904,7 +933,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
         const int glane = 32 * q + lane;                     // TMEM lane = feature row of the M operand (+ its lane offset)
         const uint32_t t_lq = (uint32_t)(32 * q) << 16;
         const uint32_t lane_off = ((uint32_t)(lane >> 2) << 4) | ((uint32_t)(lane & 3) << 2);
-        uint8_t* const qbuf = smem_raw + (q < 2 ? SM::STAGE + (uint32_t)q * 2u * SUB_BYTES : SM::RELOAD_LO + (uint32_t)(q - 2) * 2u * SUB_BYTES);
+        uint8_t* const qbuf = smem_raw + SM::REGION0 + (uint32_t)q * SM::REGION_BYTES;
         float acc[TB::wg_regs];
         float dbacc[11];                                     // bias-gradient sums: lane = feature, one register per 32 features of a layer
 #pragma unroll
@@ -925,7 +954,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
             stage_act<TB, NL - 1>(qbuf, t_lq, lane_off, a.knobs, knob_off, nk);
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[q]);
+            if (lane == 0) mbar_arrive(&afull[2 * q]);
 #define ST_FL(L, DBSLOT)                                                                                              \
             {                                                                                                          \
                 using S = Stg<TB, L>;                                                                                  \
@@ -937,14 +966,14 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 }                                                                                                      \
                 __syncwarp();                                                                                          \
                 if (lane == 0) mbar_arrive(&freeb[q]);                                                                 \
-                /* next layer's act into the same buffer as soon as this layer's MMAs have read it */                  \
+                /* the next layer's act, one layer ahead: its block is disjoint from this layer's, and what it overwrites */ \
+                /* (layer L + 1) was consumed before the chain warps could write the gz this warp has just read        */ \
                 if constexpr ((L) > 1) {                                                                               \
-                    mbar_wait_spin(&freeb[q], (uint32_t)(nl & 1));                                                     \
                     stage_act<TB, ((L) > 1 ? (L) - 1 : 1)>(qbuf, t_lq, lane_off, a.knobs, knob_off, nk);               \
                     fence_async_smem();                                                                                \
                     __syncwarp();                                                                                      \
                 }                                                                                                      \
-                if constexpr ((L) > 0) { if (lane == 0) mbar_arrive(&full[q]); }                                       \
+                if constexpr ((L) > 0) { if (lane == 0) mbar_arrive(&afull[2 * q + (((L) - 1) & 1)]); }                \
                 mbar_wait_spin(&dw_ready[nl & 3], (uint32_t)(nl >> 2) & 1u);                                           \
                 tc_fence_after();                                                                                      \
                 constexpr int MO = TB::wg_moff(L), MF = S::MF, NF = S::NF, RG = TB::wg_reg(L);                         \
@@ -1000,6 +1029,7 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
 #undef ST_WR
         // bias gradients: the four flush warps hold the sums of their own quadrant's rows -> add through shared memory
         float* dbs = reinterpret_cast<float*>(smem_raw + SM::STAGE);          // staging is idle now: [4][11][32]
+        static_assert(SM::STAGE + 4u * 11u * 32u * 4u <= SM::WT_HI, "bias-gradient exchange must fit the dedicated staging bytes");
 #pragma unroll
         for (int i = 0; i < 11; ++i) dbs[(q * 11 + i) * 32 + lane] = dbacc[i];
         asm volatile("bar.sync 2, 128;" ::: "memory");
