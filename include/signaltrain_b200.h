@@ -195,6 +195,17 @@ int st_grad_step(st_handle* h, const float* x, const float* y, const float* knob
 long st_packed_grad_floats(const st_handle* h);
 int st_pack_grads(st_handle* h, float* const* grads, float* packed, void* stream);
 int st_unpack_grads(st_handle* h, const float* packed, float* const* grads, void* stream);
+/* The data-parallel step in three calls around ONE collective: st_grad_step_packed = st_grad_step whose gradients leave directly
+ * as the packed payload (no 40-tensor materialisation, no pack pass); [allreduce-sum of `packed`]; st_unpack_clip = st_unpack_grads
+ * fused with the L1 norm of the four restored DFT tensors times grad_scale and the clip coefficient min(1, max_norm / (norm + 1e-6))
+ * (nn_proc.py:299-302; total_norm may be NULL); st_adam_step_clipped = st_adam_step that uses that coefficient and skips the
+ * analysis rows >= F, whose gradient is identically zero (cls_fe_dft.py:55-56). */
+int st_grad_step_packed(st_handle* h, const float* x, const float* y, const float* knobs, int batch, float* const* params,
+                        float* packed, const float* scale_by_freq, float l1_coef, float* loss, void* stream);
+int st_unpack_clip(st_handle* h, const float* packed, float* const* grads, float grad_scale, float max_norm, float* total_norm,
+                   void* stream);
+int st_adam_step_clipped(st_handle* h, float* const* params, const float* const* grads, float* const* exp_avg,
+                         float* const* exp_avg_sq, const st_adam* hp, void* stream);
 
 /* Measurement support (bench.py): number of kernels / device copies this handle has launched, and per-stage
  * device time bracketed with CUDA events on the launching stream.  st_profile_read synchronises the device,

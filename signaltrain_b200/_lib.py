@@ -76,6 +76,12 @@ _SIGNATURES = {
     "st_packed_grad_floats": (ctypes.c_long, [ctypes.c_void_p]),
     "st_pack_grads": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_float_p, ctypes.c_void_p]),
     "st_unpack_grads": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "st_grad_step_packed": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p,
+                                           c_float_p, c_float_p, ctypes.c_float, c_float_p, ctypes.c_void_p]),
+    "st_unpack_clip": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_float, c_float_p,
+                                      ctypes.c_void_p]),
+    "st_adam_step_clipped": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.POINTER(StAdam), ctypes.c_void_p]),
     "st_debug_fallbacks": (ctypes.c_long, [ctypes.c_void_p]),
     "st_debug_ae_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]),
     "st_debug_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, c_float_p, ctypes.c_long,

@@ -611,9 +611,13 @@ extern "C" int st_mae(st_handle* h, const float* a, const float* b, long n, floa
 // gwave_ready (st_train_step / st_grad_step): gwave already holds the padded 2*dL/dy_hat, written by the fused forward tail.
 // fused_clip (st_train_step only): the final DFT-gradient pass also produces the L1 norm / clip coefficient for the Adam launch
 // that follows.
+static long packed_grad_floats(const st_handle* h, int* ae_off);
+
+// packed (st_grad_step_packed): the gradients leave as the data-parallel exchange payload instead of the 40 tensors -- the
+// final DFT pass writes the live rows only, the autoencoder partial sums land in their payload slots; `grads` is not touched.
 static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag, const float* g_mag_hat, int B,
                          const float* const* params, float* const* grads, cudaStream_t s, int phase = 0,
-                         bool gwave_ready = false, const st_adam* fused_clip = nullptr) {
+                         bool gwave_ready = false, const st_adam* fused_clip = nullptr, float* packed = nullptr) {
     const StDims& d = h->d;
     if (B != h->fwdB || B > h->maxB)
         return st_fail_msg(h, "st_backward: batch %d does not match the preceding st_forward (%d)", B, h->fwdB);
@@ -696,9 +700,19 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         cudaStream_t sr = beside ? h->side : s;
         StageScope sc(h, SG_AE_REDUCE, 1, s);
         AeGrads gm, gp;
-        for (int l = 0; l < ST_AE_LAYERS; ++l) {
-            gm.W[l] = grads[4 + 2 * l];  gm.b[l] = grads[5 + 2 * l];
-            gp.W[l] = grads[22 + 2 * l]; gp.b[l] = grads[23 + 2 * l];
+        if (packed) {
+            int ae_off[ST_NUM_PARAMS - 4];
+            packed_grad_floats(h, ae_off);
+            float* base = packed + 4L * d.F * d.N;
+            for (int l = 0; l < ST_AE_LAYERS; ++l) {
+                gm.W[l] = base + ae_off[2 * l];       gm.b[l] = base + ae_off[2 * l + 1];
+                gp.W[l] = base + ae_off[18 + 2 * l];  gp.b[l] = base + ae_off[19 + 2 * l];
+            }
+        } else {
+            for (int l = 0; l < ST_AE_LAYERS; ++l) {
+                gm.W[l] = grads[4 + 2 * l];  gm.b[l] = grads[5 + 2 * l];
+                gp.W[l] = grads[22 + 2 * l]; gp.b[l] = grads[23 + 2 * l];
+            }
         }
         if (beside) {
             ST_CUDA_OK(cudaEventRecord(h->ev_fork, s));
@@ -724,7 +738,9 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
     ST_LAUNCH_OK(h);
     {
         StageScope sc(h, SG_FINALIZE, 1, s);
-        if (fused_clip && phase == 0)
+        if (packed)
+            st_launch_finalize_packed(d, h->part_a, h->part_s, sa, ss, packed, s);
+        else if (fused_clip && phase == 0)
             st_launch_finalize_norm(d, h->part_a, h->part_s, sa, ss, grads[0], grads[1], grads[2], grads[3], fused_clip->grad_scale,
                                     fused_clip->max_norm, h->small + SM_TOTAL_NORM, h->small + SM_COEF, h->small + SM_NORM,
                                     h->counters + CT_NORM, s);
@@ -840,7 +856,8 @@ extern "C" int st_adam_step(st_handle* h, float* const* params, const float* con
 // padded (hi, lo) 2*dL/dy_hat operand; then the whole backward.  With fused_clip the last DFT-gradient pass also yields the
 // clip coefficient (single-GPU step); without it the gradients are left for the caller's allreduce.
 static int grad_step_impl(st_handle* h, const float* x, const float* y, const float* knobs, int batch, float* const* params,
-                          float* const* grads, const float* sbf, float l1_coef, float* loss, cudaStream_t s, const st_adam* fused_clip) {
+                          float* const* grads, const float* sbf, float l1_coef, float* loss, cudaStream_t s, const st_adam* fused_clip,
+                          float* packed = nullptr) {
     if (forward_impl(h, x, knobs, batch, params, nullptr, nullptr, nullptr, nullptr, s)) return 1;
     {
         StageScope sc(h, SG_LOSS, 1, s);
@@ -848,7 +865,7 @@ static int grad_step_impl(st_handle* h, const float* x, const float* y, const fl
                            h->small + SM_LOSS, h->counters + CT_LOSS, s);
     }
     ST_LAUNCH_OK(h);
-    return backward_impl(h, h->gy_ws, nullptr, h->gmh_ws, batch, params, grads, s, 0, /*gwave_ready=*/true, fused_clip);
+    return backward_impl(h, h->gy_ws, nullptr, h->gmh_ws, batch, params, grads, s, 0, /*gwave_ready=*/true, fused_clip, packed);
 }
 
 extern "C" int st_grad_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch, float* const* params,
@@ -901,6 +918,53 @@ extern "C" int st_unpack_grads(st_handle* h, const float* packed, float* const* 
     if (!h) return 1;
     ST_ON_DEVICE(h);
     return pack_impl(h, grads, const_cast<float*>(packed), 1, (cudaStream_t)stream);
+}
+
+extern "C" int st_grad_step_packed(st_handle* h, const float* x, const float* y, const float* knobs, int batch, float* const* params,
+                                   float* packed, const float* sbf, float l1_coef, float* loss, void* stream) {
+    if (!h) return 1;
+    ST_ON_DEVICE(h);
+    if (!x || !y || !knobs || !loss || !packed) return st_fail_msg(h, "st_grad_step_packed: null argument");
+    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_grad_step_packed(params)")) return 1;
+    if (ensure_workspace(h, batch)) return 1;
+    return grad_step_impl(h, x, y, knobs, batch, params, nullptr, sbf, l1_coef, loss, (cudaStream_t)stream, nullptr, packed);
+}
+
+extern "C" int st_unpack_clip(st_handle* h, const float* packed, float* const* grads, float grad_scale, float max_norm,
+                              float* total_norm, void* stream) {
+    if (!h) return 1;
+    ST_ON_DEVICE(h);
+    if (check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_unpack_clip(grads)")) return 1;
+    if (!packed) return st_fail_msg(h, "st_unpack_clip: null packed buffer");
+    GradPack gp;
+    for (int t = 0; t < ST_NUM_PARAMS; ++t) gp.g[t] = grads[t];
+    gp.packed = const_cast<float*>(packed);
+    gp.live = (long)h->d.F * h->d.N;
+    gp.N = h->d.N;
+    packed_grad_floats(h, gp.ae_off);
+    for (int t = 4; t < ST_NUM_PARAMS; ++t) gp.ae_n[t - 4] = (int)h->numel[t];
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+        StageScope sc(h, SG_L1NORM, 1, s);
+        st_launch_unpack_clip(gp, grad_scale, max_norm, total_norm ? total_norm : h->small + SM_TOTAL_NORM, h->small + SM_COEF,
+                              h->small + SM_NORM, h->counters + CT_NORM, s);
+    }
+    ST_LAUNCH_OK(h);
+    return 0;
+}
+
+extern "C" int st_adam_step_clipped(st_handle* h, float* const* params, const float* const* grads, float* const* exp_avg,
+                                    float* const* exp_avg_sq, const st_adam* hp, void* stream) {
+    if (!h) return 1;
+    ST_ON_DEVICE(h);
+    if (!hp) return st_fail_msg(h, "st_adam_step_clipped: null hyper-parameters");
+    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_adam_step_clipped(params)") ||
+        check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_adam_step_clipped(grads)") ||
+        check_ptrs(h, (const void* const*)exp_avg, ST_NUM_PARAMS, "st_adam_step_clipped(exp_avg)") ||
+        check_ptrs(h, (const void* const*)exp_avg_sq, ST_NUM_PARAMS, "st_adam_step_clipped(exp_avg_sq)"))
+        return 1;
+    // the clip coefficient is the one st_unpack_clip left in the handle; rows >= F of the analysis tensors never change
+    return adam_impl(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/true, (cudaStream_t)stream, /*coef_ready=*/true);
 }
 
 extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch,

@@ -204,6 +204,9 @@ struct GradPack {
     int ae_n[ST_NUM_PARAMS - 4];
 };
 void st_launch_pack_grads(const GradPack& gp, int dir, cudaStream_t s);
+void st_launch_unpack_clip(const GradPack& gp, float grad_scale, float max_norm, float* norm_out, float* coef_out, float* scratch,
+                           unsigned* counter, cudaStream_t s);
+void st_launch_finalize_packed(const StDims& d, const float* pa, const float* ps, int sa, int ss, float* packed, cudaStream_t s);
 
 struct AdamTensors {
     float* p[ST_NUM_PARAMS];

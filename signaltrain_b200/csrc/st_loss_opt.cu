@@ -423,6 +423,86 @@ pack_grads_kernel(GradPack gp, int dir /*0: pack, 1: unpack*/) {
 
 void st_launch_pack_grads(const GradPack& gp, int dir, cudaStream_t s) { pack_grads_kernel<<<148 * 4, 256, 0, s>>>(gp, dir); }
 
+// Unpack (as above, dir = 1) fused with the L1 norm of the four unpacked DFT tensors and the clip coefficient
+// (nn_proc.py:299-302) for the Adam launch that follows: mirrored synthesis rows count twice, like the tensors they restore.
+__global__ void __launch_bounds__(256)
+unpack_clip_kernel(GradPack gp, float grad_scale, float max_norm, float* __restrict__ norm_out, float* __restrict__ coef_out,
+                   float* scratch, unsigned* counter) {
+    const long live4 = gp.live / 4;
+    const long stride = (long)gridDim.x * blockDim.x;
+    float acc[1] = {0.f};
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < 4 * live4; i += stride) {
+        const int t = (int)(i / live4);
+        const long e = i - t * live4;
+        const float4 v = *(reinterpret_cast<const float4*>(gp.packed + t * gp.live) + e);
+        *(reinterpret_cast<float4*>(gp.g[t]) + e) = v;
+        float mult = 1.f;
+        if (t >= 2) {
+            const long row = (e * 4) / gp.N, col4 = e - row * (gp.N / 4);
+            if (row >= 1 && row < gp.N / 2) {
+                float4* m = reinterpret_cast<float4*>(gp.g[t]) + (gp.N - row) * (gp.N / 4) + col4;
+                *m = t == 2 ? v : make_float4(-v.x, -v.y, -v.z, -v.w);
+                mult = 2.f;
+            }
+        }
+        acc[0] += mult * ((fabsf(v.x) + fabsf(v.y)) + (fabsf(v.z) + fabsf(v.w)));
+    }
+    for (int t = 4 + blockIdx.x; t < ST_NUM_PARAMS; t += gridDim.x) {
+        float* full = gp.g[t];
+        const float* pk = gp.packed + 4 * gp.live + gp.ae_off[t - 4];
+        for (int e = threadIdx.x; e < gp.ae_n[t - 4]; e += blockDim.x) full[e] = pk[e];
+    }
+    grid_finish<1>(acc, scratch, counter, [&](const double* s) {
+        const double total_norm = s[0] * (double)grad_scale;
+        if (norm_out) norm_out[0] = (float)total_norm;
+        float cf = 1.f;
+        if (max_norm > 0.f) {
+            const double cc = (double)max_norm / (total_norm + 1e-6);
+            cf = cc < 1.0 ? (float)cc : 1.f;
+        }
+        coef_out[0] = cf;
+    });
+}
+void st_launch_unpack_clip(const GradPack& gp, float grad_scale, float max_norm, float* norm_out, float* coef_out, float* scratch,
+                           unsigned* counter, cudaStream_t s) {
+    unpack_clip_kernel<<<148 * 4, 256, 0, s>>>(gp, grad_scale, max_norm, norm_out, coef_out, scratch, counter);
+}
+
+// Split-K sum of the DFT gradient planes straight into the packed exchange payload: rows k < F of the four tensors only (no
+// dead analysis rows, no mirrored synthesis rows -- the unpack restores those after the allreduce).
+__global__ void __launch_bounds__(256)
+finalize_packed_kernel(StDims d, const float* __restrict__ pa, const float* __restrict__ ps, int sa, int ss, float* __restrict__ packed) {
+    const int n4 = d.N >> 2;
+    const long plane = 2L * d.Fp * d.N, live = (long)d.F * d.N;
+    const long total = (long)d.F * n4;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / n4);
+        const int c = (int)(i - (long)k * n4) << 2;
+        const long o = (long)k * d.N + c;
+        float4 ar = z4, ai = z4, sr = z4, si = z4;
+        for (int s = 0; s < sa; ++s) {
+            const float4 a = *reinterpret_cast<const float4*>(pa + s * plane + (long)k * d.N + c);
+            const float4 b = *reinterpret_cast<const float4*>(pa + s * plane + (long)(d.Fp + k) * d.N + c);
+            ar.x += a.x; ar.y += a.y; ar.z += a.z; ar.w += a.w;
+            ai.x += b.x; ai.y += b.y; ai.z += b.z; ai.w += b.w;
+        }
+        for (int s = 0; s < ss; ++s) {
+            const float4 a = *reinterpret_cast<const float4*>(ps + s * plane + (long)k * d.N + c);
+            const float4 b = *reinterpret_cast<const float4*>(ps + s * plane + (long)(d.Fp + k) * d.N + c);
+            sr.x += a.x; sr.y += a.y; sr.z += a.z; sr.w += a.w;
+            si.x += b.x; si.y += b.y; si.z += b.z; si.w += b.w;
+        }
+        *reinterpret_cast<float4*>(packed + o) = ar;
+        *reinterpret_cast<float4*>(packed + live + o) = ai;
+        *reinterpret_cast<float4*>(packed + 2 * live + o) = sr;
+        *reinterpret_cast<float4*>(packed + 3 * live + o) = si;
+    }
+}
+void st_launch_finalize_packed(const StDims& d, const float* pa, const float* ps, int sa, int ss, float* packed, cudaStream_t s) {
+    finalize_packed_kernel<<<148 * 4, 256, 0, s>>>(d, pa, ps, sa, ss, packed);
+}
+
 void st_launch_adam(const AdamTensors& t, const int2* chunk_map, int nchunks, const AdamScalars& sc, const float* clip_coef,
                     cudaStream_t s) {
     adam_kernel<<<nchunks, 256, 0, s>>>(t, chunk_map, sc, clip_coef);

@@ -341,6 +341,33 @@ class Engine:
         _check(packed, "packed", (self.packed_grad_floats(),), self.device)
         self._ok(self.lib.st_unpack_grads(self.h, _ptr(packed), self.table(grads, "grads"), self._stream()), "st_unpack_grads")
 
+    def grad_step_packed(self, x, y, knobs, params, packed, sbf, l1_coef, loss_out=None):
+        """st_grad_step whose gradients leave directly as the packed data-parallel payload (st_grad_step_packed)."""
+        g = self.g
+        B = x.shape[0]
+        _check(x, "x", (B, g.C), self.device)
+        _check(y, "y", (B, g.L), self.device)
+        _check(knobs, "knobs", (B, g.K), self.device)
+        _check(packed, "packed", (self.packed_grad_floats(),), self.device)
+        if sbf is not None:
+            _check(sbf, "scale_by_freq", (g.F,), self.device)
+        loss = loss_out if loss_out is not None else torch.empty((), device=self.device, dtype=torch.float32)
+        self._ok(self.lib.st_grad_step_packed(self.h, _ptr(x), _ptr(y), _ptr(knobs), B, self.table(params, "params"), _ptr(packed),
+                                              _ptr(sbf), float(l1_coef), _ptr(loss), self._stream()), "st_grad_step_packed")
+        return loss
+
+    def unpack_clip(self, packed, grads, grad_scale, max_norm, total_norm=None):
+        """Scatter the reduced payload back into the 40 gradient tensors and leave the L1 clip coefficient of the four DFT
+        tensors (times grad_scale) in the engine for adam_step_clipped (st_unpack_clip)."""
+        _check(packed, "packed", (self.packed_grad_floats(),), self.device)
+        self._ok(self.lib.st_unpack_clip(self.h, _ptr(packed), self.table(grads, "grads"), float(grad_scale), float(max_norm),
+                                         _ptr(total_norm), self._stream()), "st_unpack_clip")
+
+    def adam_step_clipped(self, params, grads, exp_avg, exp_avg_sq, hp):
+        self._ok(self.lib.st_adam_step_clipped(self.h, self.table(params, "params"), self.table(grads, "grads"),
+                                               self.table(exp_avg, "exp_avg"), self.table(exp_avg_sq, "exp_avg_sq"),
+                                               ctypes.byref(hp), self._stream()), "st_adam_step_clipped")
+
     def launch_count(self):
         return int(self.lib.st_launch_count(self.h))
 

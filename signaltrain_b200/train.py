@@ -84,12 +84,21 @@ class FusedTrainer:
                 scale = self.reducer.finish()
             elif mode == "packed":                # default: st_grad_step, then ONE allreduce of the packed payload (8.5 MB: analysis
                 # rows >= F are zero and the synthesis pair is Hermitian), scattered back by st_unpack_grads
-                loss = eng.grad_step(x, y, knobs, self.params, self.grads, self.sbf, self.l1_lambda / 10, loss_out=self.loss_buf)
+                # (the gradients leave the backward AS that payload: st_grad_step_packed), and st_unpack_clip computes the L1 clip
+                # coefficient while it scatters, so the update below is the live-row Adam launch of the single-GPU step
                 if getattr(self, "_packed", None) is None:
                     self._packed = torch.empty(eng.packed_grad_floats(), device=self.device, dtype=torch.float32)
-                eng.pack_grads(self.grads, self._packed)
+                loss = eng.grad_step_packed(x, y, knobs, self.params, self._packed, self.sbf, self.l1_lambda / 10, loss_out=self.loss_buf)
                 scale = parallel.allreduce_sum_(self._packed, self.pg)
-                eng.unpack_grads(self._packed, self.grads)
+                eng.unpack_clip(self._packed, self.grads, scale, 1.0)
+                hp = eng.adam_hp(self.lr, step_no, grad_scale=scale, max_norm=1.0)
+                eng.adam_step_clipped(self.params, self.grads, self.m, self.v, hp)
+                self.loss_buf = loss
+                self.optimizer._step = step_no
+                self.lr = float(self.lr_sched[min(self.iter_count, len(self.lr_sched) - 1)])
+                self.optimizer.param_groups[0]['lr'] = self.lr
+                self.iter_count += 1
+                return self.loss_buf
             else:                                 # "whole": st_grad_step (forward + fused loss tail + backward in one call),
                 # then ONE allreduce of the whole flat buffer (16.8 MB).  Measured on 2 B200s (ms/step, v7): whole 1.011,
                 # sliced 1.056, overlap 1.060 -- at this size NCCL is launch / latency bound, so four smaller collectives

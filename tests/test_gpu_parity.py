@@ -484,3 +484,46 @@ def test_packed_exchange_payload_roundtrip():
     torch.cuda.synchronize()
     for i, (a, b) in enumerate(zip(grads, restored)):
         assert torch.equal(a, b), i
+
+
+def test_packed_grad_step_unpack_clip_and_clipped_adam_match_the_piecewise_calls():
+    """The three calls of the data-parallel step (st_grad_step_packed -> [allreduce] -> st_unpack_clip -> st_adam_step_clipped)
+    against st_grad_step + st_adam_step with the L1 clip: the restored gradients are BIT-identical (same split-K and partial
+    sums, only the destination differs), the norm agrees to summation order, and the parameters after the update to 1e-7 --
+    with a grad_scale != 1, as after an allreduce over two ranks."""
+    d = O.model_dims(1, 4, 4)
+    eng = _engine(d)
+    P = O.init_params(d, seed=5)
+    rng = np.random.RandomState(11)
+    B = 9
+    x = (0.3 * rng.standard_normal((B, d.C))).astype(np.float32)
+    knobs = (rng.beta(0.8, 0.8, (B, d.K)) - 0.5).astype(np.float32)
+    y = np.tanh(x[:, -d.L:]).astype(np.float32)
+    sbf = _t(O.scale_by_freq(d.F))
+    scale = 0.5
+
+    def fresh():
+        p = _dev_params(P, d)
+        return p, [torch.zeros_like(t) for t in p], [torch.zeros_like(t) for t in p], [torch.zeros_like(t) for t in p]
+
+    pa, ga, ma, va = fresh()
+    loss_a = eng.grad_step(_t(x), _t(y), _t(knobs), pa, ga, sbf, 2e-6)
+    ga_keep = [g_.clone() for g_ in ga]
+    eng.adam_step(pa, ga, ma, va, eng.adam_hp(1e-3, 1, grad_scale=scale, max_norm=1.0))
+
+    pb, gb, mb, vb = fresh()
+    packed = torch.full((eng.packed_grad_floats(),), float("nan"), device="cuda")
+    loss_b = eng.grad_step_packed(_t(x), _t(y), _t(knobs), pb, packed, sbf, 2e-6)
+    total = torch.empty((), device="cuda")
+    eng.unpack_clip(packed, gb, scale, 1.0, total)
+    eng.adam_step_clipped(pb, gb, mb, vb, eng.adam_hp(1e-3, 1, grad_scale=scale, max_norm=1.0))
+    torch.cuda.synchronize()
+    assert loss_a.item() == loss_b.item()
+    for i, (a, b) in enumerate(zip(ga_keep, gb)):
+        assert torch.equal(a, b), i
+    ref_norm = scale * sum(float(g_.double().abs().sum()) for g_ in ga_keep[:4])
+    assert abs(total.item() - ref_norm) <= 1e-5 * ref_norm
+    for i, (a, b) in enumerate(zip(pa, pb)):
+        assert (a - b).abs().max().item() <= 1e-7 * max(1.0, a.abs().max().item()), i
+    for i, (a, b) in enumerate(zip(ma + va, mb + vb)):
+        assert (a - b).abs().max().item() <= 1e-6 * max(1e-12, a.abs().max().item()), i
