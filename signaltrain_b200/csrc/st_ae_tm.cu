@@ -92,7 +92,6 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
     if (x < 0.f) r = 3.14159265358979323846f - r;
     return copysignf(r, y);
 }
-__device__ __noinline__ float atan2_ni(float y, float x) { return atan2_fast(y, x); }
 __device__ __noinline__ float2 sincos_ni(float x) {
     float s, c;
     sincosf(x, &s, &c);
@@ -280,7 +279,7 @@ __device__ __forceinline__ void epi_hidden(uint32_t t_d, uint32_t t_hi, uint32_t
 template <class TB>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 ae_fwd_tm_kernel(StDims d, const float* __restrict__ image, const float* __restrict__ spec,
-                 const float* __restrict__ knobs, int B, float* __restrict__ mag_out, float* __restrict__ mag_hat,
+                 const float* __restrict__ knobs, int B, float* __restrict__ mag_out, float* __restrict__ trk_out, float* __restrict__ mag_hat,
                  float* __restrict__ phs_hat, float* __restrict__ ri, float* __restrict__ ri_lo, float* __restrict__ dbg,
                  long long* __restrict__ timing) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];       // SWIZZLE_128B operands need 1024-byte alignment (checked below)
@@ -427,6 +426,10 @@ ae_fwd_tm_kernel(StDims d, const float* __restrict__ image, const float* __restr
                     vm[e] = sqrtf(re[e] * re[e] + im[e] * im[e]);
                     vp[e] = in ? atan2_fast(im[e], re[e] + 1e-7f) : 0.f;
                     if (in && mag_out) mag_out[((long)b * d.T + t) * d.F + f] = vm[e];
+                    if (in && trk_out) {                       // both tracks, for the backward kernel's prologue
+                        trk_out[((long)b * d.T + t) * d.F + f] = vm[e];
+                        trk_out[(long)B * d.T * d.F + ((long)b * d.T + t) * d.F + f] = vp[e];
+                    }
                     if (t >= tail0 && t < d.T) {
                         tails[(t - tail0) * TILE + row] = vm[e];
                         tails[(XCH_J + t - tail0) * TILE + row] = vp[e];
@@ -809,7 +812,7 @@ __device__ __forceinline__ void stage_act(uint8_t* buf, uint32_t t_lq, uint32_t 
 
 struct BwdArgs {
     const float* image;      // [2 autoencoders] backward images
-    const float* spec;
+    const float* trk;        // [2][B][T][F] magnitude | phase tracks written by the forward kernel
     const float* knobs;
     const float* mag_hat;    // forward outputs
     const float* phs_hat;
@@ -1075,22 +1078,16 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
             float* mydbg = (DBG && a.dbg && tile == 0 && ae == 0) ? a.dbg + (long)row * 64 : nullptr;
             float vkeep[16];
             BT0()
-            // ---- input track (this thread: frames [16 half, +16)) -> A operand, kept in registers for layer 0's weight gradient
+            // ---- input track (this thread: frames [16 half, +16)) -> A operand, kept in registers for layer 0's weight gradient.
+            // The forward kernel stored both tracks (nn_proc.py:309-310), so nothing is re-derived from the spectrum here.
             {
                 const int c0 = 16 * half;
-                const float* sp = a.spec + (long)b * d.Tp * rowstride + f;
-                float re[16], im[16];
+                const float* tp = a.trk + (long)ae * ntrk + ((long)b * d.T) * d.F + f;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const bool in = ok && c0 + e < d.T;
-                    re[e] = in ? __ldg(sp + (long)(c0 + e) * rowstride) : 0.f;
-                    im[e] = in ? __ldg(sp + (long)(c0 + e) * rowstride + d.Fp) : 0.f;
-                }
+                for (int e = 0; e < 16; ++e) vkeep[e] = (ok && c0 + e < d.T) ? __ldg(tp + (long)(c0 + e) * d.F) : 0.f;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     const int t = c0 + e;
-                    const bool in = ok && t < d.T;
-                    vkeep[e] = ae == 0 ? sqrtf(re[e] * re[e] + im[e] * im[e]) : (in ? atan2_ni(im[e], re[e] + 1e-7f) : 0.f);
                     if (t >= tail0 && t < d.T) vtail[(t - tail0) * TILE + row] = vkeep[e];
                 }
                 store_pair<16>(t_lane + TC_AH + c0, t_lane + TC_AL + c0, vkeep);
@@ -1263,7 +1260,7 @@ constexpr size_t fwd_smem_bytes() {
 
 template <class TB>
 bool launch_fwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, const float* knobs,
-                int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo, float* wpack, float* dbg,
+                int B, float* mag, float* trk, float* mag_hat, float* phs_hat, float* ri, float* ri_lo, float* wpack, float* dbg,
                 long long* timing, int sm_count, bool pack, cudaStream_t s_pack, cudaStream_t s) {
     constexpr size_t smem = fwd_smem_bytes<TB>();
     static_assert(smem <= 227 * 1024, "forward tile does not fit shared memory");
@@ -1276,7 +1273,7 @@ bool launch_fwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AePa
     if (B > 0) {
         const long ntiles = ((long)B * d.F + TILE - 1) / TILE;
         const int grid = (int)std::min<long>(ntiles, sm_count);
-        ae_fwd_tm_kernel<TB><<<grid, FWD_THREADS, smem, s>>>(d, wpack, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, dbg, timing);
+        ae_fwd_tm_kernel<TB><<<grid, FWD_THREADS, smem, s>>>(d, wpack, spec, knobs, B, mag, trk, mag_hat, phs_hat, ri, ri_lo, dbg, timing);
     }
     return true;
 }
@@ -1309,7 +1306,8 @@ __global__ void ae_track_to_spec_kernel(StDims d, int B, const float* __restrict
 }
 
 template <class TB>
-int launch_bwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, const float* knobs, int B,
+int launch_bwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, const float* trk,
+               const float* knobs, int B,
                const float* mag_hat, const float* phs_hat, const float* g_ri, const float* g_mag_hat, const float* g_mag,
                float* g_track, float* g_spec, float* g_spec_lo, float* partials, float* wpack, float* dbg, long long* timing, int sm_count, bool pack,
                cudaStream_t s_pack, cudaStream_t s) {
@@ -1326,7 +1324,7 @@ int launch_bwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AePar
     const long ntiles = ((long)B * d.F + TILE - 1) / TILE;
     const int nslot = (int)std::min<long>(ntiles, sm_count / 2);
     BwdArgs a;
-    a.image = wpack; a.spec = spec; a.knobs = knobs; a.mag_hat = mag_hat; a.phs_hat = phs_hat; a.g_ri = g_ri; a.g_mag_hat = g_mag_hat;
+    a.image = wpack; a.trk = trk; a.knobs = knobs; a.mag_hat = mag_hat; a.phs_hat = phs_hat; a.g_ri = g_ri; a.g_mag_hat = g_mag_hat;
     a.g_track = g_track; a.partials = partials; a.dbg = dbg; a.timing = timing; a.B = B;
     if (dbg) ae_bwd_tm_kernel<TB, true><<<2 * nslot, BWD_THREADS, smem, s>>>(d, g, a);
     else ae_bwd_tm_kernel<TB, false><<<2 * nslot, BWD_THREADS, smem, s>>>(d, g, a);
@@ -1342,16 +1340,17 @@ int launch_bwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AePar
 
 long st_ae_tm_pack_floats() { return 2L * image_floats<Tab<64, 24>>(); }
 
-// Covers T <= 64, OT <= 16, K <= 8.  Writes mag (optional), mag_hat, phs_hat and the (hi, lo) polar->rect operand ri.
+// Covers T <= 64, OT <= 16, K <= 8.  Writes mag (optional), trk (optional: [2][B][T][F] magnitude | phase tracks for the backward
+// kernel), mag_hat, phs_hat and the (hi, lo) polar->rect operand ri.
 // wpack: workspace of st_ae_tm_pack_floats() floats.  pack: (re)build the weight image on `s_pack` first (the launching stream,
 // or a side stream the caller joins before the forward); B = 0 packs only.
 // dbg (nullable): [2 autoencoders][9 layers][128 rows][64] layer outputs of tile 0 (test harness only).
 bool st_launch_ae_forward_tm(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
-                             const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo,
+                             const float* knobs, int B, float* mag, float* trk, float* mag_hat, float* phs_hat, float* ri, float* ri_lo,
                              float* wpack, float* dbg, long long* timing, int sm_count, bool pack, cudaStream_t s_pack, cudaStream_t s) {
     if (d.T > 64 || d.OT > 16 || d.K > 8) return false;
     const bool wide = d.T > 32, knob = d.K > 0;
-#define ST_FWD(...) launch_fwd<__VA_ARGS__>(d, g, pm, pp, spec, knobs, B, mag, mag_hat, phs_hat, ri, ri_lo, wpack, dbg, timing, sm_count, pack, s_pack, s)
+#define ST_FWD(...) launch_fwd<__VA_ARGS__>(d, g, pm, pp, spec, knobs, B, mag, trk, mag_hat, phs_hat, ri, ri_lo, wpack, dbg, timing, sm_count, pack, s_pack, s)
     if (!wide && knob) return ST_FWD(Tab<32, 24>);
     if (!wide) return ST_FWD(Tab<32, 16>);
     if (knob) return ST_FWD(Tab<64, 24>);
@@ -1365,14 +1364,14 @@ long st_ae_tm_bwd_pack_floats() { return 2L * bwd_image_floats<Tab<32, 24>>(); }
 // floats) and, when g_spec is non-null, dL/d(re, im) as the (hi, lo) operand of the analysis weight-gradient GEMM; per-CTA
 // partial weight / bias gradients -> partials ([(slot, autoencoder)][flat_total]).  Returns the number of slots written per
 // autoencoder (0: geometry not covered -- T <= 32, OT <= 16, K <= 8).  wpack: st_ae_tm_bwd_pack_floats() floats.
-int st_launch_ae_backward_tm(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
+int st_launch_ae_backward_tm(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec, const float* trk,
                              const float* knobs, int B, const float* mag_hat, const float* phs_hat, const float* g_ri,
                              const float* g_mag_hat, const float* g_mag, float* g_track, float* g_spec, float* g_spec_lo,
                              float* partials, float* wpack, float* dbg, long long* timing, int sm_count, bool pack, cudaStream_t s_pack, cudaStream_t s) {
     if (d.T > 32 || d.OT > 16 || d.K > 8) return 0;
     if (d.K > 0)
-        return launch_bwd<Tab<32, 24>>(d, g, pm, pp, spec, knobs, B, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, g_track, g_spec, g_spec_lo,
+        return launch_bwd<Tab<32, 24>>(d, g, pm, pp, spec, trk, knobs, B, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, g_track, g_spec, g_spec_lo,
                                        partials, wpack, dbg, timing, sm_count, pack, s_pack, s);
-    return launch_bwd<Tab<32, 16>>(d, g, pm, pp, spec, knobs, B, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, g_track, g_spec, g_spec_lo,
+    return launch_bwd<Tab<32, 16>>(d, g, pm, pp, spec, trk, knobs, B, mag_hat, phs_hat, g_ri, g_mag_hat, g_mag, g_track, g_spec, g_spec_lo,
                                    partials, wpack, dbg, timing, sm_count, pack, s_pack, s);
 }

@@ -42,6 +42,7 @@ struct st_handle {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float* dct_ws = nullptr;      // workspace of the DCT / MDCT front-end variant (st_dct_analysis / st_dct_synthesis)
     long dct_ws_floats = 0;
+    float* trk_ws = nullptr;      // magnitude | phase tracks written by the TMEM forward kernel, read by the TMEM backward kernel
     float* gtrack_ws = nullptr;   // track gradients of the two autoencoders (FFMA2 backward -> ae_input_grad_kernel)
     float* tail_ws = nullptr;     // skip / residual gradient scratch of the tensor-core backward
     bool training = true;         // st_set_training: save activations in st_forward for a following st_backward
@@ -293,7 +294,7 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
 static void free_batch_buffers(st_handle* h) {
     float** bufs[] = {&h->xpad, &h->xpad_lo, &h->spec, &h->ri, &h->ri_lo, &h->fo, &h->mag_hat_ws, &h->phs_hat_ws, &h->gwave,
                       &h->gwave_lo, &h->g_ri, &h->g_spec, &h->g_spec_lo, &h->ae_part, &h->yhat_ws, &h->gy_ws, &h->gmh_ws,
-                      &h->knobs_ws, &h->ae_save_m, &h->ae_save_p, &h->tail_ws, &h->gtrack_ws};
+                      &h->knobs_ws, &h->ae_save_m, &h->ae_save_p, &h->tail_ws, &h->gtrack_ws, &h->trk_ws};
     for (float** b : bufs) {
         if (*b) cudaFree(*b);
         *b = nullptr;
@@ -357,7 +358,7 @@ static int ensure_workspace(st_handle* h, int B) {
         {&h->ae_save_m, (long)B * d.F * st_ae_mma_record_floats(d), false},
         {&h->ae_save_p, (long)B * d.F * st_ae_mma_record_floats(d), false},
         {&h->tail_ws, (long)B * d.OT * d.F, false},
-        {&h->gtrack_ws, 2L * B * d.T * d.F, false},
+        {&h->gtrack_ws, 2L * B * d.T * d.F, false}, {&h->trk_ws, 2L * B * d.T * d.F, false},
     };
     for (auto& r : req) {
         ST_CUDA_OK(cudaMalloc(r.p, r.n * sizeof(float)));
@@ -467,11 +468,11 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         st_launch_pack_analysis(d, params[0], params[1], h->wcat, h->wcat_lo, sp);
         st_launch_fold_synthesis(d, params[2], params[3], h->sfold, h->sfold_lo, sp);
         if (tm_fwd)       // shared-memory images of the autoencoder weights (B = 0: pack only)
-            st_launch_ae_forward_tm(d, h->g, pm, pp, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, h->ae_wpack, nullptr,
-                                    nullptr, h->sm_count, true, sp, sp);
+            st_launch_ae_forward_tm(d, h->g, pm, pp, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, h->ae_wpack,
+                                    nullptr, nullptr, h->sm_count, true, sp, sp);
         if (tm_fwd && tm_bwd_geom && h->training) {
-            st_launch_ae_backward_tm(d, h->g, pm, pp, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                     nullptr, h->ae_wpack_bwd, nullptr, nullptr, h->sm_count, true, sp, sp);
+            st_launch_ae_backward_tm(d, h->g, pm, pp, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                     nullptr, nullptr, h->ae_wpack_bwd, nullptr, nullptr, h->sm_count, true, sp, sp);
             h->tm_bwd_image = true;
         }
         if (beside) ST_CUDA_OK(cudaEventRecord(h->ev_join, sp));
@@ -509,7 +510,7 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         h->tm_fwd = false;
         bool done = false;
         if (tm_fwd) {
-            done = st_launch_ae_forward_tm(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo, h->ae_wpack,
+            done = st_launch_ae_forward_tm(d, h->g, pm, pp, h->spec, knobs, B, mag, h->trk_ws, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo, h->ae_wpack,
                                            nullptr, nullptr, h->sm_count, false, s, s);
             h->tm_fwd = done;
         }
@@ -678,7 +679,7 @@ static int backward_impl(st_handle* h, const float* g_y_hat, const float* g_mag,
         split_params(params, pm, pp);
         int gr = 0;
         if (h->tm_fwd && h->use_tm)       // recompute in tensor memory; the weight image is packed here when the forward was an eval one
-            gr = st_launch_ae_backward_tm(d, h->g, pm, pp, h->spec, h->knobs_ws, B, h->mag_hat_ws, h->phs_hat_ws, h->g_ri, g_mag_hat, g_mag,
+            gr = st_launch_ae_backward_tm(d, h->g, pm, pp, h->spec, h->trk_ws, h->knobs_ws, B, h->mag_hat_ws, h->phs_hat_ws, h->g_ri, g_mag_hat, g_mag,
                                           h->gtrack_ws, h->g_spec, h->g_spec_lo, h->ae_part, h->ae_wpack_bwd, nullptr, h->ae_timing, h->sm_count,
                                           !h->tm_bwd_image, s, s);
         if (gr > 0) h->tm_bwd_image = true;

@@ -160,14 +160,15 @@ int st_launch_ae_backward_mma(const StDims& d, const AeGeom& g, const AeParams& 
 // dbg (nullable, tests only): [2][9][128][64] layer outputs of tile 0.
 long st_ae_tm_pack_floats();
 bool st_launch_ae_forward_tm(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
-                             const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo,
+                             const float* knobs, int B, float* mag, float* trk /*nullable: [2][B][T][F] tracks for the backward*/,
+                             float* mag_hat, float* phs_hat, float* ri, float* ri_lo,
                              float* wpack, float* dbg, long long* timing /*nullable: 256 counters*/, int sm_count,
                              bool pack, cudaStream_t s_pack, cudaStream_t s);
 
 long st_ae_tm_bwd_pack_floats();
 // Backward with in-kernel recompute.  Returns the number of per-CTA partial-gradient vectors per autoencoder (0: not covered).
 int st_launch_ae_backward_tm(const StDims& d, const AeGeom& g, const AeParams& pm, const AeParams& pp, const float* spec,
-                             const float* knobs, int B, const float* mag_hat, const float* phs_hat, const float* g_ri,
+                             const float* trk /*the forward kernel's tracks*/, const float* knobs, int B, const float* mag_hat, const float* phs_hat, const float* g_ri,
                              const float* g_mag_hat, const float* g_mag, float* g_track, float* g_spec, float* g_spec_lo,
                              float* partials, float* wpack, float* dbg, long long* timing /*nullable: 64 counters*/, int sm_count, bool pack,
                              cudaStream_t s_pack, cudaStream_t s);

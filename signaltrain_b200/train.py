@@ -48,7 +48,9 @@ class FusedTrainer:
         self.world = parallel.world_size(self.pg) if distributed is not False else 1
         if self.world > 1:
             parallel.broadcast_parameters(self.params, 0, self.pg)
-        self.loss_buf = torch.zeros((), device=dev, dtype=torch.float32)
+        # two loss slots, used alternately: the host loop reads step i's loss from a side stream while step i + 1 writes the other
+        self._loss_bufs = [torch.zeros((), device=dev, dtype=torch.float32) for _ in range(2)]
+        self.loss_buf = self._loss_bufs[0]
 
     def _setup(self, x):
         self.eng = self.model.mpaec._engine_for(x)
@@ -62,6 +64,7 @@ class FusedTrainer:
             self._setup(x)
         eng = self.eng
         step_no = self.optimizer._step + 1
+        self.loss_buf = self._loss_bufs[step_no & 1]
         if self.world == 1:
             hp = eng.adam_hp(self.lr, step_no, max_norm=1.0)
             eng.train_step(x, y, knobs, self.params, self.grads, self.m, self.v, self.sbf, self.l1_lambda / 10, hp,
@@ -168,10 +171,16 @@ class FusedTrainer:
             if nxt is not None:
                 upload(1 - cur, nxt)
             main.wait_event(ready[cur])
+            if i >= 2:
+                main.wait_event(loss_ev[cur])                # the read-back of the loss slot this step writes (step i - 2's) is done
             loss = self.step(*bufs[cur])
             free[cur].record(main)
-            loss_host[cur].copy_(loss, non_blocking=True)
-            loss_ev[cur].record(main)
+            # loss read-back on the copy stream: a 4-byte D2H in the step's own stream would put the copy engine's latency
+            # between every two steps
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[cur])
+                loss_host[cur].copy_(loss, non_blocking=True)
+                loss_ev[cur].record(copy_stream)
             if i > 0:
                 collect(i - 1)
             i += 1

@@ -88,6 +88,8 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dmh, nout * sizeof(float))); CK(cudaMalloc(&dph, nout * sizeof(float)));
     CK(cudaMalloc(&dri, nri * sizeof(float))); CK(cudaMalloc(&dril, nri * sizeof(float)));
     CK(cudaMalloc(&ddbg, 2L * 9 * 128 * 64 * sizeof(float)));
+    float* dtrk;                                             // [2][Bmax][T][F]: the forward kernel's tracks, read by the backward kernel
+    CK(cudaMalloc(&dtrk, 2L * std::max(B, TB) * d.T * d.F * sizeof(float)));
     CK(cudaMemcpy(dspec, spec.data(), nspec * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dknobs, knobs.data(), knobs.size() * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaMemset(dri, 0, nri * sizeof(float))); CK(cudaMemset(dril, 0, nri * sizeof(float)));
@@ -96,7 +98,7 @@ int main(int argc, char** argv) {
     CK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0));
 
     // ---------------- forward check ----------------
-    if (!st_launch_ae_forward_tm(d, g, dp[0], dp[1], dspec, dknobs, B, dmag, dmh, dph, dri, dril, dwpack, ddbg, nullptr, sm, true, 0, 0)) { printf("forward: geometry not covered\n"); return 3; }
+    if (!st_launch_ae_forward_tm(d, g, dp[0], dp[1], dspec, dknobs, B, dmag, dtrk, dmh, dph, dri, dril, dwpack, ddbg, nullptr, sm, true, 0, 0)) { printf("forward: geometry not covered\n"); return 3; }
     CK(cudaDeviceSynchronize());
     std::vector<float> mh(nout), ph(nout), ri(nri), ril(nri), mag((long)B * d.T * d.F), dbg(2L * 9 * 128 * 64);
     CK(cudaMemcpy(mh.data(), dmh, (long)B * d.OT * d.F * sizeof(float), cudaMemcpyDeviceToHost));
@@ -246,7 +248,7 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(dgri, gri.data(), nri * 4, cudaMemcpyHostToDevice)); CK(cudaMemset(dgmh, 0, (long)Bmax * d.OT * d.F * 4));
         CK(cudaMemcpy(dgmh, gmh.data(), gmh.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemset(dpart, 0, (long)sm * g.flat_total * 4)); CK(cudaMemset(ddbg2, 0, 18L * 128 * 64 * 4)); CK(cudaMemset(dgt, 0, 2L * Bmax * d.T * d.F * 4));
-        const int nslot = st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, B, dcmh, dcph, dgri, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb,
+        const int nslot = st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dtrk, dknobs, B, dcmh, dcph, dgri, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb,
                                                    ddbg2, nullptr, sm, true, 0, 0);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("backward: CUDA error %s\n", cudaGetErrorString(e)); return 2; }
@@ -295,10 +297,11 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&dcmh2, nout * 4)); CK(cudaMalloc(&dcph2, nout * 4));
         CK(cudaMemset(dcmh2, 0, nout * 4)); CK(cudaMemset(dcph2, 0, nout * 4));
         float* dgri2; CK(cudaMalloc(&dgri2, nri * 4)); CK(cudaMemset(dgri2, 0, nri * 4));
-        for (int i = 0; i < 3; ++i) st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, nullptr, sm, false, 0, 0);
+        st_launch_ae_forward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, nullptr, dtrk, dmh, dph, dri, dril, dwpack, nullptr, nullptr, sm, false, 0, 0);
+        for (int i = 0; i < 3; ++i) st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dtrk, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, nullptr, sm, false, 0, 0);
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(b0));
-        for (int i = 0; i < 20; ++i) st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, nullptr, sm, false, 0, 0);
+        for (int i = 0; i < 20; ++i) st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dtrk, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, nullptr, sm, false, 0, 0);
         CK(cudaEventRecord(b1));
         CK(cudaDeviceSynchronize());
         float bms = 0;
@@ -308,7 +311,7 @@ int main(int argc, char** argv) {
             long long* dt2;
             CK(cudaMalloc(&dt2, 128 * sizeof(long long)));
             CK(cudaMemset(dt2, 0, 128 * sizeof(long long)));
-            const int ns = st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, dt2, sm, false, 0, 0);
+            const int ns = st_launch_ae_backward_tm(d, g, dp[0], dp[1], dspec, dtrk, dknobs, TB, dcmh2, dcph2, dgri2, dgmh, nullptr, dgt, nullptr, nullptr, dpart, dwb, nullptr, dt2, sm, false, 0, 0);
             CK(cudaDeviceSynchronize());
             long long ht2[128];
             CK(cudaMemcpy(ht2, dt2, sizeof(ht2), cudaMemcpyDeviceToHost));
@@ -327,11 +330,11 @@ int main(int argc, char** argv) {
     // ---------------- timing ----------------
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) st_launch_ae_forward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, nullptr, dmh, dph, dri, dril, dwpack, nullptr, nullptr, sm, false, 0, 0);
+    for (int i = 0; i < 3; ++i) st_launch_ae_forward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, nullptr, dtrk, dmh, dph, dri, dril, dwpack, nullptr, nullptr, sm, false, 0, 0);
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));
     const int reps = 20;
-    for (int i = 0; i < reps; ++i) st_launch_ae_forward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, nullptr, dmh, dph, dri, dril, dwpack, nullptr, nullptr, sm, false, 0, 0);
+    for (int i = 0; i < reps; ++i) st_launch_ae_forward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, nullptr, dtrk, dmh, dph, dri, dril, dwpack, nullptr, nullptr, sm, false, 0, 0);
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms = 0;
@@ -341,7 +344,7 @@ int main(int argc, char** argv) {
         long long* dt;
         CK(cudaMalloc(&dt, 256 * sizeof(long long)));
         CK(cudaMemset(dt, 0, 256 * sizeof(long long)));
-        st_launch_ae_forward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, nullptr, dmh, dph, dri, dril, dwpack, nullptr, dt, sm, false, 0, 0);
+        st_launch_ae_forward_tm(d, g, dp[0], dp[1], dspec, dknobs, TB, nullptr, dtrk, dmh, dph, dri, dril, dwpack, nullptr, dt, sm, false, 0, 0);
         CK(cudaDeviceSynchronize());
         long long ht[256];
         CK(cudaMemcpy(ht, dt, sizeof(ht), cudaMemcpyDeviceToHost));
