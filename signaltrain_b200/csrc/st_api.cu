@@ -39,7 +39,7 @@ struct st_handle {
     // side stream: independent small kernels run beside the main stream's work (fork / join with events; off while profiling
     // stages, whose event pairs live on the main stream)
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pack = nullptr;
     float* dct_ws = nullptr;      // workspace of the DCT / MDCT front-end variant (st_dct_analysis / st_dct_synthesis)
     long dct_ws_floats = 0;
     float* trk_ws = nullptr;      // magnitude | phase tracks written by the TMEM forward kernel, read by the TMEM backward kernel
@@ -215,7 +215,8 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     d.Sx = d.Tp * H; d.Sg = d.OTp * H;
     if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming) != cudaSuccess) {
         cudaGetLastError();
         h->side = nullptr;                       // no overlap: everything stays on the caller's stream
     }
@@ -309,6 +310,7 @@ extern "C" void st_destroy(st_handle* h) {
     if (h->dct_ws) cudaFree(h->dct_ws);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_pack) cudaEventDestroy(h->ev_pack);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->small) cudaFree(h->small);
     if (h->counters) cudaFree(h->counters);
@@ -466,6 +468,7 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
             ST_CUDA_OK(cudaStreamWaitEvent(sp, h->ev_fork, 0));
         }
         st_launch_pack_analysis(d, params[0], params[1], h->wcat, h->wcat_lo, sp);
+        if (beside) ST_CUDA_OK(cudaEventRecord(h->ev_pack, sp));     // all the analysis GEMM needs; the rest hides behind that GEMM
         st_launch_fold_synthesis(d, params[2], params[3], h->sfold, h->sfold_lo, sp);
         if (tm_fwd)       // shared-memory images of the autoencoder weights (B = 0: pack only)
             st_launch_ae_forward_tm(d, h->g, pm, pp, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, h->ae_wpack,
@@ -486,7 +489,7 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         st_launch_pad_split(x, h->xpad, h->xpad_lo, B, d.C, d.N, d.Sx, 0.5f, s);
         if (keep_knobs) ST_CUDA_OK(cudaMemcpyAsync(h->knobs_ws, knobs, (long)B * d.K * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
-    if (beside) ST_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
+    if (beside) ST_CUDA_OK(cudaStreamWaitEvent(s, h->ev_pack, 0));
     ST_LAUNCH_OK(h);
     const int MT = B * d.Tp, MO = B * d.OTp, F2 = 2 * d.Fp;
     {   // analysis: spec[(b,t), (re|im) k] = sum_n frame[(b,t), n] * wcat[k, n]
@@ -503,6 +506,7 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
         }
     }
     ST_LAUNCH_OK(h);
+    if (beside) ST_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));        // folded synthesis weights, autoencoder weight images
     {
         StageScope sc(h, SG_AE_FWD, ((acts || tm_fwd) ? 1 : 2) + (mag_hat_user != nullptr), s);
         const bool save = h->training && h->use_mma_bwd;
