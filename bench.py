@@ -292,6 +292,8 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from signaltrain_b200 import parallel as _parallel
+        _parallel.nccl_env_defaults(world)
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     CHUNK_SCALE, KNOBS = wl["scale"], wl["knobs"]
@@ -441,6 +443,9 @@ def run_native(args):
                     "ms_per_step": 1e3 * e2e_s / Ke,
                     "api": "signaltrain_b200.train.FusedTrainer.run_host_batches: pinned host batches, H2D of batch i+1 on a copy stream while step i (st_train_step) runs, every step's loss read back to the host (one step late)"},
             "gpu_launches": int(launches), "simt_fallbacks": eng.fallback_count(), "clocks": clk, "roofline": roofline}
+    if world > 1:
+        line["config"]["exchange"] = (f"{os.environ.get('ST_DP_EXCHANGE', 'packed')}: one NCCL allreduce of the packed gradient payload per step "
+                                      f"(NCCL_ALGO={os.environ.get('NCCL_ALGO', 'default')}, NCCL_PROTO={os.environ.get('NCCL_PROTO', 'default')})")
     if replicas_equal is not None:
         line["replica_parameters_identical"] = replicas_equal
     if cpu_fps is not None:
