@@ -106,3 +106,73 @@ class DeviceAudioFileBatches:
                 x, y = x * s, (y * s).contiguous()
             knobs_nn = (k_wc - self.kr[:, 0]) / (self.kr[:, 1] - self.kr[:, 0]) - 0.5                     # datasets.py:246-247
             yield x, y, torch.from_numpy(knobs_nn.astype(np.float32)).to(x.device)
+
+
+# ---- file datasets: what AudioFileDataSet(preload=True) reads from disk (datasets.py:102-160), handed to the device batches ----
+
+def parse_knob_string(filename, ext=".wav"):
+    """Knob settings from a target filename (datasets.py:177-185): double underscores precede every setting, e.g.
+    'target_9400_Compressor_4c__-10.95__3.428__0.005043__0.01308.wav' -> [-10.95, 3.428, 0.005043, 0.01308]."""
+    import os
+    parts = os.path.basename(filename).replace(ext, "").split("__")[1:]
+    return np.array([float(p) for p in parts], dtype=np.float32)
+
+
+def read_wav(filename, sr=44100):
+    """audio.read_audio_file's scipy branch (audio.py:207-233): first channel of a multi-channel file, int16 -> float / 32767.
+    Resampling (the reference falls back to librosa, audio.py:234-242) is outside this path: a sample-rate mismatch raises."""
+    from scipy.io import wavfile
+    read_sr, signal = wavfile.read(filename)
+    if signal.ndim > 1:
+        signal = signal[:, 0]
+    if signal.dtype == np.int16:
+        signal = np.array(signal / 32767.0, dtype=np.float32)
+    if int(read_sr) != int(sr):
+        raise RuntimeError(f"{filename}: sample rate {read_sr} Hz, expected {sr} Hz (resample the corpus first; the reference "
+                           "would call librosa here)")
+    return np.asarray(signal, dtype=np.float32)
+
+
+def mu_compand(y, mu=32):
+    """audio.mu_compand (audio.py:339-340)."""
+    return (np.sign(y) * np.log(1 + mu * np.abs(y)) / np.log(1 + mu)).astype(np.float32)
+
+
+def load_file_pairs(path, sr=44100, is_inverse=False, compand=False, max_files=100000):
+    """The preload of AudioFileDataSet (datasets.py:104-160): sorted input_* / target_* pairs under `path`, knobs from the target
+    names, unequal lengths aligned to their ends (align_end, :146-152), input and target swapped for inverse effects (:154-155),
+    optional mu-law companding (:198-200).  Returns (files_x, files_y, knobs_wc[nfiles, K])."""
+    import glob
+    inputs = sorted(glob.glob(path + "/" + "input_*"))
+    targets = sorted(glob.glob(path + "/" + "target_*"))
+    print("AudioFileDataSet: Found", len(inputs), "input files and", len(targets), " target files in path", path)
+    assert len(inputs) == len(targets)
+    if not inputs:
+        raise RuntimeError(f"no input_* / target_* file pairs under {path}")
+    n = min(max_files, len(inputs))
+    xs, ys, knobs = [], [], []
+    for i in range(n):
+        x, y = read_wav(inputs[i], sr), read_wav(targets[i], sr)
+        knobs.append(parse_knob_string(targets[i]))
+        if compand:
+            x, y = mu_compand(x), mu_compand(y)
+        if len(x) != len(y):
+            m = min(len(x), len(y))
+            x, y = x[-m:], y[-m:]
+        if is_inverse:
+            x, y = y, x
+        xs.append(x)
+        ys.append(y)
+    return xs, ys, np.stack(knobs).astype(np.float32)
+
+
+def file_batches(path, effect, chunk_size, y_size, batch_size, datapoints, device, sr=44100, rerun=False, augment=True,
+                 compand=False):
+    """DeviceAudioFileBatches over the file pairs under `path` -- the on-device counterpart of
+    DataLoader(AudioFileDataSet(chunk_size, effect, path=..., preload=True, rerun=..., augment=..., compand=...)) (train.py:240-248)."""
+    if rerun and len(getattr(effect, "knob_names", [])) != 4:
+        raise NotImplementedError("target_type != 'stream' re-runs the effect on every chunk (datasets.py:241-242); on the device "
+                                  "that exists for the 4-knob compressor only (st_compressor_4c)")
+    xs, ys, knobs_wc = load_file_pairs(path, sr=sr, is_inverse=bool(getattr(effect, "is_inverse", False)), compand=compand)
+    return DeviceAudioFileBatches(xs, ys, knobs_wc, np.asarray(effect.knob_ranges, np.float64), chunk_size, y_size, batch_size,
+                                  datapoints, device=device, augment=augment, rerun_effect=rerun, sr=float(sr))

@@ -314,8 +314,15 @@ def train(effect=None, epochs=100, n_data_points=200000, batch_size=20, device=N
                                                     batch_size=batch_size, y_size=out_chunk_size, augment=False,
                                                     recycle=True, seed=99991)
     else:
-        raise NotImplementedError("file datasets (signaltrain/datasets.py AudioFileDataSet) are outside this hot path; "
-                                  "build DataLoaders with the reference's datasets.py and pass them to train_loop()")
+        # prerecorded input / target files (train.py:240-246): the corpus is preloaded into HBM, windows are cropped (and, for
+        # target_type != "stream", the effect re-run) on the device; the host only draws the reference's random numbers
+        from . import device_data
+        rerun = target_type != "stream"
+        dataloader = device_data.file_batches(datapath + "/Train/", effect, chunk_size, out_chunk_size, batch_size, n_data_points,
+                                              device, sr=sr, rerun=rerun, augment=True, compand=compand)
+        dataloader_val = device_data.file_batches(datapath + "/Val/", effect, chunk_size, out_chunk_size, batch_size,
+                                                  max(batch_size, n_data_points // 4), device, sr=sr, rerun=rerun, augment=False,
+                                                  compand=compand)
 
     logfilename = "vl_avg_out.dat"
     open(logfilename, "a").close()

@@ -86,3 +86,51 @@ def test_cuda_crop_and_device_batches():
             np.testing.assert_array_equal(gx[b], s * xi)
             assert np.abs(gy[b] - (s * yi).astype(np.float32)).max() < 5e-7
             np.testing.assert_allclose(gk[b], (kwc[i] - kr[:, 0]) / (kr[:, 1] - kr[:, 0]) - 0.5, atol=1e-7)
+
+
+def _write_pairs(root, n_files, n_samples, rng, extra_target=0):
+    """input_*/target_* wav pairs with the reference's naming (datasets.py:177-185); returns (xs, ys, knobs)."""
+    from scipy.io import wavfile
+    os.makedirs(root, exist_ok=True)
+    xs, ys, ks = [], [], []
+    for i in range(n_files):
+        x = (0.3 * rng.standard_normal(n_samples)).astype(np.float32)
+        y = np.tanh(np.concatenate([np.zeros(extra_target, np.float32), x])).astype(np.float32)
+        k = [round(float(rng.uniform(-30, 0)), 3), round(float(rng.uniform(1, 5)), 3), 0.01, 0.02]
+        wavfile.write(os.path.join(root, f"input_{i}_.wav"), 44100, x)
+        wavfile.write(os.path.join(root, f"target_{i}_Compressor_4c__{k[0]}__{k[1]}__{k[2]}__{k[3]}.wav"), 44100, y)
+        xs.append(x); ys.append(y); ks.append(k)
+    return xs, ys, np.array(ks, np.float32)
+
+
+def test_file_pair_loader_follows_the_reference_conventions(tmp_path):
+    """load_file_pairs = the preload of AudioFileDataSet (datasets.py:104-160, audio.py:207-233): sorted pairs, knobs from the
+    target name, int16 scaling, first channel of stereo, unequal lengths aligned to their ends, inverse effects swapped,
+    mu-law companding, and a loud error instead of a silent resample."""
+    from scipy.io import wavfile
+    from signaltrain_b200 import device_data as dd
+    rng = np.random.RandomState(0)
+    root = str(tmp_path / "Train")
+    xs, ys, ks = _write_pairs(root, 3, 3000, rng, extra_target=7)
+    fx, fy, kw = dd.load_file_pairs(root)
+    assert len(fx) == 3 and kw.shape == (3, 4)
+    np.testing.assert_array_equal(kw, ks)
+    for a, b, x, y in zip(fx, fy, xs, ys):
+        assert len(a) == len(b) == 3000                       # the 7 extra leading target samples are cut: ends aligned
+        np.testing.assert_array_equal(a, x)
+        np.testing.assert_array_equal(b, y[-3000:])
+    ix, iy, _ = dd.load_file_pairs(root, is_inverse=True)
+    np.testing.assert_array_equal(ix[0], fy[0]); np.testing.assert_array_equal(iy[0], fx[0])
+    cx, _, _ = dd.load_file_pairs(root, compand=True)
+    np.testing.assert_allclose(cx[1], np.sign(xs[1]) * np.log(1 + 32 * np.abs(xs[1])) / np.log(33), rtol=1e-6, atol=1e-7)
+    assert list(dd.parse_knob_string("target_9400_Compressor_4c__-10.95__3.428__0.005043__0.01308.wav")) == \
+        [np.float32(-10.95), np.float32(3.428), np.float32(0.005043), np.float32(0.01308)]
+    # int16 stereo file: first channel, / 32767
+    st = (rng.randint(-3000, 3000, size=(500, 2))).astype(np.int16)
+    wavfile.write(str(tmp_path / "s.wav"), 44100, st)
+    np.testing.assert_array_equal(dd.read_wav(str(tmp_path / "s.wav")), np.array(st[:, 0] / 32767.0, dtype=np.float32))
+    wavfile.write(str(tmp_path / "r.wav"), 22050, xs[0])
+    with pytest.raises(RuntimeError, match="sample rate"):
+        dd.read_wav(str(tmp_path / "r.wav"))
+    with pytest.raises(RuntimeError, match="no input_"):
+        dd.load_file_pairs(str(tmp_path / "nothing"))

@@ -209,3 +209,28 @@ def test_library_calls_leave_the_current_device_alone():
         model.forward(x, k)
     assert torch.cuda.current_device() == 0
     assert float(st.loss_functions.mae(x, x)) == 0.0 and torch.cuda.current_device() == 0
+
+
+def test_train_from_prerecorded_files(tmp_path, monkeypatch):
+    """train(datapath=...) (train.py:240-246): Train/ and Val/ file pairs preloaded into HBM, windows cropped on the device;
+    with target_type != "stream" the 4-knob compressor is re-run on every chunk on the device (datasets.py:241-242)."""
+    import signaltrain_b200 as st
+    from tests.test_data_step import _write_pairs
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.RandomState(1)
+    for sub in ("Train", "Val"):
+        _write_pairs(str(tmp_path / "data" / sub), 3, 12000, rng)
+    torch.manual_seed(218)
+    np.random.seed(218)
+    model = st.train.train(effect=st.data.Compressor_4c(), epochs=1, n_data_points=40, batch_size=4, device=torch.device("cuda:0"),
+                           datapath=str(tmp_path / "data"), lr_max=1e-4)
+    ep, val = open("vl_avg_out.dat").read().split()
+    assert ep == "1" and 0.0 < float(val) < 1.0
+    assert all(torch.isfinite(p).all() for p in model.parameters())
+    os.remove("modelcheckpoint.tar")
+    model = st.train.train(effect=st.data.Compressor_4c(), epochs=1, n_data_points=40, batch_size=4, device=torch.device("cuda:0"),
+                           datapath=str(tmp_path / "data"), target_type="chunk", lr_max=1e-4)
+    assert all(torch.isfinite(p).all() for p in model.parameters())
+    with pytest.raises(NotImplementedError):
+        st.train.train(effect=st.data.Denoise(), epochs=1, n_data_points=40, batch_size=4, device=torch.device("cuda:0"),
+                       datapath=str(tmp_path / "data"), target_type="chunk", in_checkpointname="none.tar")
