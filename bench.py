@@ -307,6 +307,11 @@ def run_native(args):
     C, L = model.in_chunk_size, model.out_chunk_size
     lr_sched, _ = st.learningrate.get_1cycle_schedule(lr_max=1e-4, n_data_points=200000, epochs=1000, batch_size=200)
     trainer = FusedTrainer(model, lr_sched)
+    # every measured launch goes to ONE explicit stream (the legacy default stream cannot be captured into a CUDA graph, which
+    # st_train_step does with its ~17 launches after it has seen the same buffers twice); events are recorded on that stream
+    bench_stream = torch.cuda.Stream(device=dev)
+    bench_stream.wait_stream(torch.cuda.current_stream(dev))
+    torch.cuda.set_stream(bench_stream)
 
     # window pool larger than L2 (126 MB): P windows * (C + L + K) * 4 B
     nbatch = max(4, -(-int(168e6) // (B * (C + L + KNOBS) * 4)))
@@ -442,7 +447,8 @@ def run_native(args):
             "e2e": {"value": frames * Ke / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": 1e3 * e2e_s / Ke,
                     "api": "signaltrain_b200.train.FusedTrainer.run_host_batches: pinned host batches, H2D of batch i+1 on a copy stream while step i (st_train_step) runs, every step's loss read back to the host (one step late)"},
-            "gpu_launches": int(launches), "simt_fallbacks": eng.fallback_count(), "clocks": clk, "roofline": roofline}
+            "gpu_launches": int(launches), "cuda_graph_replays": eng.graph_replays(), "simt_fallbacks": eng.fallback_count(),
+            "clocks": clk, "roofline": roofline}
     if world > 1:
         line["config"]["exchange"] = (f"{os.environ.get('ST_DP_EXCHANGE', 'packed')}: one NCCL allreduce of the packed gradient payload per step "
                                       f"(NCCL_ALGO={os.environ.get('NCCL_ALGO', 'default')}, NCCL_PROTO={os.environ.get('NCCL_PROTO', 'default')})")

@@ -172,7 +172,11 @@ int st_adam_step(st_handle* h, float* const* params, const float* const* grads,
 
 /* One whole iteration of the loop body train.py:112-147: forward, calc_loss, backward, clip, Adam.
  * y is (B,L) float32.  loss[0] (device) receives the scalar loss.  If allreduce-before-update is
- * needed (data parallel), call st_forward/st_loss/st_backward, reduce, then st_adam_step instead. */
+ * needed (data parallel), call st_forward/st_loss/st_backward, reduce, then st_adam_step instead.
+ * On a stream that can be captured (not the legacy default stream) the second call with the same tensor tables, batch size and
+ * stream captures the step into a CUDA graph and later calls replay it (x, y, knobs, loss and the Adam scalars are refreshed in
+ * the graph on every call, so the batch may live anywhere); ST_CUDA_GRAPH=0 disables that.  st_debug_graph_replays counts replays. */
+long st_debug_graph_replays(const st_handle* h);
 int st_train_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch,
                   float* const* params, float* const* grads, float* const* exp_avg,
                   float* const* exp_avg_sq, const float* scale_by_freq, float l1_coef,

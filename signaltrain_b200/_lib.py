@@ -83,6 +83,7 @@ _SIGNATURES = {
     "st_adam_step_clipped": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.POINTER(StAdam), ctypes.c_void_p]),
     "st_debug_fallbacks": (ctypes.c_long, [ctypes.c_void_p]),
+    "st_debug_graph_replays": (ctypes.c_long, [ctypes.c_void_p]),
     "st_debug_ae_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]),
     "st_debug_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, c_float_p, ctypes.c_long,
                                      c_float_p, c_float_p, ctypes.c_long, c_float_p, ctypes.c_long, ctypes.c_int, ctypes.c_int,

@@ -65,6 +65,10 @@ struct st_handle {
     bool prof_on = false;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
     long launches = 0;            // kernels + device copies launched by this handle since creation
+    // st_train_step captured into a CUDA graph per (buffers, batch, stream): see StepGraph below
+    bool use_graph = true;
+    std::vector<struct StepGraph*> graphs;
+    long graph_replays = 0;
     long simt_fallbacks = 0;      // calls served by a SIMT fallback kernel (GEMM shape or autoencoder geometry not covered by the
                                   // tensor-core kernels; return_acts forwards count too): st_debug_fallbacks
     char err[1024];
@@ -223,6 +227,7 @@ extern "C" int st_create(const st_config* cfg, int device, st_handle** out) {
     if (const char* e = getenv("ST_DISABLE_TCGEN05")) h->use_tc = !(e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_MMA_BACKWARD")) h->use_mma_bwd = !(e[0] == '1');
     if (const char* e = getenv("ST_DISABLE_TMEM_AE")) h->use_tm = !(e[0] == '1');
+    if (const char* e = getenv("ST_CUDA_GRAPH")) h->use_graph = !(e[0] == '0');
     if (const char* e = getenv("ST_DISABLE_FUSED_TAIL")) h->fuse_tail = !(e[0] == '1');
     build_geom(d, h->g);
     if (st_ae_configure(h, d, h->g)) {
@@ -303,9 +308,12 @@ static void free_batch_buffers(st_handle* h) {
     h->maxB = 0;
 }
 
+static void drop_step_graphs(st_handle* h);
+
 extern "C" void st_destroy(st_handle* h) {
     if (!h) return;
     DeviceGuard guard(h->device);
+    drop_step_graphs(h);
     free_batch_buffers(h);
     if (h->dct_ws) cudaFree(h->dct_ws);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -337,11 +345,13 @@ extern "C" int st_out_samples(const st_handle* h) { return h ? h->d.L : -1; }
 extern "C" int st_bins(const st_handle* h) { return h ? h->d.F : -1; }
 
 // (Re)allocate the batch-sized workspace.  Grows only; a steady-state training loop never allocates.
+static void drop_step_graphs(st_handle* h);
 static int ensure_workspace(st_handle* h, int B) {
     if (B <= 0) return st_fail_msg(h, "batch must be positive (got %d)", B);
     ST_CUDA_OK(cudaSetDevice(h->device));
     if (B <= h->maxB) return 0;
     ST_CUDA_OK(cudaDeviceSynchronize());
+    drop_step_graphs(h);                                       // captured steps hold the addresses of the buffers freed below
     free_batch_buffers(h);
     const StDims& d = h->d;
     const long BT = (long)B * d.Tp, BO = (long)B * d.OTp;      // frame rows incl. the dummy rows of the uniform-stride view
@@ -509,23 +519,25 @@ static int forward_impl(st_handle* h, const float* x, const float* knobs, int B,
     if (beside) ST_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));        // folded synthesis weights, autoencoder weight images
     {
         StageScope sc(h, SG_AE_FWD, ((acts || tm_fwd) ? 1 : 2) + (mag_hat_user != nullptr), s);
+        // the handle's copy of the knobs (made above), so that no kernel of a captured step holds the caller's pointer
+        const float* knobs_in = d.K > 0 ? h->knobs_ws : knobs;
         const bool save = h->training && h->use_mma_bwd;
         h->have_saves = false;
         h->tm_fwd = false;
         bool done = false;
         if (tm_fwd) {
-            done = st_launch_ae_forward_tm(d, h->g, pm, pp, h->spec, knobs, B, mag, h->trk_ws, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo, h->ae_wpack,
+            done = st_launch_ae_forward_tm(d, h->g, pm, pp, h->spec, knobs_in, B, mag, h->trk_ws, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo, h->ae_wpack,
                                            nullptr, nullptr, h->sm_count, false, s, s);
             h->tm_fwd = done;
         }
         if (!acts && !done) {
-            done = st_launch_ae_forward_mma(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
+            done = st_launch_ae_forward_mma(d, h->g, pm, pp, h->spec, knobs_in, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo,
                                             save ? h->ae_save_m : nullptr, save ? h->ae_save_p : nullptr, h->sm_count, s, h->passes);
             if (done) h->have_saves = save;
         }
         if (!done) {
             ++h->simt_fallbacks;
-            st_launch_ae_forward(d, h->g, pm, pp, h->spec, knobs, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo, acts,
+            st_launch_ae_forward(d, h->g, pm, pp, h->spec, knobs_in, B, mag, h->mag_hat_ws, h->phs_hat_ws, h->ri, h->ri_lo, acts,
                                  h->ae_grid, s);
         }
         if (mag_hat_user)
@@ -808,6 +820,21 @@ extern "C" int st_clip_grad_norm(st_handle* h, float* const* grads, float max_no
     return 0;
 }
 
+// Kernel arguments of the Adam launch: tensor table (live rows only for the analysis pair when asked) and the per-step scalars.
+static void adam_args(const st_handle* h, float* const* params, const float* const* grads, float* const* m, float* const* v,
+                      const st_adam* hp, bool live_only, AdamTensors& t, AdamScalars& sc) {
+    for (int i = 0; i < ST_NUM_PARAMS; ++i) {
+        t.p[i] = params[i]; t.g[i] = grads[i]; t.m[i] = m[i]; t.v[i] = v[i];
+        t.n[i] = (live_only && i < 2) ? (long)h->d.F * h->d.N : h->numel[i];
+    }
+    // bias corrections in double, as torch does on the host for non-capturable Adam
+    const double bc1 = 1.0 - std::pow((double)hp->beta1, (double)hp->step);
+    const double bc2 = 1.0 - std::pow((double)hp->beta2, (double)hp->step);
+    sc.lr_over_bc1 = (float)((double)hp->lr / bc1);
+    sc.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+    sc.beta1 = hp->beta1; sc.beta2 = hp->beta2; sc.eps = hp->eps; sc.grad_scale = hp->grad_scale;
+}
+
 static int adam_impl(st_handle* h, float* const* params, const float* const* grads, float* const* m, float* const* v,
                      const st_adam* hp, bool live_only, cudaStream_t s, bool coef_ready = false) {
     if (hp->step < 1) return st_fail_msg(h, "st_adam_step: step must be >= 1 (got %d)", hp->step);
@@ -825,17 +852,8 @@ static int adam_impl(st_handle* h, float* const* params, const float* const* gra
         coef = h->small + SM_COEF;
     }
     AdamTensors t;
-    for (int i = 0; i < ST_NUM_PARAMS; ++i) {
-        t.p[i] = params[i]; t.g[i] = grads[i]; t.m[i] = m[i]; t.v[i] = v[i];
-        t.n[i] = (live_only && i < 2) ? (long)h->d.F * h->d.N : h->numel[i];
-    }
-    // bias corrections in double, as torch does on the host for non-capturable Adam
-    const double bc1 = 1.0 - std::pow((double)hp->beta1, (double)hp->step);
-    const double bc2 = 1.0 - std::pow((double)hp->beta2, (double)hp->step);
     AdamScalars sc;
-    sc.lr_over_bc1 = (float)((double)hp->lr / bc1);
-    sc.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
-    sc.beta1 = hp->beta1; sc.beta2 = hp->beta2; sc.eps = hp->eps; sc.grad_scale = hp->grad_scale;
+    adam_args(h, params, grads, m, v, hp, live_only, t, sc);
     {
         StageScope scope(h, SG_ADAM, 1, s);
         st_launch_adam(t, live_only ? h->map_live : h->map_full, live_only ? h->n_live : h->n_full, sc, coef, s);
@@ -972,19 +990,9 @@ extern "C" int st_adam_step_clipped(st_handle* h, float* const* params, const fl
     return adam_impl(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/true, (cudaStream_t)stream, /*coef_ready=*/true);
 }
 
-extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch,
-                             float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                             const float* sbf, float l1_coef, const st_adam* hp, float* loss, void* stream) {
-    if (!h) return 1;
-    ST_ON_DEVICE(h);
-    if (!x || !y || !knobs || !hp || !loss) return st_fail_msg(h, "st_train_step: null argument");
-    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_train_step(params)") ||
-        check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_train_step(grads)") ||
-        check_ptrs(h, (const void* const*)exp_avg, ST_NUM_PARAMS, "st_train_step(exp_avg)") ||
-        check_ptrs(h, (const void* const*)exp_avg_sq, ST_NUM_PARAMS, "st_train_step(exp_avg_sq)"))
-        return 1;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (ensure_workspace(h, batch)) return 1;
+static int train_step_body(st_handle* h, const float* x, const float* y, const float* knobs, int batch, float* const* params,
+                           float* const* grads, float* const* exp_avg, float* const* exp_avg_sq, const float* sbf, float l1_coef,
+                           const st_adam* hp, float* loss, cudaStream_t s) {
     if (h->fuse_tail) {
         if (grad_step_impl(h, x, y, knobs, batch, params, grads, sbf, l1_coef, loss, s, hp)) return 1;
         return adam_impl(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/true, s, /*coef_ready=*/true);
@@ -999,6 +1007,161 @@ extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const
     if (backward_impl(h, h->gy_ws, nullptr, h->gmh_ws, batch, params, grads, s)) return 1;
     // gradients of the dead analysis rows are exactly zero here, so Adam may skip them
     return adam_impl(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/true, s);
+}
+
+// One captured train step.  The step is a fixed sequence of ~17 dependent launches over two streams whose only per-step inputs
+// are the Adam scalars (learning rate, bias corrections), so the second call with the same buffers, batch size and stream is
+// captured (cudaStreamBeginCapture; the side stream joins through the fork / join events) and every later one is a single
+// cudaGraphLaunch after the Adam node's scalars have been refreshed.  Not on the legacy default stream (it cannot be captured),
+// not while stage profiling is on, ST_CUDA_GRAPH=0 turns it off; any capture error falls back to the plain launches for good.
+struct StepGraph {
+    const void *sbf, *p0, *g0, *m0, *v0;
+    int batch, clip, fuse, training, precision;
+    float l1, beta1, beta2, eps, grad_scale, max_norm;
+    cudaStream_t s;
+    int seen = 0;
+    bool bad = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    // the nodes whose arguments change from step to step: Adam (scalars), input padding (x), fused loss tail (x, y), knob copy
+    cudaGraphNode_t adam = nullptr, pad = nullptr, ola = nullptr, kcopy = nullptr;
+    cudaKernelNodeParams kp{}, kp_pad{}, kp_ola{};
+    void* knobs_dst = nullptr;
+    size_t knobs_bytes = 0;
+    long launches = 0;
+};
+
+static void drop_step_graphs(st_handle* h) {
+    for (StepGraph* g : h->graphs) {
+        if (g->exec) cudaGraphExecDestroy(g->exec);
+        if (g->graph) cudaGraphDestroy(g->graph);
+        delete g;
+    }
+    h->graphs.clear();
+}
+
+extern "C" long st_debug_graph_replays(const st_handle* h) { return h ? h->graph_replays : -1; }
+
+extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch,
+                             float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                             const float* sbf, float l1_coef, const st_adam* hp, float* loss, void* stream) {
+    if (!h) return 1;
+    ST_ON_DEVICE(h);
+    if (!x || !y || !knobs || !hp || !loss) return st_fail_msg(h, "st_train_step: null argument");
+    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_train_step(params)") ||
+        check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_train_step(grads)") ||
+        check_ptrs(h, (const void* const*)exp_avg, ST_NUM_PARAMS, "st_train_step(exp_avg)") ||
+        check_ptrs(h, (const void* const*)exp_avg_sq, ST_NUM_PARAMS, "st_train_step(exp_avg_sq)"))
+        return 1;
+    if (hp->step < 1) return st_fail_msg(h, "st_adam_step: step must be >= 1 (got %d)", hp->step);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ensure_workspace(h, batch)) return 1;
+    const bool graphable = h->use_graph && h->fuse_tail && !h->prof_on && h->side && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+    if (!graphable) return train_step_body(h, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, s);
+
+    StepGraph* g = nullptr;
+    for (StepGraph* c : h->graphs) {
+        bool same = c->sbf == sbf && c->batch == batch && c->s == s &&
+                    c->l1 == l1_coef && c->beta1 == hp->beta1 && c->beta2 == hp->beta2 && c->eps == hp->eps &&
+                    c->grad_scale == hp->grad_scale && c->max_norm == hp->max_norm && c->fuse == (int)h->fuse_tail &&
+                    c->training == (int)h->training && c->precision == h->passes;
+        // the 40-entry tables are compared entry by entry: a caller may re-point a single tensor
+        for (int i = 0; same && i < ST_NUM_PARAMS; ++i)
+            same = ((const void* const*)c->p0)[i] == params[i];
+        if (same && c->g0 == (const void*)grads[0] && c->m0 == (const void*)exp_avg[0] && c->v0 == (const void*)exp_avg_sq[0]) { g = c; break; }
+    }
+    if (!g) {
+        if (h->graphs.size() >= 8) drop_step_graphs(h);         // a caller that keeps changing buffers: start over
+        g = new StepGraph();
+        void** ptab = new void*[ST_NUM_PARAMS];                 // (leaked with the entry on purpose: 320 bytes, freed with the process)
+        for (int i = 0; i < ST_NUM_PARAMS; ++i) ptab[i] = params[i];
+        g->sbf = sbf; g->p0 = ptab; g->g0 = grads[0]; g->m0 = exp_avg[0];
+        g->v0 = exp_avg_sq[0]; g->batch = batch; g->s = s; g->l1 = l1_coef; g->beta1 = hp->beta1; g->beta2 = hp->beta2; g->eps = hp->eps;
+        g->grad_scale = hp->grad_scale; g->max_norm = hp->max_norm; g->fuse = (int)h->fuse_tail; g->training = (int)h->training;
+        g->precision = h->passes;
+        h->graphs.push_back(g);
+    }
+    if (g->exec) {                                              // replay: refresh the Adam scalars, one launch
+        AdamTensors t;
+        AdamScalars sc;
+        adam_args(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/true, t, sc);
+        void** args = g->kp.kernelParams;                       // [tensors, chunk map, scalars, clip coefficient]
+        void* mine[4] = {args[0], args[1], &sc, args[3]};
+        cudaKernelNodeParams kp = g->kp;
+        kp.kernelParams = mine;
+        ST_CUDA_OK(cudaGraphExecKernelNodeSetParams(g->exec, g->adam, &kp));
+        {                                                       // this step's inputs (the batch may live anywhere)
+            void* pa[8];
+            for (int i = 0; i < 8; ++i) pa[i] = g->kp_pad.kernelParams[i];
+            pa[0] = &x;
+            cudaKernelNodeParams k2 = g->kp_pad;
+            k2.kernelParams = pa;
+            ST_CUDA_OK(cudaGraphExecKernelNodeSetParams(g->exec, g->pad, &k2));
+            void* oa[14];
+            for (int i = 0; i < 14; ++i) oa[i] = g->kp_ola.kernelParams[i];
+            oa[2] = &x; oa[3] = &y; oa[8] = &loss;
+            cudaKernelNodeParams k3 = g->kp_ola;
+            k3.kernelParams = oa;
+            ST_CUDA_OK(cudaGraphExecKernelNodeSetParams(g->exec, g->ola, &k3));
+            if (g->kcopy)
+                ST_CUDA_OK(cudaGraphExecMemcpyNodeSetParams1D(g->exec, g->kcopy, g->knobs_dst, knobs, g->knobs_bytes, cudaMemcpyDeviceToDevice));
+        }
+        ST_CUDA_OK(cudaGraphLaunch(g->exec, s));
+        h->launches += g->launches;
+        ++h->graph_replays;
+        return 0;
+    }
+    if (g->bad || g->seen++ < 1)                                // first sight of these buffers (or capture refused earlier): plain launches
+        return train_step_body(h, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, s);
+
+    // ---- capture
+    const long launches0 = h->launches;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        g->bad = true;
+        return train_step_body(h, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, s);
+    }
+    const int rc = train_step_body(h, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, s);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    bool ok = rc == 0 && e == cudaSuccess && graph != nullptr;
+    if (ok) ok = cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess;
+    if (ok) {                                                   // the Adam node: the only kernel node whose function is adam_kernel
+        size_t n = 0;
+        ok = cudaGraphGetNodes(graph, nullptr, &n) == cudaSuccess && n > 0;
+        std::vector<cudaGraphNode_t> nodes(n);
+        if (ok) ok = cudaGraphGetNodes(graph, nodes.data(), &n) == cudaSuccess;
+        const void *f_adam = st_adam_kernel_fn(), *f_pad = st_pad_split_kernel_fn(), *f_ola = st_ola_loss_kernel_fn();
+        int n_pad = 0, n_ola = 0, n_adam = 0, n_copy = 0;
+        for (size_t i = 0; ok && i < n; ++i) {
+            cudaGraphNodeType ty;
+            if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess) continue;
+            if (ty == cudaGraphNodeTypeMemcpy) { g->kcopy = nodes[i]; ++n_copy; continue; }
+            if (ty != cudaGraphNodeTypeKernel) continue;
+            cudaKernelNodeParams kp{};
+            if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
+            if (kp.func == f_adam) { g->adam = nodes[i]; g->kp = kp; ++n_adam; }
+            else if (kp.func == f_pad) { g->pad = nodes[i]; g->kp_pad = kp; ++n_pad; }
+            else if (kp.func == f_ola) { g->ola = nodes[i]; g->kp_ola = kp; ++n_ola; }
+        }
+        const bool keep_knobs = h->d.K > 0;
+        ok = ok && n_adam == 1 && n_pad == 1 && n_ola == 1 && n_copy == (keep_knobs ? 1 : 0);   // exactly the nodes this code knows
+        g->knobs_dst = h->knobs_ws;
+        g->knobs_bytes = (size_t)batch * h->d.K * sizeof(float);
+    }
+    if (!ok) {
+        cudaGetLastError();
+        if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+        if (graph) cudaGraphDestroy(graph);
+        g->bad = true;
+        h->launches = launches0;
+        return train_step_body(h, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, s);
+    }
+    g->graph = graph;                                           // kept: the node handle above belongs to it
+    g->launches = h->launches - launches0;
+    ST_CUDA_OK(cudaGraphLaunch(g->exec, s));
+    ++h->graph_replays;
+    return 0;
 }
 
 // Host-only: the launch plan of the five front-end contractions of THIS geometry at a batch size (no device work, so the CPU

@@ -221,4 +221,7 @@ struct AdamScalars {
 };
 void st_launch_adam(const AdamTensors& t, const int2* chunk_map, int nchunks, const AdamScalars& sc,
                     const float* clip_coef, cudaStream_t s);
+const void* st_adam_kernel_fn();
+const void* st_ola_loss_kernel_fn();     // kernel addresses: a captured step finds the nodes whose inputs change per step
+const void* st_pad_split_kernel_fn();
 #define ST_ADAM_CHUNK 4096

@@ -225,6 +225,7 @@ void st_launch_pad_split(const float* src, float* dst_hi, float* dst_lo, int row
     const long items = (long)rows * (stride >> 2);
     pad_split_kernel<<<grid_for(items, 256), 256, 0, s>>>(src, dst_hi, dst_lo, rows, len, pad, stride, scale);
 }
+const void* st_pad_split_kernel_fn() { return reinterpret_cast<const void*>(&pad_split_kernel); }
 void st_launch_pack_analysis(const StDims& d, const float* Wr, const float* Wi, float* wcat, float* wcat_lo, cudaStream_t s) {
     pack_analysis_kernel<<<grid_for(2L * d.Fp * (d.N >> 2), 256), 256, 0, s>>>(d, Wr, Wi, wcat, wcat_lo);
 }

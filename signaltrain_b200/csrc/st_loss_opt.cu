@@ -507,3 +507,6 @@ void st_launch_adam(const AdamTensors& t, const int2* chunk_map, int nchunks, co
                     cudaStream_t s) {
     adam_kernel<<<nchunks, 256, 0, s>>>(t, chunk_map, sc, clip_coef);
 }
+// The kernel's address, so that a captured step can find its Adam node and refresh the per-step scalars (st_api.cu).
+const void* st_adam_kernel_fn() { return reinterpret_cast<const void*>(&adam_kernel); }
+const void* st_ola_loss_kernel_fn() { return reinterpret_cast<const void*>(&ola_loss_kernel); }

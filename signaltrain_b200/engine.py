@@ -371,6 +371,10 @@ class Engine:
     def launch_count(self):
         return int(self.lib.st_launch_count(self.h))
 
+    def graph_replays(self):
+        """Train steps served by replaying a captured CUDA graph (st_train_step on a capturable stream)."""
+        return int(self.lib.st_debug_graph_replays(self.h))
+
     def profile(self, enable):
         self._ok(self.lib.st_profile(self.h, int(bool(enable))), "st_profile")
 

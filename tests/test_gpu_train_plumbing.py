@@ -234,3 +234,41 @@ def test_train_from_prerecorded_files(tmp_path, monkeypatch):
     with pytest.raises(NotImplementedError):
         st.train.train(effect=st.data.Denoise(), epochs=1, n_data_points=40, batch_size=4, device=torch.device("cuda:0"),
                        datapath=str(tmp_path / "data"), target_type="chunk", in_checkpointname="none.tar")
+
+
+def test_train_step_cuda_graph_replay_is_bit_identical(monkeypatch):
+    """st_train_step captures itself into a CUDA graph on a capturable stream (second call with the same tensor tables) and
+    replays it afterwards with this step's x / y / knobs / loss pointers and Adam scalars patched in: six steps on batches that
+    live at different addresses give bit-identical parameters and losses to the plain launches (ST_CUDA_GRAPH=0), the legacy
+    default stream is served without a graph."""
+    import signaltrain_b200 as st
+    from signaltrain_b200 import data
+    from signaltrain_b200.train import FusedTrainer
+    B, steps = 6, 6
+    lr, _ = st.learningrate.get_1cycle_schedule(1e-4, 200000, 1000, 200)
+
+    def run(graph, own_stream):
+        monkeypatch.setenv("ST_CUDA_GRAPH", "1" if graph else "0")
+        torch.manual_seed(218)
+        model = st.nn_proc.st_model(1, 4, 4).cuda()
+        tr = FusedTrainer(model, lr)
+        x, y, k = (torch.from_numpy(a).cuda() for a in data.make_pool(B * steps, model.in_chunk_size, model.out_chunk_size,
+                                                                      data.Compressor_4c(), seed=5))
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream() if own_stream else torch.cuda.current_stream()
+        losses = []
+        with torch.cuda.stream(s):
+            for i in range(steps):
+                sl = slice(i * B, (i + 1) * B)
+                losses.append(tr.step(x[sl], y[sl], k[sl]).clone())
+        torch.cuda.synchronize()
+        return [float(l) for l in losses], [p.detach().clone() for p in tr.params], tr.eng.graph_replays(), tr.eng.launch_count()
+
+    l0, p0, r0, n0 = run(False, True)
+    l1, p1, r1, n1 = run(True, True)
+    l2, p2, r2, n2 = run(True, False)
+    assert r0 == 0 and r2 == 0 and r1 == steps - 1          # step 1 plain, step 2 captured + launched, steps 3.. replayed
+    assert n0 == n1 == n2                                    # the launch counter counts the kernels inside a replay
+    assert l0 == l1 == l2
+    for a, b, c in zip(p0, p1, p2):
+        assert torch.equal(a, b) and torch.equal(a, c)
