@@ -731,7 +731,8 @@ template <int NT9, int PASSES>
 void launch_fwd_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const AeParams& pm, const AeParams& pp, const float* spec,
                      const float* knobs, int B, float* mag, float* mag_hat, float* phs_hat, float* ri, float* ri_lo, float* save_m,
                      float* save_p, int grid, size_t smem, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_on[ST_MAX_DEVICES] = {};              // function attributes are per device (context), not per process
+    bool& configured = configured_on[st_current_device_slot()];
     if (!configured) {
         cudaFuncSetAttribute(ae_fwd_mma_kernel<NT9, 0, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(ae_fwd_mma_kernel<NT9, 1, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -770,7 +771,8 @@ void launch_bwd_pair(const StDims& d, const AeGeom& g, const MmaGeom& mg, const 
                      int B, const float* save_m, const float* save_p, const float* mag_hat, const float* phs_hat, const float* g_ri,
                      const float* g_mag_hat, const float* g_mag, float* tail_ws, float* g_spec, float* g_spec_lo, float* partials,
                      long long* timing, int grid, size_t smem, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_on[ST_MAX_DEVICES] = {};              // function attributes are per device (context), not per process
+    bool& configured = configured_on[st_current_device_slot()];
     if (!configured) {
         cudaFuncSetAttribute(ae_bwd_mma_kernel<NT1, 0, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(ae_bwd_mma_kernel<NT1, 1, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

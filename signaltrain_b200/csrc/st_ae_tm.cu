@@ -1264,7 +1264,8 @@ bool launch_fwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AePa
                 long long* timing, int sm_count, bool pack, cudaStream_t s_pack, cudaStream_t s) {
     constexpr size_t smem = fwd_smem_bytes<TB>();
     static_assert(smem <= 227 * 1024, "forward tile does not fit shared memory");
-    static bool configured = false;
+    static bool configured_on[ST_MAX_DEVICES] = {};              // function attributes are per device (context), not per process
+    bool& configured = configured_on[st_current_device_slot()];
     if (!configured) {
         if (cudaFuncSetAttribute(ae_fwd_tm_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
         configured = true;
@@ -1313,7 +1314,8 @@ int launch_bwd(const StDims& d, const AeGeom& g, const AeParams& pm, const AePar
                cudaStream_t s_pack, cudaStream_t s) {
     constexpr size_t smem = BwdSmem<TB>::TOTAL;
     static_assert(smem <= 227 * 1024, "backward tile does not fit shared memory");
-    static bool configured = false;
+    static bool configured_on[ST_MAX_DEVICES] = {};              // function attributes are per device (context), not per process
+    bool& configured = configured_on[st_current_device_slot()];
     if (!configured) {
         if (cudaFuncSetAttribute(ae_bwd_tm_kernel<TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
         if (cudaFuncSetAttribute(ae_bwd_tm_kernel<TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;

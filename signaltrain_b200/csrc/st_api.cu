@@ -943,14 +943,18 @@ extern "C" int st_unpack_grads(st_handle* h, const float* packed, float* const* 
     return pack_impl(h, grads, const_cast<float*>(packed), 1, (cudaStream_t)stream);
 }
 
+static int step_with_graph(st_handle* h, int kind, const float* x, const float* y, const float* knobs, int batch, float* const* params,
+                           float* const* grads, float* const* exp_avg, float* const* exp_avg_sq, const float* sbf, float l1_coef,
+                           const st_adam* hp, float* loss, float* packed, cudaStream_t s);
+
 extern "C" int st_grad_step_packed(st_handle* h, const float* x, const float* y, const float* knobs, int batch, float* const* params,
                                    float* packed, const float* sbf, float l1_coef, float* loss, void* stream) {
     if (!h) return 1;
     ST_ON_DEVICE(h);
     if (!x || !y || !knobs || !loss || !packed) return st_fail_msg(h, "st_grad_step_packed: null argument");
     if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_grad_step_packed(params)")) return 1;
-    if (ensure_workspace(h, batch)) return 1;
-    return grad_step_impl(h, x, y, knobs, batch, params, nullptr, sbf, l1_coef, loss, (cudaStream_t)stream, nullptr, packed);
+    return step_with_graph(h, 1, x, y, knobs, batch, params, nullptr, nullptr, nullptr, sbf, l1_coef, nullptr, loss, packed,
+                           (cudaStream_t)stream);
 }
 
 extern "C" int st_unpack_clip(st_handle* h, const float* packed, float* const* grads, float grad_scale, float max_norm,
@@ -1015,9 +1019,9 @@ static int train_step_body(st_handle* h, const float* x, const float* y, const f
 // cudaGraphLaunch after the Adam node's scalars have been refreshed.  Not on the legacy default stream (it cannot be captured),
 // not while stage profiling is on, ST_CUDA_GRAPH=0 turns it off; any capture error falls back to the plain launches for good.
 struct StepGraph {
-    const void *sbf, *p0, *g0, *m0, *v0;
-    int batch, clip, fuse, training, precision;
-    float l1, beta1, beta2, eps, grad_scale, max_norm;
+    const void *sbf, *p0, *g0 = nullptr, *m0 = nullptr, *v0 = nullptr, *packed = nullptr;
+    int kind = 0, batch, clip, fuse, training, precision;
+    float l1, beta1 = 0.f, beta2 = 0.f, eps = 0.f, grad_scale = 0.f, max_norm = 0.f;
     cudaStream_t s;
     int seen = 0;
     bool bad = false;
@@ -1042,54 +1046,59 @@ static void drop_step_graphs(st_handle* h) {
 
 extern "C" long st_debug_graph_replays(const st_handle* h) { return h ? h->graph_replays : -1; }
 
-extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch,
-                             float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                             const float* sbf, float l1_coef, const st_adam* hp, float* loss, void* stream) {
-    if (!h) return 1;
-    ST_ON_DEVICE(h);
-    if (!x || !y || !knobs || !hp || !loss) return st_fail_msg(h, "st_train_step: null argument");
-    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_train_step(params)") ||
-        check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_train_step(grads)") ||
-        check_ptrs(h, (const void* const*)exp_avg, ST_NUM_PARAMS, "st_train_step(exp_avg)") ||
-        check_ptrs(h, (const void* const*)exp_avg_sq, ST_NUM_PARAMS, "st_train_step(exp_avg_sq)"))
-        return 1;
-    if (hp->step < 1) return st_fail_msg(h, "st_adam_step: step must be >= 1 (got %d)", hp->step);
-    cudaStream_t s = (cudaStream_t)stream;
+// kind 0: st_train_step (forward .. Adam); kind 1: st_grad_step_packed (forward .. packed gradient payload, no update)
+static int step_body(st_handle* h, int kind, const float* x, const float* y, const float* knobs, int batch, float* const* params,
+                     float* const* grads, float* const* exp_avg, float* const* exp_avg_sq, const float* sbf, float l1_coef,
+                     const st_adam* hp, float* loss, float* packed, cudaStream_t s) {
+    if (kind == 0) return train_step_body(h, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, s);
+    return grad_step_impl(h, x, y, knobs, batch, params, nullptr, sbf, l1_coef, loss, s, nullptr, packed);
+}
+
+static int step_with_graph(st_handle* h, int kind, const float* x, const float* y, const float* knobs, int batch, float* const* params,
+                           float* const* grads, float* const* exp_avg, float* const* exp_avg_sq, const float* sbf, float l1_coef,
+                           const st_adam* hp, float* loss, float* packed, cudaStream_t s) {
     if (ensure_workspace(h, batch)) return 1;
     const bool graphable = h->use_graph && h->fuse_tail && !h->prof_on && h->side && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
-    if (!graphable) return train_step_body(h, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, s);
+    if (!graphable) return step_body(h, kind, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, packed, s);
 
     StepGraph* g = nullptr;
     for (StepGraph* c : h->graphs) {
-        bool same = c->sbf == sbf && c->batch == batch && c->s == s &&
-                    c->l1 == l1_coef && c->beta1 == hp->beta1 && c->beta2 == hp->beta2 && c->eps == hp->eps &&
-                    c->grad_scale == hp->grad_scale && c->max_norm == hp->max_norm && c->fuse == (int)h->fuse_tail &&
-                    c->training == (int)h->training && c->precision == h->passes;
+        bool same = c->kind == kind && c->packed == (const void*)packed && c->sbf == sbf && c->batch == batch && c->s == s &&
+                    c->l1 == l1_coef && c->fuse == (int)h->fuse_tail && c->training == (int)h->training && c->precision == h->passes;
+        if (same && kind == 0)
+            same = c->beta1 == hp->beta1 && c->beta2 == hp->beta2 && c->eps == hp->eps && c->grad_scale == hp->grad_scale &&
+                   c->max_norm == hp->max_norm;
         // the 40-entry tables are compared entry by entry: a caller may re-point a single tensor
         for (int i = 0; same && i < ST_NUM_PARAMS; ++i)
             same = ((const void* const*)c->p0)[i] == params[i];
-        if (same && c->g0 == (const void*)grads[0] && c->m0 == (const void*)exp_avg[0] && c->v0 == (const void*)exp_avg_sq[0]) { g = c; break; }
+        if (same && kind == 0) same = c->g0 == (const void*)grads[0] && c->m0 == (const void*)exp_avg[0] && c->v0 == (const void*)exp_avg_sq[0];
+        if (same) { g = c; break; }
     }
     if (!g) {
         if (h->graphs.size() >= 8) drop_step_graphs(h);         // a caller that keeps changing buffers: start over
         g = new StepGraph();
         void** ptab = new void*[ST_NUM_PARAMS];                 // (leaked with the entry on purpose: 320 bytes, freed with the process)
         for (int i = 0; i < ST_NUM_PARAMS; ++i) ptab[i] = params[i];
-        g->sbf = sbf; g->p0 = ptab; g->g0 = grads[0]; g->m0 = exp_avg[0];
-        g->v0 = exp_avg_sq[0]; g->batch = batch; g->s = s; g->l1 = l1_coef; g->beta1 = hp->beta1; g->beta2 = hp->beta2; g->eps = hp->eps;
-        g->grad_scale = hp->grad_scale; g->max_norm = hp->max_norm; g->fuse = (int)h->fuse_tail; g->training = (int)h->training;
+        g->kind = kind; g->packed = packed; g->sbf = sbf; g->p0 = ptab; g->batch = batch; g->s = s; g->l1 = l1_coef;
+        if (kind == 0) {
+            g->g0 = grads[0]; g->m0 = exp_avg[0]; g->v0 = exp_avg_sq[0];
+            g->beta1 = hp->beta1; g->beta2 = hp->beta2; g->eps = hp->eps; g->grad_scale = hp->grad_scale; g->max_norm = hp->max_norm;
+        }
+        g->fuse = (int)h->fuse_tail; g->training = (int)h->training;
         g->precision = h->passes;
         h->graphs.push_back(g);
     }
     if (g->exec) {                                              // replay: refresh the Adam scalars, one launch
-        AdamTensors t;
-        AdamScalars sc;
-        adam_args(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/true, t, sc);
-        void** args = g->kp.kernelParams;                       // [tensors, chunk map, scalars, clip coefficient]
-        void* mine[4] = {args[0], args[1], &sc, args[3]};
-        cudaKernelNodeParams kp = g->kp;
-        kp.kernelParams = mine;
-        ST_CUDA_OK(cudaGraphExecKernelNodeSetParams(g->exec, g->adam, &kp));
+        if (kind == 0) {
+            AdamTensors t;
+            AdamScalars sc;
+            adam_args(h, params, grads, exp_avg, exp_avg_sq, hp, /*live_only=*/true, t, sc);
+            void** args = g->kp.kernelParams;                   // [tensors, chunk map, scalars, clip coefficient]
+            void* mine[4] = {args[0], args[1], &sc, args[3]};
+            cudaKernelNodeParams kp = g->kp;
+            kp.kernelParams = mine;
+            ST_CUDA_OK(cudaGraphExecKernelNodeSetParams(g->exec, g->adam, &kp));
+        }
         {                                                       // this step's inputs (the batch may live anywhere)
             void* pa[8];
             for (int i = 0; i < 8; ++i) pa[i] = g->kp_pad.kernelParams[i];
@@ -1112,16 +1121,16 @@ extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const
         return 0;
     }
     if (g->bad || g->seen++ < 1)                                // first sight of these buffers (or capture refused earlier): plain launches
-        return train_step_body(h, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, s);
+        return step_body(h, kind, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, packed, s);
 
     // ---- capture
     const long launches0 = h->launches;
     if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError();
         g->bad = true;
-        return train_step_body(h, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, s);
+        return step_body(h, kind, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, packed, s);
     }
-    const int rc = train_step_body(h, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, s);
+    const int rc = step_body(h, kind, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, packed, s);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(s, &graph);
     bool ok = rc == 0 && e == cudaSuccess && graph != nullptr;
@@ -1145,7 +1154,7 @@ extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const
             else if (kp.func == f_ola) { g->ola = nodes[i]; g->kp_ola = kp; ++n_ola; }
         }
         const bool keep_knobs = h->d.K > 0;
-        ok = ok && n_adam == 1 && n_pad == 1 && n_ola == 1 && n_copy == (keep_knobs ? 1 : 0);   // exactly the nodes this code knows
+        ok = ok && n_adam == (kind == 0 ? 1 : 0) && n_pad == 1 && n_ola == 1 && n_copy == (keep_knobs ? 1 : 0);   // exactly the nodes this code knows
         g->knobs_dst = h->knobs_ws;
         g->knobs_bytes = (size_t)batch * h->d.K * sizeof(float);
     }
@@ -1155,13 +1164,28 @@ extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const
         if (graph) cudaGraphDestroy(graph);
         g->bad = true;
         h->launches = launches0;
-        return train_step_body(h, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, s);
+        return step_body(h, kind, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, packed, s);
     }
     g->graph = graph;                                           // kept: the node handle above belongs to it
     g->launches = h->launches - launches0;
     ST_CUDA_OK(cudaGraphLaunch(g->exec, s));
     ++h->graph_replays;
     return 0;
+}
+
+extern "C" int st_train_step(st_handle* h, const float* x, const float* y, const float* knobs, int batch,
+                             float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                             const float* sbf, float l1_coef, const st_adam* hp, float* loss, void* stream) {
+    if (!h) return 1;
+    ST_ON_DEVICE(h);
+    if (!x || !y || !knobs || !hp || !loss) return st_fail_msg(h, "st_train_step: null argument");
+    if (check_ptrs(h, (const void* const*)params, ST_NUM_PARAMS, "st_train_step(params)") ||
+        check_ptrs(h, (const void* const*)grads, ST_NUM_PARAMS, "st_train_step(grads)") ||
+        check_ptrs(h, (const void* const*)exp_avg, ST_NUM_PARAMS, "st_train_step(exp_avg)") ||
+        check_ptrs(h, (const void* const*)exp_avg_sq, ST_NUM_PARAMS, "st_train_step(exp_avg_sq)"))
+        return 1;
+    if (hp->step < 1) return st_fail_msg(h, "st_adam_step: step must be >= 1 (got %d)", hp->step);
+    return step_with_graph(h, 0, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, nullptr, (cudaStream_t)stream);
 }
 
 // Host-only: the launch plan of the five front-end contractions of THIS geometry at a batch size (no device work, so the CPU

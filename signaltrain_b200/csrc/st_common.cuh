@@ -12,6 +12,14 @@
 #define ST_MAX_TFRAMES 64      // AE kernels keep ceil(T/16) register tiles; T, OT <= 64
 
 // Geometry, device-visible.  Names follow the reference.
+// per-device bookkeeping of one-time kernel configuration (cudaFuncSetAttribute applies to the current device only)
+constexpr int ST_MAX_DEVICES = 64;
+inline int st_current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < ST_MAX_DEVICES ? dev : 0;
+}
+
 struct StDims {
     int C;    // chunk
     int N;    // ft size (taps)

@@ -593,7 +593,8 @@ bool make_map(CUtensorMap* tm, const float* base, long rows, long cols, long ld,
 template <bool A_MN, bool B_MN, bool MC, int PASSES>
 cudaError_t launch_p(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcParams& p,
                    int grid, size_t smem, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_on[ST_MAX_DEVICES] = {};              // function attributes are per device (context), not per process
+    bool& configured = configured_on[st_current_device_slot()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, MC, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
@@ -621,7 +622,8 @@ cudaError_t launch_p(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
 template <bool A_MN, bool B_MN, int PASSES>
 cudaError_t launch_pair_p(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcParams& p,
                         int grid, size_t smem, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_on[ST_MAX_DEVICES] = {};              // function attributes are per device (context), not per process
+    bool& configured = configured_on[st_current_device_slot()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<A_MN, B_MN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;

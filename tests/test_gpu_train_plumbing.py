@@ -272,3 +272,37 @@ def test_train_step_cuda_graph_replay_is_bit_identical(monkeypatch):
     assert l0 == l1 == l2
     for a, b, c in zip(p0, p1, p2):
         assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_packed_grad_step_cuda_graph_replay_is_bit_identical(monkeypatch):
+    """The data-parallel rank step (st_grad_step_packed) is captured and replayed the same way: payloads bit-identical to the
+    plain launches on batches at different addresses."""
+    import signaltrain_b200 as st
+    from signaltrain_b200 import data
+    B, steps = 5, 5
+
+    def run(graph):
+        monkeypatch.setenv("ST_CUDA_GRAPH", "1" if graph else "0")
+        torch.manual_seed(218)
+        model = st.nn_proc.st_model(1, 4, 4).cuda()
+        x, y, k = (torch.from_numpy(a).cuda() for a in data.make_pool(B * steps, model.in_chunk_size, model.out_chunk_size,
+                                                                      data.Compressor_4c(), seed=9))
+        eng = model.mpaec._engine_for(x)
+        params = [p.detach() for p in model.ordered_parameters()]
+        sbf = torch.exp(torch.tensor(7.0 / eng.g.F) * torch.arange(0., eng.g.F)).float().cuda()
+        packed = torch.empty(eng.packed_grad_floats(), device="cuda")
+        out, losses = [], []
+        torch.cuda.synchronize()
+        with torch.cuda.stream(torch.cuda.Stream()):
+            for i in range(steps):
+                sl = slice(i * B, (i + 1) * B)
+                losses.append(eng.grad_step_packed(x[sl], y[sl], k[sl], params, packed, sbf, 2e-6).clone())
+                out.append(packed.clone())
+        torch.cuda.synchronize()
+        return out, [float(l) for l in losses], eng.graph_replays()
+
+    a, la, ra = run(False)
+    b, lb, rb = run(True)
+    assert ra == 0 and rb == steps - 1 and la == lb
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
