@@ -1161,7 +1161,10 @@ ae_bwd_tm_kernel(StDims d, AeGeom g, BwdArgs a) {
                 for (int j = 0; j < 8; ++j) {
                     const float e9 = elu_f(__uint_as_float(rr[j]) + bl[j]);
                     if (mydbg) mydbg[(long)(NL - 1) * TILE * 64 + j0 + j] = e9;
-                    const float2 sc = sincos_ni(phv[j]);
+                    // sin / cos of phs_hat for the polar->rect gradient: the fast approximations (abs error ~1e-6 for |x| of a few
+                    // radians) are far inside the gradient tolerance and keep 8 x 40 instructions off every tile's critical path
+                    float2 sc;
+                    __sincosf(phv[j], &sc.x, &sc.y);
                     float tb;
                     if (ae == 0) {                  // an = mag_hat (cos, sin);  mag_hat = ELU(dec) * track tail
                         const float gm = gre[j] * sc.y + gim[j] * sc.x + x3[j];
