@@ -36,9 +36,11 @@ def nccl_env_defaults(world):
     8 GPUs 0.815-0.826 vs 0.804-0.808 (tree + LL128 0.830, ring + LL 0.836, ring + Simple 0.920; NVLS-only is refused for the
     float64 control reductions).  Per-collective syntax (NCCL >= 2.24), so broadcast and barrier keep their defaults."""
     import os
+    if "NCCL_ALGO" in os.environ or "NCCL_PROTO" in os.environ:
+        return
     if world >= 8 or world == 2:
-        os.environ.setdefault("NCCL_ALGO", "allreduce:ring")
-        os.environ.setdefault("NCCL_PROTO", "allreduce:LL128")
+        os.environ["NCCL_ALGO"] = "allreduce:ring"
+        os.environ["NCCL_PROTO"] = "allreduce:LL128"
 
 
 def world_size(group=None):

@@ -101,3 +101,19 @@ def test_flat_buffer_alignment():
     assert [tuple(v.shape) for v in fb.views] == [(3,), (5, 7), (1024, 1, 1024), (9,)]
     fb.views[1].fill_(2.0)
     assert fb.flat[fb.offsets[1]:fb.offsets[1] + 35].eq(2.0).all() and fb.flat[fb.offsets[1] + 35] == 0
+
+
+def test_nccl_env_defaults_only_fill_what_the_user_left_unset(monkeypatch):
+    """parallel.nccl_env_defaults: ring + LL128 for the step's allreduce at the world sizes where it measured faster (2, >= 8),
+    NCCL's own choice at 4, and never over something the user exported."""
+    from signaltrain_b200 import parallel
+    for w, want in ((2, True), (4, False), (8, True), (16, True), (1, False)):
+        monkeypatch.delenv("NCCL_ALGO", raising=False)
+        monkeypatch.delenv("NCCL_PROTO", raising=False)
+        parallel.nccl_env_defaults(w)
+        assert (os.environ.get("NCCL_ALGO") == "allreduce:ring") == want, w
+        assert (os.environ.get("NCCL_PROTO") == "allreduce:LL128") == want, w
+    monkeypatch.setenv("NCCL_ALGO", "Tree")
+    monkeypatch.delenv("NCCL_PROTO", raising=False)
+    parallel.nccl_env_defaults(8)
+    assert os.environ["NCCL_ALGO"] == "Tree" and "NCCL_PROTO" not in os.environ
