@@ -1019,8 +1019,9 @@ static int train_step_body(st_handle* h, const float* x, const float* y, const f
 // cudaGraphLaunch after the Adam node's scalars have been refreshed.  Not on the legacy default stream (it cannot be captured),
 // not while stage profiling is on, ST_CUDA_GRAPH=0 turns it off; any capture error falls back to the plain launches for good.
 struct StepGraph {
-    const void *sbf, *p0, *g0 = nullptr, *m0 = nullptr, *v0 = nullptr, *packed = nullptr;
-    int kind = 0, batch, clip, fuse, training, precision;
+    const void *sbf, *g0 = nullptr, *m0 = nullptr, *v0 = nullptr, *packed = nullptr;
+    const void* ptab[ST_NUM_PARAMS];     // the parameter table the step was captured with
+    int kind = 0, batch, fuse, training, precision;
     float l1, beta1 = 0.f, beta2 = 0.f, eps = 0.f, grad_scale = 0.f, max_norm = 0.f;
     cudaStream_t s;
     int seen = 0;
@@ -1070,16 +1071,15 @@ static int step_with_graph(st_handle* h, int kind, const float* x, const float* 
                    c->max_norm == hp->max_norm;
         // the 40-entry tables are compared entry by entry: a caller may re-point a single tensor
         for (int i = 0; same && i < ST_NUM_PARAMS; ++i)
-            same = ((const void* const*)c->p0)[i] == params[i];
+            same = c->ptab[i] == (const void*)params[i];
         if (same && kind == 0) same = c->g0 == (const void*)grads[0] && c->m0 == (const void*)exp_avg[0] && c->v0 == (const void*)exp_avg_sq[0];
         if (same) { g = c; break; }
     }
     if (!g) {
         if (h->graphs.size() >= 8) drop_step_graphs(h);         // a caller that keeps changing buffers: start over
         g = new StepGraph();
-        void** ptab = new void*[ST_NUM_PARAMS];                 // (leaked with the entry on purpose: 320 bytes, freed with the process)
-        for (int i = 0; i < ST_NUM_PARAMS; ++i) ptab[i] = params[i];
-        g->kind = kind; g->packed = packed; g->sbf = sbf; g->p0 = ptab; g->batch = batch; g->s = s; g->l1 = l1_coef;
+        for (int i = 0; i < ST_NUM_PARAMS; ++i) g->ptab[i] = params[i];
+        g->kind = kind; g->packed = packed; g->sbf = sbf; g->batch = batch; g->s = s; g->l1 = l1_coef;
         if (kind == 0) {
             g->g0 = grads[0]; g->m0 = exp_avg[0]; g->v0 = exp_avg_sq[0];
             g->beta1 = hp->beta1; g->beta2 = hp->beta2; g->eps = hp->eps; g->grad_scale = hp->grad_scale; g->max_norm = hp->max_norm;
@@ -1088,7 +1088,8 @@ static int step_with_graph(st_handle* h, int kind, const float* x, const float* 
         g->precision = h->passes;
         h->graphs.push_back(g);
     }
-    if (g->exec) {                                              // replay: refresh the Adam scalars, one launch
+    if (g->exec) {                                              // replay: refresh the per-step arguments, one launch
+        bool ok = true;
         if (kind == 0) {
             AdamTensors t;
             AdamScalars sc;
@@ -1097,28 +1098,36 @@ static int step_with_graph(st_handle* h, int kind, const float* x, const float* 
             void* mine[4] = {args[0], args[1], &sc, args[3]};
             cudaKernelNodeParams kp = g->kp;
             kp.kernelParams = mine;
-            ST_CUDA_OK(cudaGraphExecKernelNodeSetParams(g->exec, g->adam, &kp));
+            ok = cudaGraphExecKernelNodeSetParams(g->exec, g->adam, &kp) == cudaSuccess;
         }
-        {                                                       // this step's inputs (the batch may live anywhere)
+        if (ok) {                                               // this step's inputs (the batch may live anywhere)
             void* pa[8];
             for (int i = 0; i < 8; ++i) pa[i] = g->kp_pad.kernelParams[i];
             pa[0] = &x;
             cudaKernelNodeParams k2 = g->kp_pad;
             k2.kernelParams = pa;
-            ST_CUDA_OK(cudaGraphExecKernelNodeSetParams(g->exec, g->pad, &k2));
+            ok = cudaGraphExecKernelNodeSetParams(g->exec, g->pad, &k2) == cudaSuccess;
             void* oa[14];
             for (int i = 0; i < 14; ++i) oa[i] = g->kp_ola.kernelParams[i];
             oa[2] = &x; oa[3] = &y; oa[8] = &loss;
             cudaKernelNodeParams k3 = g->kp_ola;
             k3.kernelParams = oa;
-            ST_CUDA_OK(cudaGraphExecKernelNodeSetParams(g->exec, g->ola, &k3));
-            if (g->kcopy)
-                ST_CUDA_OK(cudaGraphExecMemcpyNodeSetParams1D(g->exec, g->kcopy, g->knobs_dst, knobs, g->knobs_bytes, cudaMemcpyDeviceToDevice));
+            ok = ok && cudaGraphExecKernelNodeSetParams(g->exec, g->ola, &k3) == cudaSuccess;
+            if (ok && g->kcopy)
+                ok = cudaGraphExecMemcpyNodeSetParams1D(g->exec, g->kcopy, g->knobs_dst, knobs, g->knobs_bytes, cudaMemcpyDeviceToDevice) == cudaSuccess;
         }
-        ST_CUDA_OK(cudaGraphLaunch(g->exec, s));
-        h->launches += g->launches;
-        ++h->graph_replays;
-        return 0;
+        if (ok) ok = cudaGraphLaunch(g->exec, s) == cudaSuccess;
+        if (ok) {
+            h->launches += g->launches;
+            ++h->graph_replays;
+            return 0;
+        }
+        // a refused update or launch (nothing of this step has run): give the graph up for these buffers, plain launches from here on
+        cudaGetLastError();
+        cudaGraphExecDestroy(g->exec);
+        g->exec = nullptr;
+        g->bad = true;
+        return step_body(h, kind, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, packed, s);
     }
     if (g->bad || g->seen++ < 1)                                // first sight of these buffers (or capture refused earlier): plain launches
         return step_body(h, kind, x, y, knobs, batch, params, grads, exp_avg, exp_avg_sq, sbf, l1_coef, hp, loss, packed, s);
