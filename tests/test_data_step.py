@@ -134,3 +134,11 @@ def test_file_pair_loader_follows_the_reference_conventions(tmp_path):
         dd.read_wav(str(tmp_path / "r.wav"))
     with pytest.raises(RuntimeError, match="no input_"):
         dd.load_file_pairs(str(tmp_path / "nothing"))
+
+
+def test_file_batches_refuses_a_chunk_rerun_it_cannot_do_on_the_device(tmp_path):
+    """target_type != "stream" re-runs the effect per chunk (datasets.py:241-242); only the 4-knob compressor exists as a device
+    kernel, so any other effect is refused up front instead of silently training on stale targets."""
+    from signaltrain_b200 import data, device_data as dd
+    with pytest.raises(NotImplementedError, match="st_compressor_4c"):
+        dd.file_batches(str(tmp_path), data.Denoise(), 8192, 2048, 4, 40, "cuda:0", rerun=True)
